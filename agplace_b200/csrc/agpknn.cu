@@ -1,0 +1,569 @@
+// agpknn.cu -- C ABI (include/agpknn.h) and host orchestration of the sm_100a kernels.
+//
+// HBM layout of one index (one shard, one GPU):
+//   xb      fp32 [cap, d]        raw rows, add order            (difference-form / SIMT paths)
+//   xb_hi   fp32 [cap, d_pad]    rna_tf32(x), d_pad = ceil32(d)  (3xTF32 operand planes, TMA source)
+//   xb_lo   fp32 [cap, d_pad]    rna_tf32(x - hi)
+//   yn      fp32 [cap]           |x|^2, +inf beyond ntotal (masks TMA zero-filled tail rows)
+// cap is a multiple of 256 and grows geometrically.  Scratch (query planes, candidate buffers,
+// partial lists, distance panels) is pooled per index and reused across searches.
+#include "../../include/agpknn.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <new>
+
+#include "launch.h"
+
+using namespace agp;
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            int code__ = (e__ == cudaErrorMemoryAllocation) ? AGP_ENOMEM : AGP_ECUDA;                    \
+            return set_err(code__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                                \
+    } while (0)
+
+#define CKR(expr)                 \
+    do {                          \
+        int r__ = (expr);         \
+        if (r__ != 0) return r__; \
+    } while (0)
+
+#define LAUNCH(expr)              \
+    do {                          \
+        g_launches.fetch_add(1);  \
+        CK(expr);                 \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ index
+struct Buf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct agp_index {
+    int d = 0, d_pad = 0, device = 0, mode = 0, num_sms = 0;
+    int64_t ntotal = 0, cap = 0, id_base = 0;
+    float *xb = nullptr, *xb_hi = nullptr, *xb_lo = nullptr, *yn = nullptr;
+    bool planes = false;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    Buf q_raw, q_hi, q_lo, qn, cand, partial, panel, d_out, i_out;
+    bool profile = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double prof_ms = 0.0;
+    int64_t prof_launches = 0;
+};
+
+static int ensure(Buf& b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return 0;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.bytes = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    CK(cudaMalloc(&b.p, want));
+    b.bytes = want;
+    return 0;
+}
+
+static int free_buf(Buf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+    return 0;
+}
+
+static inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------ TMA maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn* out) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (!p || qres != cudaDriverEntryPointSuccess) return set_err(AGP_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    *out = fn;
+    return 0;
+}
+
+// fp32 [rows, d_pad] row-major plane -> boxes of (32 floats x box_rows), 128B swizzle, zero OOB fill
+static int make_plane_map(CUtensorMap* m, const float* base, int64_t rows, int d_pad, int box_rows) {
+    EncodeTiledFn fn;
+    CKR(get_encode_fn(&fn));
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(d_pad), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(d_pad) * sizeof(float)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(TC_BK), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(AGP_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ storage
+static int grow(agp_index* ix, int64_t need) {
+    if (need <= ix->cap) return 0;
+    int64_t ncap = std::max<int64_t>(need, ix->cap + ix->cap / 2);
+    ncap = round_up(std::max<int64_t>(ncap, 256), 256);
+    float *nxb = nullptr, *nhi = nullptr, *nlo = nullptr, *nyn = nullptr;
+    CK(cudaMalloc(&nxb, static_cast<size_t>(ncap) * ix->d * sizeof(float)));
+    CK(cudaMalloc(&nyn, static_cast<size_t>(ncap) * sizeof(float)));
+    if (ix->planes) {
+        CK(cudaMalloc(&nhi, static_cast<size_t>(ncap) * ix->d_pad * sizeof(float)));
+        CK(cudaMalloc(&nlo, static_cast<size_t>(ncap) * ix->d_pad * sizeof(float)));
+    }
+    LAUNCH(launch_fill_f32(nyn, ncap, HUGE_VALF, ix->stream));
+    if (ix->ntotal > 0) {
+        CK(cudaMemcpyAsync(nxb, ix->xb, static_cast<size_t>(ix->ntotal) * ix->d * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+        CK(cudaMemcpyAsync(nyn, ix->yn, static_cast<size_t>(ix->ntotal) * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+        if (ix->planes) {
+            CK(cudaMemcpyAsync(nhi, ix->xb_hi, static_cast<size_t>(ix->ntotal) * ix->d_pad * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+            CK(cudaMemcpyAsync(nlo, ix->xb_lo, static_cast<size_t>(ix->ntotal) * ix->d_pad * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(ix->stream));
+    if (ix->xb) cudaFree(ix->xb);
+    if (ix->yn) cudaFree(ix->yn);
+    if (ix->xb_hi) cudaFree(ix->xb_hi);
+    if (ix->xb_lo) cudaFree(ix->xb_lo);
+    ix->xb = nxb; ix->yn = nyn; ix->xb_hi = nhi; ix->xb_lo = nlo;
+    ix->cap = ncap;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ dispatch helpers
+#define DISPATCH_E(k, fn, ...)                                                                   \
+    [&]() -> int {                                                                               \
+        switch (sel_regs_for_k(k)) {                                                             \
+            case 2: LAUNCH(fn<2>(__VA_ARGS__)); return 0;                                        \
+            case 4: LAUNCH(fn<4>(__VA_ARGS__)); return 0;                                        \
+            case 8: LAUNCH(fn<8>(__VA_ARGS__)); return 0;                                        \
+            case 16: LAUNCH(fn<16>(__VA_ARGS__)); return 0;                                      \
+            default: return set_err(AGP_EINVAL, "k=%d needs more than 512 candidate slots", k);  \
+        }                                                                                        \
+    }()
+
+#define DISPATCH_E32(k, fn, ...)                                                                 \
+    [&]() -> int {                                                                               \
+        switch (sel_regs_for_k(k)) {                                                             \
+            case 2: LAUNCH(fn<2>(__VA_ARGS__)); return 0;                                        \
+            case 4: LAUNCH(fn<4>(__VA_ARGS__)); return 0;                                        \
+            case 8: LAUNCH(fn<8>(__VA_ARGS__)); return 0;                                        \
+            case 16: LAUNCH(fn<16>(__VA_ARGS__)); return 0;                                      \
+            case 32: LAUNCH(fn<32>(__VA_ARGS__)); return 0;                                      \
+            default: return set_err(AGP_EINVAL, "k=%d exceeds AGP_MAX_K=%d", k, AGP_MAX_K);      \
+        }                                                                                        \
+    }()
+
+struct ProfScope {
+    agp_index* ix;
+    explicit ProfScope(agp_index* i) : ix(i) {
+        if (ix->profile) cudaEventRecord(ix->ev0, ix->stream);
+    }
+    void stop() {
+        if (ix->profile) {
+            cudaEventRecord(ix->ev1, ix->stream);
+            cudaEventSynchronize(ix->ev1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ix->ev0, ix->ev1);
+            ix->prof_ms += ms;
+            ix->prof_launches += 1;
+        }
+    }
+};
+
+// choose the number of database splits: minimise waves * tiles-per-item (+ per-item overhead)
+static int choose_splits(int n_qtiles, int n_dbtiles, int num_sms) {
+    int best = 1;
+    double best_cost = 1e300;
+    const int max_s = std::min(n_dbtiles, 64);
+    for (int s = 1; s <= max_s; ++s) {
+        const int64_t items = static_cast<int64_t>(n_qtiles) * s;
+        const int64_t waves = (items + num_sms - 1) / num_sms;
+        const int tiles = (n_dbtiles + s - 1) / s;
+        const double cost = static_cast<double>(waves) * (tiles + 0.75);   // ~0.75 tile of fill/drain/emit per item
+        if (cost < best_cost * 0.999) {
+            best_cost = cost;
+            best = s;
+        }
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------ search paths
+// every path writes D/I (device) for queries [q0, q0+nqc)
+
+static int search_empty(agp_index* ix, int64_t nq, int k, float* D, int64_t* I) {
+    // no database rows: emit padding through the merge kernel with zero lists
+    return DISPATCH_E32(k, launch_merge_keys, static_cast<const uint64_t*>(nullptr), nq, 0, k, ix->id_base, D, I, ix->stream);
+}
+
+static int select_and_merge(agp_index* ix, const float* panel, int64_t ld, int nqp, int k, float* D, int64_t* I) {
+    const int64_t n = ix->ntotal;
+    int n_chunks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 2047) / 2048, (ix->num_sms * 16 + nqp - 1) / nqp)));
+    CKR(ensure(ix->partial, static_cast<size_t>(nqp) * n_chunks * k * sizeof(uint64_t)));
+    CKR(DISPATCH_E32(k, launch_select_rows, panel, ld, n, k, nqp, n_chunks, static_cast<uint64_t*>(ix->partial.p), ix->stream));
+    CKR(DISPATCH_E32(k, launch_merge_keys, static_cast<const uint64_t*>(ix->partial.p), static_cast<int64_t>(nqp), n_chunks, k,
+                     ix->id_base, D, I, ix->stream));
+    return 0;
+}
+
+static int search_diff(agp_index* ix, const float* xq_dev, int64_t nq, int k, float* D, int64_t* I) {
+    const int64_t n = ix->ntotal;
+    const int64_t ld = round_up(n, 32);
+    const int max_group = std::max(1, std::min<int>(kMaxSmallNq - 1, static_cast<int>(96 * 1024 / (sizeof(float) * ix->d))));
+    CKR(ensure(ix->panel, static_cast<size_t>(max_group) * ld * sizeof(float)));
+    for (int64_t q0 = 0; q0 < nq; q0 += max_group) {
+        const int g = static_cast<int>(std::min<int64_t>(max_group, nq - q0));
+        ProfScope prof(ix);
+        LAUNCH(launch_diff_small(xq_dev + q0 * ix->d, g, ix->xb, n, ix->d, static_cast<float*>(ix->panel.p), ld, ix->num_sms, ix->stream));
+        prof.stop();
+        CKR(select_and_merge(ix, static_cast<const float*>(ix->panel.p), ld, g, k, D + q0 * k, I + q0 * k));
+    }
+    return 0;
+}
+
+static int search_simt(agp_index* ix, const float* xq_dev, int64_t nq, int k, float* D, int64_t* I) {
+    const int64_t n = ix->ntotal;
+    const int64_t ld = round_up(n, 32);
+    const int64_t max_rows = std::max<int64_t>(1, std::min<int64_t>(nq, (static_cast<int64_t>(128) << 20) / ld));
+    CKR(ensure(ix->panel, static_cast<size_t>(max_rows) * ld * sizeof(float)));
+    CKR(ensure(ix->qn, static_cast<size_t>(nq) * sizeof(float)));
+    LAUNCH(launch_prep_rows(false, xq_dev, nq, ix->d, ix->d_pad, static_cast<float*>(ix->qn.p), nullptr, nullptr, ix->num_sms * 32, ix->stream));
+    for (int64_t q0 = 0; q0 < nq; q0 += max_rows) {
+        const int rows = static_cast<int>(std::min<int64_t>(max_rows, nq - q0));
+        ProfScope prof(ix);
+        LAUNCH(launch_dist_simt(xq_dev + q0 * ix->d, static_cast<const float*>(ix->qn.p) + q0, rows, ix->xb, ix->yn, n, ix->d,
+                                static_cast<float*>(ix->panel.p), ld, ix->stream));
+        prof.stop();
+        CKR(select_and_merge(ix, static_cast<const float*>(ix->panel.p), ld, rows, k, D + q0 * k, I + q0 * k));
+    }
+    return 0;
+}
+
+static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, float* D, int64_t* I) {
+    const int64_t n = ix->ntotal;
+    const int E = sel_regs_for_k(k);
+    if (E > 16) return search_simt(ix, xq_dev, nq, k, D, I);   // fused epilogue holds <= 512 candidates per query
+    const int n_dbtiles = static_cast<int>((n + TC_BN - 1) / TC_BN);
+    const int64_t max_chunk = 65536;
+    CUtensorMap m_bhi, m_blo;
+    CKR(make_plane_map(&m_bhi, ix->xb_hi, n, ix->d_pad, TC_BN));
+    CKR(make_plane_map(&m_blo, ix->xb_lo, n, ix->d_pad, TC_BN));
+    for (int64_t q0 = 0; q0 < nq; q0 += max_chunk) {
+        const int nqc = static_cast<int>(std::min<int64_t>(max_chunk, nq - q0));
+        CKR(ensure(ix->q_hi, static_cast<size_t>(nqc) * ix->d_pad * sizeof(float)));
+        CKR(ensure(ix->q_lo, static_cast<size_t>(nqc) * ix->d_pad * sizeof(float)));
+        CKR(ensure(ix->qn, static_cast<size_t>(nqc) * sizeof(float)));
+        LAUNCH(launch_prep_rows(true, xq_dev + q0 * ix->d, nqc, ix->d, ix->d_pad, static_cast<float*>(ix->qn.p),
+                                static_cast<float*>(ix->q_hi.p), static_cast<float*>(ix->q_lo.p), ix->num_sms * 32, ix->stream));
+        CUtensorMap m_qhi, m_qlo;
+        CKR(make_plane_map(&m_qhi, static_cast<float*>(ix->q_hi.p), nqc, ix->d_pad, TC_BM));
+        CKR(make_plane_map(&m_qlo, static_cast<float*>(ix->q_lo.p), nqc, ix->d_pad, TC_BM));
+        TcParams p;
+        p.nq = nqc;
+        p.d_pad = ix->d_pad;
+        p.k = k;
+        p.n_qtiles = (nqc + TC_BM - 1) / TC_BM;
+        p.n_dbtiles = n_dbtiles;
+        p.n_splits = choose_splits(p.n_qtiles, n_dbtiles, ix->num_sms);
+        const int n_items = p.n_qtiles * p.n_splits;
+        const int grid = std::min(n_items, ix->num_sms);
+        CKR(ensure(ix->cand, static_cast<size_t>(grid) * TC_BM * 32 * E * sizeof(uint64_t)));
+        CKR(ensure(ix->partial, static_cast<size_t>(nqc) * p.n_splits * k * sizeof(uint64_t)));
+        p.qn = static_cast<const float*>(ix->qn.p);
+        p.yn = ix->yn;
+        p.cand = static_cast<uint64_t*>(ix->cand.p);
+        p.partial = static_cast<uint64_t*>(ix->partial.p);
+        ProfScope prof(ix);
+        CKR(DISPATCH_E(k, launch_knn_tc, m_qhi, m_qlo, m_bhi, m_blo, p, grid, ix->stream));
+        prof.stop();
+        CKR(DISPATCH_E32(k, launch_merge_keys, static_cast<const uint64_t*>(ix->partial.p), static_cast<int64_t>(nqc), p.n_splits, k,
+                         ix->id_base, D + q0 * k, I + q0 * k, ix->stream));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* agp_last_error(void) { return g_err; }
+const char* agp_version(void) { return "agpknn 0.1 (sm_100a)"; }
+int64_t agp_kernel_launches(void) { return g_launches.load(); }
+
+int agp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int agp_index_create(int d, int device, int precision_mode, agp_index** out) {
+    if (!out) return set_err(AGP_EINVAL, "out is null");
+    *out = nullptr;
+    if (d <= 0) return set_err(AGP_EINVAL, "d must be positive, got %d", d);
+    if (precision_mode < 0 || precision_mode > 3) return set_err(AGP_EINVAL, "unknown precision_mode %d", precision_mode);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_err(AGP_ENODEV, "no CUDA device visible: agpknn has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return set_err(AGP_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return set_err(AGP_ENODEV, "device %d is sm_%d%d; agpknn is built for sm_100a only", device, prop.major, prop.minor);
+    CK(cudaSetDevice(device));
+    agp_index* ix = new (std::nothrow) agp_index();
+    if (!ix) return set_err(AGP_ENOMEM, "host allocation failed");
+    ix->d = d;
+    ix->d_pad = static_cast<int>(round_up(d, TC_BK));
+    ix->device = device;
+    ix->mode = precision_mode;
+    ix->num_sms = prop.multiProcessorCount;
+    ix->planes = (precision_mode == AGP_PRECISION_AUTO || precision_mode == AGP_PRECISION_3XTF32);
+    cudaError_t e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ix->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ix->ev1);
+    if (e != cudaSuccess) {
+        delete ix;
+        return set_err(AGP_ECUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
+    }
+    ix->stream = ix->own_stream;
+    *out = ix;
+    return 0;
+}
+
+void agp_index_free(agp_index* ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    if (ix->xb) cudaFree(ix->xb);
+    if (ix->xb_hi) cudaFree(ix->xb_hi);
+    if (ix->xb_lo) cudaFree(ix->xb_lo);
+    if (ix->yn) cudaFree(ix->yn);
+    free_buf(ix->q_raw); free_buf(ix->q_hi); free_buf(ix->q_lo); free_buf(ix->qn); free_buf(ix->cand);
+    free_buf(ix->partial); free_buf(ix->panel); free_buf(ix->d_out); free_buf(ix->i_out);
+    if (ix->ev0) cudaEventDestroy(ix->ev0);
+    if (ix->ev1) cudaEventDestroy(ix->ev1);
+    if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
+    delete ix;
+}
+
+int64_t agp_index_ntotal(const agp_index* ix) { return ix ? ix->ntotal : -1; }
+int agp_index_dim(const agp_index* ix) { return ix ? ix->d : -1; }
+
+int agp_index_set_stream(agp_index* ix, void* s) {
+    if (!ix) return set_err(AGP_EINVAL, "index is null");
+    ix->stream = s ? static_cast<cudaStream_t>(s) : ix->own_stream;
+    return 0;
+}
+
+int agp_index_set_id_base(agp_index* ix, int64_t b) {
+    if (!ix) return set_err(AGP_EINVAL, "index is null");
+    ix->id_base = b;
+    return 0;
+}
+
+int agp_index_set_profiling(agp_index* ix, int on) {
+    if (!ix) return set_err(AGP_EINVAL, "index is null");
+    ix->profile = on != 0;
+    return 0;
+}
+
+int agp_index_get_profile(agp_index* ix, double* ms, int64_t* launches, int reset) {
+    if (!ix) return set_err(AGP_EINVAL, "index is null");
+    if (ms) *ms = ix->prof_ms;
+    if (launches) *launches = ix->prof_launches;
+    if (reset) {
+        ix->prof_ms = 0.0;
+        ix->prof_launches = 0;
+    }
+    return 0;
+}
+
+int agp_index_reserve(agp_index* ix, int64_t n) {
+    if (!ix) return set_err(AGP_EINVAL, "index is null");
+    CK(cudaSetDevice(ix->device));
+    return grow(ix, n);
+}
+
+int agp_index_reset(agp_index* ix) {
+    if (!ix) return set_err(AGP_EINVAL, "index is null");
+    CK(cudaSetDevice(ix->device));
+    if (ix->cap > 0) {
+        LAUNCH(launch_fill_f32(ix->yn, ix->cap, HUGE_VALF, ix->stream));
+    }
+    ix->ntotal = 0;
+    return 0;
+}
+
+int agp_index_add(agp_index* ix, int64_t n, const float* x, int mem_kind) {
+    if (!ix) return set_err(AGP_EINVAL, "index is null");
+    if (n < 0) return set_err(AGP_EINVAL, "n must be >= 0");
+    if (n == 0) return 0;
+    if (!x) return set_err(AGP_EINVAL, "x is null");
+    if (ix->ntotal + n > 0x7fffffffLL) return set_err(AGP_EINVAL, "a single shard holds at most 2^31-1 rows");
+    CK(cudaSetDevice(ix->device));
+    CKR(grow(ix, ix->ntotal + n));
+    float* dst = ix->xb + ix->ntotal * ix->d;
+    CK(cudaMemcpyAsync(dst, x, static_cast<size_t>(n) * ix->d * sizeof(float),
+                       mem_kind == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ix->stream));
+    if (ix->planes) {
+        LAUNCH(launch_prep_rows(true, dst, n, ix->d, ix->d_pad, ix->yn + ix->ntotal, ix->xb_hi + ix->ntotal * ix->d_pad,
+                                ix->xb_lo + ix->ntotal * ix->d_pad, ix->num_sms * 32, ix->stream));
+    } else {
+        LAUNCH(launch_prep_rows(false, dst, n, ix->d, ix->d_pad, ix->yn + ix->ntotal, nullptr, nullptr, ix->num_sms * 32, ix->stream));
+    }
+    ix->ntotal += n;
+    if (mem_kind != AGP_MEM_DEVICE) CK(cudaStreamSynchronize(ix->stream));   // caller may reuse x immediately
+    return 0;
+}
+
+int agp_index_search(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, int k, float* D, int64_t* I, int out_mem_kind) {
+    if (!ix) return set_err(AGP_EINVAL, "index is null");
+    if (nq < 0) return set_err(AGP_EINVAL, "nq must be >= 0");
+    if (k <= 0) return set_err(AGP_EINVAL, "k must be positive, got %d", k);
+    if (k > AGP_MAX_K) return set_err(AGP_EINVAL, "k=%d exceeds AGP_MAX_K=%d", k, AGP_MAX_K);
+    if (nq == 0) return 0;
+    if (!x || !D || !I) return set_err(AGP_EINVAL, "x, D and I must be non-null");
+    if (nq > 0x7fffffffLL) return set_err(AGP_EINVAL, "nq too large");
+    CK(cudaSetDevice(ix->device));
+
+    const float* xq_dev = x;
+    if (x_mem_kind != AGP_MEM_DEVICE) {
+        CKR(ensure(ix->q_raw, static_cast<size_t>(nq) * ix->d * sizeof(float)));
+        CK(cudaMemcpyAsync(ix->q_raw.p, x, static_cast<size_t>(nq) * ix->d * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+        xq_dev = static_cast<const float*>(ix->q_raw.p);
+    }
+    float* D_dev = D;
+    int64_t* I_dev = I;
+    if (out_mem_kind != AGP_MEM_DEVICE) {
+        CKR(ensure(ix->d_out, static_cast<size_t>(nq) * k * sizeof(float)));
+        CKR(ensure(ix->i_out, static_cast<size_t>(nq) * k * sizeof(int64_t)));
+        D_dev = static_cast<float*>(ix->d_out.p);
+        I_dev = static_cast<int64_t*>(ix->i_out.p);
+    }
+
+    int rc = 0;
+    if (ix->ntotal == 0) {
+        rc = search_empty(ix, nq, k, D_dev, I_dev);
+    } else {
+        switch (ix->mode) {
+            case AGP_PRECISION_AUTO:
+                rc = (nq < kMaxSmallNq) ? search_diff(ix, xq_dev, nq, k, D_dev, I_dev) : search_tc(ix, xq_dev, nq, k, D_dev, I_dev);
+                break;
+            case AGP_PRECISION_3XTF32: rc = search_tc(ix, xq_dev, nq, k, D_dev, I_dev); break;
+            case AGP_PRECISION_FP32_SIMT: rc = search_simt(ix, xq_dev, nq, k, D_dev, I_dev); break;
+            default: rc = search_diff(ix, xq_dev, nq, k, D_dev, I_dev); break;
+        }
+    }
+    if (rc != 0) return rc;
+    if (out_mem_kind != AGP_MEM_DEVICE) {
+        CK(cudaMemcpyAsync(D, D_dev, static_cast<size_t>(nq) * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+        CK(cudaMemcpyAsync(I, I_dev, static_cast<size_t>(nq) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
+        CK(cudaStreamSynchronize(ix->stream));
+    } else if (x_mem_kind != AGP_MEM_DEVICE) {
+        CK(cudaStreamSynchronize(ix->stream));
+    }
+    return 0;
+}
+
+int agp_merge_topk(int device, void* stream, int64_t nq, int k, int n_lists, const float* D_lists, const int64_t* I_lists,
+                   float* D_out, int64_t* I_out) {
+    if (k <= 0 || k > AGP_MAX_K) return set_err(AGP_EINVAL, "k=%d out of range 1..%d", k, AGP_MAX_K);
+    if (nq < 0 || n_lists < 0) return set_err(AGP_EINVAL, "negative size");
+    if (nq == 0) return 0;
+    if ((n_lists > 0 && (!D_lists || !I_lists)) || !D_out || !I_out) return set_err(AGP_EINVAL, "null pointer");
+    if (static_cast<int64_t>(n_lists) * k > 0x7fffffffLL) return set_err(AGP_EINVAL, "n_lists * k too large");
+    CK(cudaSetDevice(device));
+    return DISPATCH_E32(k, launch_merge_lists, D_lists, I_lists, nq, n_lists, k, D_out, I_out, static_cast<cudaStream_t>(stream));
+}
+
+int agp_recall_at_n(int device, void* stream_v, const int64_t* I, int mem_kind, int64_t nq, int k, const int64_t* pos_offsets,
+                    const int64_t* pos_ids, const int* ns, int n_ns, int64_t* hit_counts) {
+    if (!I || !pos_offsets || !ns || !hit_counts) return set_err(AGP_EINVAL, "null pointer");
+    if (n_ns <= 0 || n_ns > 32) return set_err(AGP_EINVAL, "n_ns must be in 1..32");
+    if (k <= 0 || nq < 0) return set_err(AGP_EINVAL, "bad k or nq");
+    for (int i = 0; i < n_ns; ++i) hit_counts[i] = 0;
+    if (nq == 0) return 0;
+    CK(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+    const bool dev = mem_kind == AGP_MEM_DEVICE;
+    int64_t n_pos = 0;
+    int64_t* d_off = nullptr;
+    int64_t* d_ids = nullptr;
+    int64_t* d_I = nullptr;
+    int* d_ns = nullptr;
+    unsigned long long* d_hits = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() {
+        if (!dev) { cudaFree(d_off); cudaFree(d_ids); cudaFree(d_I); }
+        cudaFree(d_ns);
+        cudaFree(d_hits);
+    };
+#define CKC(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            rc = set_err(AGP_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            cleanup();                                                                              \
+            return rc;                                                                              \
+        }                                                                                           \
+    } while (0)
+    if (dev) {
+        d_off = const_cast<int64_t*>(pos_offsets);
+        d_ids = const_cast<int64_t*>(pos_ids);
+        d_I = const_cast<int64_t*>(I);
+    } else {
+        n_pos = pos_offsets[nq];
+        CKC(cudaMalloc(&d_off, static_cast<size_t>(nq + 1) * sizeof(int64_t)));
+        CKC(cudaMalloc(&d_ids, static_cast<size_t>(std::max<int64_t>(n_pos, 1)) * sizeof(int64_t)));
+        CKC(cudaMalloc(&d_I, static_cast<size_t>(nq) * k * sizeof(int64_t)));
+        CKC(cudaMemcpyAsync(d_off, pos_offsets, static_cast<size_t>(nq + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        if (n_pos > 0) CKC(cudaMemcpyAsync(d_ids, pos_ids, static_cast<size_t>(n_pos) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        CKC(cudaMemcpyAsync(d_I, I, static_cast<size_t>(nq) * k * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    }
+    CKC(cudaMalloc(&d_ns, n_ns * sizeof(int)));
+    CKC(cudaMalloc(&d_hits, n_ns * sizeof(unsigned long long)));
+    CKC(cudaMemcpyAsync(d_ns, ns, n_ns * sizeof(int), cudaMemcpyHostToDevice, st));
+    CKC(cudaMemsetAsync(d_hits, 0, n_ns * sizeof(unsigned long long), st));
+    g_launches.fetch_add(1);
+    CKC(launch_recall(d_I, nq, k, d_off, d_ids, d_ns, n_ns, d_hits, st));
+    unsigned long long h[32];
+    CKC(cudaMemcpyAsync(h, d_hits, n_ns * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CKC(cudaStreamSynchronize(st));
+    for (int i = 0; i < n_ns; ++i) hit_counts[i] = static_cast<int64_t>(h[i]);
+    cleanup();
+#undef CKC
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+// knn_tc.cuh -- K2 + K3: tcgen05 distance tiles with the top-k selection fused into the epilogue.
+//
+// One CTA (192 threads, 1 per SM) works through a static list of items; an item is one tile of
+// 128 queries against one contiguous range ("split") of 256-row database tiles.
+//
+//   warp 0    TMA producer : per 32-float K chunk loads Q_hi, Q_lo (128 x 128 B) and DB_hi, DB_lo
+//                            (256 x 128 B), 128B-swizzled K-major, into a 2-stage ring (96 KB/stage)
+//   warp 1    MMA issuer   : 3xTF32 -- hi*hi + hi*lo + lo*hi, 4 K-steps of 8 per chunk, fp32
+//                            accumulators in TMEM (128 lanes x 256 columns, double buffered = all 512)
+//   warps 2-5 epilogue     : tcgen05.ld 32 columns at a time; thread = one query (TMEM lane);
+//                            dis = max(0, (|q|^2 + |y|^2) - 2 ip)  (faiss exhaustive_L2sqr_blas formula);
+//                            compare against the query's running k-th best; the rare admissions are
+//                            appended to a per-query candidate buffer (L2-resident), which the warp
+//                            compacts with a register bitonic sort when it fills (reservoir select).
+//
+// The nq x N distance matrix never exists in HBM: only [nq, n_splits, k] partial lists leave the SM.
+// Algorithmic work per item tile: 2 * 128 * 256 * d flop (x3 on the tensor pipe).
+#pragma once
+#include "common.cuh"
+#include "sortnet.cuh"
+
+namespace agp {
+
+constexpr int TC_STAGES = 2;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 32 KB
+constexpr int TC_STAGE_BYTES = 2 * (TC_A_BYTES + TC_B_BYTES);
+constexpr int TC_SMEM_BYTES = 1024 + TC_STAGES * TC_STAGE_BYTES + 256;
+constexpr int TC_THREADS = 192;
+
+// Sort lane L's candidate buffer with the whole warp.  final == false: write the k best back and
+// refresh L's threshold; final == true: emit them to `out` (the partial list of L's query).
+template <int E>
+__device__ __forceinline__ void tc_compact(int L, bool final, uint64_t* my_buf, int& cnt, float& thr, int lane, int k,
+                                           uint64_t* out) {
+    uint64_t* buf = reinterpret_cast<uint64_t*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_buf), L));
+    const int n = __shfl_sync(kFull, cnt, L);
+    __syncwarp();
+    uint64_t key[E];
+#pragma unroll
+    for (int j = 0; j < E; ++j) key[j] = (j * 32 + lane < n) ? __ldcg(buf + j * 32 + lane) : kEmptyKey;
+    warp_bitonic_sort<E>(key, lane);
+    uint64_t* dst = final ? out : buf;
+#pragma unroll
+    for (int j = 0; j < E; ++j)
+        if (j * 32 + lane < k) __stcg(dst + j * 32 + lane, key[j]);
+    const float kth = key_dist(warp_get<E>(key, k - 1));
+    if (lane == L) {
+        if (n >= k) thr = kth;
+        cnt = n < k ? n : k;
+    }
+    __syncwarp();
+}
+
+template <int E>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
+              const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, const TcParams p) {
+    constexpr int CAP = 32 * E;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* full = bars;                    // [TC_STAGES]  TMA -> MMA
+    uint64_t* empty = bars + TC_STAGES;       // [TC_STAGES]  MMA -> TMA
+    uint64_t* tfull = bars + 2 * TC_STAGES;   // [2]          MMA -> epilogue
+    uint64_t* tempty = tfull + 2;             // [2]          epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_qhi);
+        tma_prefetch_desc(&tm_qlo);
+        tma_prefetch_desc(&tm_bhi);
+        tma_prefetch_desc(&tm_blo);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < TC_STAGES; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], 1);
+            }
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(&tfull[a], 1);
+                mbar_init(&tempty[a], 128);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    const int n_items = p.n_qtiles * p.n_splits;
+    const int num_kc = p.d_pad / TC_BK;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int split = item / p.n_qtiles, qt = item - split * p.n_qtiles;
+                const int t0 = static_cast<int>(static_cast<int64_t>(split) * p.n_dbtiles / p.n_splits);
+                const int t1 = static_cast<int>(static_cast<int64_t>(split + 1) * p.n_dbtiles / p.n_splits);
+                for (int t = t0; t < t1; ++t) {
+                    for (int kc = 0; kc < num_kc; ++kc) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* st = smem + stage * TC_STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
+                        tma_load_2d(st, &tm_qhi, &full[stage], kc * TC_BK, qt * TC_BM);
+                        tma_load_2d(st + TC_A_BYTES, &tm_qlo, &full[stage], kc * TC_BK, qt * TC_BM);
+                        tma_load_2d(st + 2 * TC_A_BYTES, &tm_bhi, &full[stage], kc * TC_BK, t * TC_BN);
+                        tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tm_blo, &full[stage], kc * TC_BK, t * TC_BN);
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            // instruction descriptor: D fp32, A/B tf32, both K-major, N = 256, M = 128
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int split = item / p.n_qtiles;
+                const int t0 = static_cast<int>(static_cast<int64_t>(split) * p.n_dbtiles / p.n_splits);
+                const int t1 = static_cast<int>(static_cast<int64_t>(split + 1) * p.n_dbtiles / p.n_splits);
+                for (int t = t0; t < t1; ++t) {
+                    mbar_wait(&tempty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + acc * TC_BN;
+                    for (int kc = 0; kc < num_kc; ++kc) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
+                        const uint64_t a_hi = make_sw128_desc(sa);
+                        const uint64_t a_lo = make_sw128_desc(sa + TC_A_BYTES);
+                        const uint64_t b_hi = make_sw128_desc(sa + 2 * TC_A_BYTES);
+                        const uint64_t b_lo = make_sw128_desc(sa + 2 * TC_A_BYTES + TC_B_BYTES);
+#pragma unroll
+                        for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                            const uint64_t off = static_cast<uint64_t>(ks * 2);   // 8 tf32 = 32 B = 2 x 16 B
+                            umma_tf32(tmem_d, a_lo + off, b_hi + off, idesc, (kc | ks) != 0 ? 1u : 0u);
+                            umma_tf32(tmem_d, a_hi + off, b_lo + off, idesc, 1u);
+                            umma_tf32(tmem_d, a_hi + off, b_hi + off, idesc, 1u);
+                        }
+                        tc_commit(&empty[stage]);
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit(&tfull[acc]);
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: fused top-k
+        const int g = warp & 3;                     // TMEM lane group this warp may read
+        const int q_local = g * 32 + lane;
+        uint64_t* my_buf = p.cand + (static_cast<size_t>(blockIdx.x) * TC_BM + q_local) * CAP;
+        const float inf = __int_as_float(0x7f800000);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int split = item / p.n_qtiles, qt = item - split * p.n_qtiles;
+            const int t0 = static_cast<int>(static_cast<int64_t>(split) * p.n_dbtiles / p.n_splits);
+            const int t1 = static_cast<int>(static_cast<int64_t>(split + 1) * p.n_dbtiles / p.n_splits);
+            const int q = qt * TC_BM + q_local;
+            const bool valid = q < p.nq;
+            const float qn = valid ? __ldg(p.qn + q) : 0.f;
+            float thr = valid ? inf : -1.f;
+            int cnt = 0;
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int cc = 0; cc < TC_BN / 32; ++cc) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * TC_BN + cc * 32, r);
+                    const int col0 = t * TC_BN + cc * 32;
+                    float y[32];
+                    const float4* y4 = reinterpret_cast<const float4*>(p.yn + col0);
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        const float4 yy = __ldg(y4 + v);
+                        y[4 * v] = yy.x; y[4 * v + 1] = yy.y; y[4 * v + 2] = yy.z; y[4 * v + 3] = yy.w;
+                    }
+                    tmem_ld_wait();
+                    float m = inf;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        float dis = fmaf(-2.f, __uint_as_float(r[c]), qn + y[c]);
+                        dis = fmaxf(dis, 0.f);
+                        y[c] = dis;
+                        m = fminf(m, dis);
+                    }
+                    if (m < thr) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            if (y[c] < thr) {
+                                __stcg(my_buf + cnt, pack_key(y[c], static_cast<uint32_t>(col0 + c)));
+                                ++cnt;
+                            }
+                        }
+                    }
+                    unsigned need = __ballot_sync(kFull, cnt > CAP - 32);
+                    while (need) {
+                        const int L = __ffs(need) - 1;
+                        need &= need - 1;
+                        tc_compact<E>(L, false, my_buf, cnt, thr, lane, p.k, nullptr);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tempty[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+            // item done: emit each query's sorted k best as a partial list
+            const int q_warp0 = qt * TC_BM + g * 32;
+            for (int L = 0; L < 32; ++L) {
+                if (q_warp0 + L >= p.nq) break;
+                uint64_t* out = p.partial + (static_cast<size_t>(q_warp0 + L) * p.n_splits + split) * p.k;
+                tc_compact<E>(L, true, my_buf, cnt, thr, lane, p.k, out);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int E>
+cudaError_t launch_knn_tc(const CUtensorMap& qhi, const CUtensorMap& qlo, const CUtensorMap& bhi, const CUtensorMap& blo,
+                          const TcParams& p, int grid, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    knn_tc_kernel<E><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(qhi, qlo, bhi, blo, p);
+    return cudaGetLastError();
+}
+
+}  // namespace agp

@@ -1,0 +1,60 @@
+// launch.h -- host-visible declarations of the kernel launchers.  Each kernel family lives in its
+// own translation unit (compiled once per register budget E) so the library builds in parallel.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace agp {
+
+constexpr int TC_BM = 128;            // queries per tile (UMMA M, TMEM lanes)
+constexpr int TC_BN = 256;            // database rows per tile (UMMA N, TMEM columns)
+constexpr int TC_BK = 32;             // fp32 per K chunk = one 128-byte swizzle row
+constexpr int kMaxSmallNq = 20;       // faiss distance_compute_blas_threshold
+
+struct TcParams {
+    int nq;
+    int d_pad;
+    int k;
+    int n_qtiles;
+    int n_splits;
+    int n_dbtiles;
+    const float* qn;        // [nq]
+    const float* yn;        // [n_dbtiles * 256], +inf beyond the last database row
+    uint64_t* cand;         // [gridDim.x][128][32*E]
+    uint64_t* partial;      // [nq][n_splits][k]
+};
+
+// smallest power-of-two register count E with 32*E >= 2*k (>= 64 keys)
+inline int sel_regs_for_k(int k) {
+    int e = 2;
+    while (32 * e < 2 * k) e <<= 1;
+    return e;
+}
+
+// E-templated launchers (explicitly instantiated in k_tc.cu / k_select.cu / k_merge.cu)
+template <int E>
+cudaError_t launch_knn_tc(const CUtensorMap& qhi, const CUtensorMap& qlo, const CUtensorMap& bhi, const CUtensorMap& blo,
+                          const TcParams& p, int grid, cudaStream_t st);
+template <int E>
+cudaError_t launch_select_rows(const float* dist, int64_t ld, int64_t n, int k, int nq, int n_chunks, uint64_t* partial,
+                               cudaStream_t st);
+template <int E>
+cudaError_t launch_merge_keys(const uint64_t* partial, int64_t nq, int n_lists, int k, int64_t id_base, float* D, int64_t* I,
+                              cudaStream_t st);
+template <int E>
+cudaError_t launch_merge_lists(const float* Din, const int64_t* Iin, int64_t nq, int n_lists, int k, float* D, int64_t* I,
+                               cudaStream_t st);
+
+// plain launchers (k_misc.cu)
+cudaError_t launch_prep_rows(bool split, const float* x, int64_t n, int d, int d_pad, float* norm, float* hi, float* lo, int max_blocks,
+                             cudaStream_t st);
+cudaError_t launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st);
+cudaError_t launch_diff_small(const float* xq, int nq, const float* xb, int64_t n, int d, float* dist, int64_t ld, int num_sms,
+                              cudaStream_t st);
+cudaError_t launch_dist_simt(const float* xq, const float* qn, int nq, const float* xb, const float* yn, int64_t n, int d, float* dist,
+                             int64_t ld, cudaStream_t st);
+cudaError_t launch_recall(const int64_t* I, int64_t nq, int k, const int64_t* pos_off, const int64_t* pos_ids, const int* ns, int n_ns,
+                          unsigned long long* hits, cudaStream_t st);
+
+}  // namespace agp

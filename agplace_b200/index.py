@@ -1,0 +1,215 @@
+"""Drop-in ``IndexFlatL2`` over libagpknn.so.
+
+Mirrors the SWIG-wrapped ``faiss.IndexFlatL2`` surface that AGPlace uses
+(reference test.py:27-32; datasets/datasets_ws_kitti360.py:976-993;
+datasets/datasets_ws_nuscenes.py:1241-1258; datasets_ws.py:689-706):
+
+    index = IndexFlatL2(d); index.add(xb); D, I = index.search(xq, k); index.reset()
+
+Same coercions as faiss's Python wrapper (``np.ascontiguousarray(x, 'float32')``, ``assert d ==
+self.d``, ``assert k > 0``, optional preallocated ``D=``/``I=``), same return layout (``D`` fp32
+[nq, k] squared L2 ascending, ``I`` int64 [nq, k], padded ``(3.4028235e38, -1)``), and the index
+copies on ``add``.  ``torch.Tensor`` inputs are accepted like ``faiss.contrib.torch_utils``
+(reference anyloc/utilities.py:14,455-456): CUDA tensors stay on the device, run on torch's
+current stream and return CUDA tensors.  All arithmetic happens in the CUDA library; there is no
+CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import _lib
+
+METRIC_L2 = 1
+FLT_MAX = np.float32(3.4028234663852886e38)
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+def default_device() -> int:
+    """AGP_DEVICE, else LOCAL_RANK (one process per GPU under torchrun), else 0."""
+    for key in ("AGP_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(key, "") != "":
+            return int(os.environ[key])
+    return 0
+
+
+class IndexFlatL2:
+    """Exact brute-force squared-L2 index resident in one B200's HBM."""
+
+    def __init__(self, d, device=None, precision=None):
+        self.d = int(d)
+        self.is_trained = True
+        self.metric_type = METRIC_L2
+        self.device = default_device() if device is None else int(device)
+        precision = precision or os.environ.get("AGP_PRECISION", "auto")
+        if precision not in _lib.PRECISION:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISION)}, got {precision!r}")
+        self.precision = precision
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        _lib.check(self._lib.agp_index_create(self.d, self.device, _lib.PRECISION[precision], ctypes.byref(self._h)),
+                   "agp_index_create")
+
+    # ------------------------------------------------------------------ faiss attributes
+    @property
+    def ntotal(self) -> int:
+        return int(self._lib.agp_index_ntotal(self._h))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.agp_index_free(h)
+            except Exception:
+                pass
+            self._h = ctypes.c_void_p()
+
+    # ------------------------------------------------------------------ helpers
+    def _use_torch_stream(self, tensor):
+        import torch
+        if tensor.device.index != self.device:
+            raise ValueError(f"tensor is on cuda:{tensor.device.index} but the index lives on cuda:{self.device}")
+        stream = torch.cuda.current_stream(tensor.device).cuda_stream
+        _lib.check(self._lib.agp_index_set_stream(self._h, ctypes.c_void_p(stream)), "agp_index_set_stream")
+
+    def _use_own_stream(self):
+        _lib.check(self._lib.agp_index_set_stream(self._h, None), "agp_index_set_stream")
+
+    # ------------------------------------------------------------------ add / reset
+    def add(self, x):
+        n, d = x.shape
+        assert d == self.d
+        if _is_torch(x) and x.is_cuda:
+            import torch
+            x = x.detach().to(torch.float32).contiguous()
+            self._use_torch_stream(x)
+            _lib.check(self._lib.agp_index_add(self._h, n, ctypes.c_void_p(x.data_ptr()), _lib.MEM_DEVICE), "agp_index_add")
+            # x may be a temporary: the copy is queued on torch's stream, which orders it before any reuse
+            x.record_stream(__import__("torch").cuda.current_stream(x.device))
+            return
+        if _is_torch(x):
+            x = x.detach().numpy()
+        x = np.ascontiguousarray(x, dtype="float32")
+        self._use_own_stream()
+        _lib.check(self._lib.agp_index_add(self._h, n, ctypes.c_void_p(x.ctypes.data), _lib.MEM_HOST), "agp_index_add")
+
+    def reset(self):
+        _lib.check(self._lib.agp_index_reset(self._h), "agp_index_reset")
+
+    def reserve(self, n):
+        _lib.check(self._lib.agp_index_reserve(self._h, int(n)), "agp_index_reserve")
+
+    def set_id_base(self, base):
+        _lib.check(self._lib.agp_index_set_id_base(self._h, int(base)), "agp_index_set_id_base")
+
+    # ------------------------------------------------------------------ search
+    def search(self, x, k, *, params=None, D=None, I=None):
+        n, d = x.shape
+        assert d == self.d
+        assert k > 0
+        k = int(k)
+        if k > _lib.MAX_K:
+            raise RuntimeError(f"k={k} exceeds the engine's maximum of {_lib.MAX_K}")
+        if _is_torch(x) and x.is_cuda:
+            return self._search_cuda(x, n, k, D, I)
+        as_torch = _is_torch(x)
+        if as_torch:
+            x = x.detach().numpy()
+        x = np.ascontiguousarray(x, dtype="float32")
+        if D is None:
+            Dn = np.empty((n, k), dtype=np.float32)
+        else:
+            Dn = D.numpy() if _is_torch(D) else D
+            assert Dn.shape == (n, k)
+        if I is None:
+            In = np.empty((n, k), dtype=np.int64)
+        else:
+            In = I.numpy() if _is_torch(I) else I
+            assert In.shape == (n, k)
+        direct = (Dn.dtype == np.float32 and Dn.flags.c_contiguous and In.dtype == np.int64 and In.flags.c_contiguous)
+        Dw = Dn if direct else np.empty((n, k), dtype=np.float32)
+        Iw = In if direct else np.empty((n, k), dtype=np.int64)
+        self._use_own_stream()
+        _lib.check(self._lib.agp_index_search(self._h, n, ctypes.c_void_p(x.ctypes.data), _lib.MEM_HOST, k,
+                                              ctypes.c_void_p(Dw.ctypes.data), ctypes.c_void_p(Iw.ctypes.data), _lib.MEM_HOST),
+                   "agp_index_search")
+        if not direct:
+            Dn[...] = Dw
+            In[...] = Iw
+        if as_torch:
+            import torch
+            return (D if D is not None else torch.from_numpy(Dn)), (I if I is not None else torch.from_numpy(In))
+        return (D if D is not None else Dn), (I if I is not None else In)
+
+    def _search_cuda(self, x, n, k, D, I):
+        import torch
+        x = x.detach().to(torch.float32).contiguous()
+        self._use_torch_stream(x)
+        if D is None:
+            D = torch.empty((n, k), dtype=torch.float32, device=x.device)
+        else:
+            assert tuple(D.shape) == (n, k) and D.is_cuda and D.dtype == torch.float32 and D.is_contiguous()
+        if I is None:
+            I = torch.empty((n, k), dtype=torch.int64, device=x.device)
+        else:
+            assert tuple(I.shape) == (n, k) and I.is_cuda and I.dtype == torch.int64 and I.is_contiguous()
+        _lib.check(self._lib.agp_index_search(self._h, n, ctypes.c_void_p(x.data_ptr()), _lib.MEM_DEVICE, k,
+                                              ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()), _lib.MEM_DEVICE),
+                   "agp_index_search")
+        x.record_stream(torch.cuda.current_stream(x.device))
+        return D, I
+
+    # ------------------------------------------------------------------ instrumentation (bench.py)
+    def set_profiling(self, enable: bool):
+        _lib.check(self._lib.agp_index_set_profiling(self._h, int(bool(enable))), "agp_index_set_profiling")
+
+    def get_profile(self, reset=True):
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        _lib.check(self._lib.agp_index_get_profile(self._h, ctypes.byref(ms), ctypes.byref(n), int(reset)), "agp_index_get_profile")
+        return ms.value, n.value
+
+
+def positives_to_csr(positives_per_query):
+    """Reference format (object array / list of unsorted int arrays, test.py:73) -> CSR int64."""
+    lens = np.fromiter((len(p) for p in positives_per_query), dtype=np.int64, count=len(positives_per_query))
+    offsets = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    ids = (np.concatenate([np.asarray(p, dtype=np.int64).reshape(-1) for p in positives_per_query])
+           if len(lens) and offsets[-1] > 0 else np.empty(0, dtype=np.int64))
+    return offsets, np.ascontiguousarray(ids)
+
+
+def recall_hits(predictions, positives_per_query, recall_values, device=None):
+    """K5 on the GPU: hits[i] = #queries whose first correct prediction has rank < recall_values[i].
+
+    ``predictions`` is the ``I`` array of ``search`` (numpy or CUDA tensor).  Mirrors the loop at
+    reference test.py:72-83 (``recalls[i:] += 1; break``)."""
+    lib = _lib.load()
+    device = default_device() if device is None else int(device)
+    ns = np.ascontiguousarray(recall_values, dtype=np.int32)
+    hits = np.zeros(len(ns), dtype=np.int64)
+    offsets, ids = positives_to_csr(positives_per_query)
+    nq, k = predictions.shape
+    if _is_torch(predictions) and predictions.is_cuda:
+        import torch
+        pred = predictions.to(torch.int64).contiguous()
+        d_off = torch.from_numpy(offsets).to(pred.device)
+        d_ids = torch.from_numpy(ids if len(ids) else np.zeros(1, np.int64)).to(pred.device)
+        stream = torch.cuda.current_stream(pred.device).cuda_stream
+        _lib.check(lib.agp_recall_at_n(pred.device.index, ctypes.c_void_p(stream), ctypes.c_void_p(pred.data_ptr()), _lib.MEM_DEVICE,
+                                       nq, k, ctypes.c_void_p(d_off.data_ptr()), ctypes.c_void_p(d_ids.data_ptr()),
+                                       ctypes.c_void_p(ns.ctypes.data), len(ns), ctypes.c_void_p(hits.ctypes.data)), "agp_recall_at_n")
+        return hits
+    if _is_torch(predictions):
+        predictions = predictions.numpy()
+    pred = np.ascontiguousarray(predictions, dtype=np.int64)
+    _lib.check(lib.agp_recall_at_n(device, None, ctypes.c_void_p(pred.ctypes.data), _lib.MEM_HOST, nq, k,
+                                   ctypes.c_void_p(offsets.ctypes.data), ctypes.c_void_p(ids.ctypes.data),
+                                   ctypes.c_void_p(ns.ctypes.data), len(ns), ctypes.c_void_p(hits.ctypes.data)), "agp_recall_at_n")
+    return hits

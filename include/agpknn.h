@@ -1,0 +1,116 @@
+/*
+ * agpknn.h -- C ABI of libagpknn.so: the B200-native exact L2 top-k engine that replaces the
+ * faiss-cpu IndexFlatL2 calls on AGPlace's retrieval hot path.
+ *
+ * Every entry point cites the reference interface it stands in for (paths relative to the
+ * AGPlace reference tree).  The arithmetic the reference reaches through those calls lives in
+ * the third-party `faiss-cpu` wheel (README.md:45); the SWIG methods named below are the ones the
+ * reference binds.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * All functions return 0 on success or a negative AGP_E* code; agp_last_error() returns the
+ * thread-local message of the most recent failure.  There is no CPU fallback: without a usable
+ * sm_100 device every call fails with AGP_ENODEV.
+ *
+ * Threading: calls on different indexes are independent; one index must not be used from two
+ * threads at once (same rule as faiss add()).  Host-output calls return after their stream has
+ * been synchronised; device-output calls are asynchronous on the index's stream.
+ */
+#ifndef AGPKNN_H
+#define AGPKNN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define AGP_API __attribute__((visibility("default")))
+#else
+#define AGP_API
+#endif
+
+typedef struct agp_index agp_index;
+
+enum agp_mem_kind { AGP_MEM_HOST = 0, AGP_MEM_DEVICE = 1 };
+
+enum agp_precision {
+    AGP_PRECISION_AUTO = 0,       /* faiss's own switch: nq < 20 exact difference form, else 3xTF32 tensor cores */
+    AGP_PRECISION_FP32_SIMT = 1,  /* fp32 FMA on CUDA cores, expansion form (reference/cross-check mode)       */
+    AGP_PRECISION_3XTF32 = 2,     /* always the tcgen05 3xTF32 fused kernel                                    */
+    AGP_PRECISION_EXACT_DIFF = 3  /* always the difference form (nq processed in groups of < 20)               */
+};
+
+enum agp_error {
+    AGP_OK = 0,
+    AGP_EINVAL = -1,   /* bad argument (d <= 0, k <= 0, k > AGP_MAX_K, null pointer, ...) */
+    AGP_ENODEV = -2,   /* no CUDA device / not sm_100 */
+    AGP_ECUDA = -3,    /* CUDA runtime or driver error; see agp_last_error() */
+    AGP_ENOMEM = -4
+};
+
+#define AGP_MAX_K 512
+
+/* faiss.IndexFlatL2(d)  -- reference test.py:27, datasets/datasets_ws_kitti360.py:978,987,
+ * datasets/datasets_ws_nuscenes.py:1243,1252, datasets_ws.py:691,700.
+ * `device` is the CUDA ordinal that owns the index (one process per GPU drives one shard). */
+AGP_API int agp_index_create(int d, int device, int precision_mode, agp_index** out);
+
+/* Index destructor (SWIG __del__).  Frees every device allocation, stream and event. */
+AGP_API void agp_index_free(agp_index* idx);
+
+/* IndexFlatL2.add(x)  -- reference test.py:28, kitti360:979,988, nuscenes:1244,1253,
+ * datasets_ws.py:692,701.  x: n x d fp32 row-major (host or device); copied, caller keeps x. */
+AGP_API int agp_index_add(agp_index* idx, int64_t n, const float* x, int mem_kind);
+
+/* IndexFlatL2.search(x, k) -> (D, I)  -- reference test.py:32, kitti360:981,990,
+ * nuscenes:1246,1255, datasets_ws.py:694,703.
+ * x: nq x d fp32 row-major.  D: nq x k fp32 squared L2, ascending.  I: nq x k int64 row ids
+ * (id_base + position in add order).  Missing results are (3.4028235e38, -1), as in faiss. */
+AGP_API int agp_index_search(agp_index* idx, int64_t nq, const float* x, int x_mem_kind, int k, float* D, int64_t* I,
+                     int out_mem_kind);
+
+/* IndexFlatL2.reset()  -- part of the drop-in surface (north_star); drops all vectors, keeps capacity. */
+AGP_API int agp_index_reset(agp_index* idx);
+
+/* IndexFlatL2.ntotal / .d attributes. */
+AGP_API int64_t agp_index_ntotal(const agp_index* idx);
+AGP_API int agp_index_dim(const agp_index* idx);
+
+/* Pre-size device storage for n vectors (faiss has no equivalent; avoids regrowth copies). */
+AGP_API int agp_index_reserve(agp_index* idx, int64_t n);
+
+/* Run this index's work on an existing CUDA stream (cudaStream_t passed as void*), e.g. torch's
+ * current stream; NULL restores the index's own stream. */
+AGP_API int agp_index_set_stream(agp_index* idx, void* cuda_stream);
+
+/* Global id of this shard's first row: I = id_base + local row.  Used by the row-sharded
+ * multi-GPU index (one shard per rank). */
+AGP_API int agp_index_set_id_base(agp_index* idx, int64_t id_base);
+
+/* CUDA-event timing of the dominant distance/select kernel of each search (forces a stream
+ * synchronise per search while enabled).  get returns accumulated milliseconds and launches. */
+AGP_API int agp_index_set_profiling(agp_index* idx, int enable);
+AGP_API int agp_index_get_profile(agp_index* idx, double* kernel_ms, int64_t* kernel_launches, int reset);
+
+/* K4 across shards: merge n_lists per-shard results laid out [n_lists][nq][k] (device memory,
+ * e.g. the output of one NCCL all-gather) into one canonical list per query.  Device in/out. */
+AGP_API int agp_merge_topk(int device, void* cuda_stream, int64_t nq, int k, int n_lists, const float* D_lists,
+                   const int64_t* I_lists, float* D_out, int64_t* I_out);
+
+/* Recall@N  -- reference test.py:72-83.  I: nq x k int64 (host or device).  positives in CSR form:
+ * pos_offsets[nq+1], pos_ids (unsorted, host or device like I).  hit_counts[i] = number of
+ * queries whose first correct prediction has rank < ns[i]  (recall = 100 * hits / nq). */
+AGP_API int agp_recall_at_n(int device, void* cuda_stream, const int64_t* I, int mem_kind, int64_t nq, int k,
+                    const int64_t* pos_offsets, const int64_t* pos_ids, const int* ns, int n_ns, int64_t* hit_counts);
+
+/* Diagnostics. */
+AGP_API const char* agp_last_error(void);
+AGP_API int agp_device_count(void);
+AGP_API int64_t agp_kernel_launches(void);   /* kernels this library has launched in this process */
+AGP_API const char* agp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGPKNN_H */
