@@ -16,6 +16,7 @@
 #include <cstring>
 #include <cmath>
 #include <new>
+#include <vector>
 
 #include "launch.h"
 
@@ -68,7 +69,8 @@ struct agp_index {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     Buf q_raw, q_hi, q_lo, qn, cand, partial, panel, d_out, i_out;
     bool profile = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
     double prof_ms = 0.0;
     int64_t prof_launches = 0;
 };
@@ -181,22 +183,40 @@ static int grow(agp_index* ix, int64_t need) {
         }                                                                                        \
     }()
 
+// Non-blocking kernel timing: an event pair is recorded around the dominant kernel on the index's
+// stream; elapsed times are only read (after a synchronise) in agp_index_get_profile().
 struct ProfScope {
     agp_index* ix;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     explicit ProfScope(agp_index* i) : ix(i) {
-        if (ix->profile) cudaEventRecord(ix->ev0, ix->stream);
+        if (!ix->profile) return;
+        if (ix->ev_used + 2 > ix->ev_pool.size()) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+            ix->ev_pool.push_back(a);
+            ix->ev_pool.push_back(b);
+        }
+        e0 = ix->ev_pool[ix->ev_used];
+        e1 = ix->ev_pool[ix->ev_used + 1];
+        ix->ev_used += 2;
+        cudaEventRecord(e0, ix->stream);
     }
     void stop() {
-        if (ix->profile) {
-            cudaEventRecord(ix->ev1, ix->stream);
-            cudaEventSynchronize(ix->ev1);
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ix->ev0, ix->ev1);
+        if (e1) cudaEventRecord(e1, ix->stream);
+    }
+};
+
+static void prof_collect(agp_index* ix) {
+    for (size_t i = 0; i + 1 < ix->ev_used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ix->ev_pool[i + 1]) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, ix->ev_pool[i], ix->ev_pool[i + 1]) == cudaSuccess) {
             ix->prof_ms += ms;
             ix->prof_launches += 1;
         }
     }
-};
+    ix->ev_used = 0;
+}
 
 // choose the number of database splits: minimise waves * tiles-per-item (+ per-item overhead)
 static int choose_splits(int n_qtiles, int n_dbtiles, int num_sms) {
@@ -350,11 +370,9 @@ int agp_index_create(int d, int device, int precision_mode, agp_index** out) {
     ix->num_sms = prop.multiProcessorCount;
     ix->planes = (precision_mode == AGP_PRECISION_AUTO || precision_mode == AGP_PRECISION_3XTF32);
     cudaError_t e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreate(&ix->ev0);
-    if (e == cudaSuccess) e = cudaEventCreate(&ix->ev1);
     if (e != cudaSuccess) {
         delete ix;
-        return set_err(AGP_ECUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
+        return set_err(AGP_ECUDA, "stream creation failed: %s", cudaGetErrorString(e));
     }
     ix->stream = ix->own_stream;
     *out = ix;
@@ -371,8 +389,7 @@ void agp_index_free(agp_index* ix) {
     if (ix->yn) cudaFree(ix->yn);
     free_buf(ix->q_raw); free_buf(ix->q_hi); free_buf(ix->q_lo); free_buf(ix->qn); free_buf(ix->cand);
     free_buf(ix->partial); free_buf(ix->panel); free_buf(ix->d_out); free_buf(ix->i_out);
-    if (ix->ev0) cudaEventDestroy(ix->ev0);
-    if (ix->ev1) cudaEventDestroy(ix->ev1);
+    for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
     delete ix;
 }
@@ -394,12 +411,15 @@ int agp_index_set_id_base(agp_index* ix, int64_t b) {
 
 int agp_index_set_profiling(agp_index* ix, int on) {
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    if (!on && ix->profile) prof_collect(ix);
     ix->profile = on != 0;
     return 0;
 }
 
 int agp_index_get_profile(agp_index* ix, double* ms, int64_t* launches, int reset) {
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    CK(cudaSetDevice(ix->device));
+    prof_collect(ix);
     if (ms) *ms = ix->prof_ms;
     if (launches) *launches = ix->prof_launches;
     if (reset) {
@@ -496,15 +516,17 @@ int agp_index_search(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, 
     return 0;
 }
 
-int agp_merge_topk(int device, void* stream, int64_t nq, int k, int n_lists, const float* D_lists, const int64_t* I_lists,
-                   float* D_out, int64_t* I_out) {
+int agp_merge_topk(int device, void* stream, int64_t nq, int k, int n_lists, const float* D_lists, int64_t d_list_stride,
+                   const int64_t* I_lists, int64_t i_list_stride, int64_t id_bound, float* D_out, int64_t* I_out) {
     if (k <= 0 || k > AGP_MAX_K) return set_err(AGP_EINVAL, "k=%d out of range 1..%d", k, AGP_MAX_K);
     if (nq < 0 || n_lists < 0) return set_err(AGP_EINVAL, "negative size");
     if (nq == 0) return 0;
     if ((n_lists > 0 && (!D_lists || !I_lists)) || !D_out || !I_out) return set_err(AGP_EINVAL, "null pointer");
     if (static_cast<int64_t>(n_lists) * k > 0x7fffffffLL) return set_err(AGP_EINVAL, "n_lists * k too large");
     CK(cudaSetDevice(device));
-    return DISPATCH_E32(k, launch_merge_lists, D_lists, I_lists, nq, n_lists, k, D_out, I_out, static_cast<cudaStream_t>(stream));
+    const bool by_id = id_bound > 0 && id_bound <= 0x100000000LL;
+    return DISPATCH_E32(k, launch_merge_lists, D_lists, d_list_stride, I_lists, i_list_stride, by_id, nq, n_lists, k, D_out, I_out,
+                        static_cast<cudaStream_t>(stream));
 }
 
 int agp_recall_at_n(int device, void* stream_v, const int64_t* I, int mem_kind, int64_t nq, int k, const int64_t* pos_offsets,

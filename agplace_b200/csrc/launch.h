@@ -43,8 +43,8 @@ template <int E>
 cudaError_t launch_merge_keys(const uint64_t* partial, int64_t nq, int n_lists, int k, int64_t id_base, float* D, int64_t* I,
                               cudaStream_t st);
 template <int E>
-cudaError_t launch_merge_lists(const float* Din, const int64_t* Iin, int64_t nq, int n_lists, int k, float* D, int64_t* I,
-                               cudaStream_t st);
+cudaError_t launch_merge_lists(const float* Din, int64_t d_stride, const int64_t* Iin, int64_t i_stride, bool by_id, int64_t nq,
+                               int n_lists, int k, float* D, int64_t* I, cudaStream_t st);
 
 // plain launchers (k_misc.cu)
 cudaError_t launch_prep_rows(bool split, const float* x, int64_t n, int d, int d_pad, float* norm, float* hi, float* lo, int max_blocks,

@@ -59,18 +59,23 @@ __global__ void __launch_bounds__(128) merge_keys_kernel(const uint64_t* __restr
     }
 }
 
+// lists: D of list g starts at Din + g * d_stride (floats), I at Iin + g * i_stride (int64); each [nq][k].
+// by_id: ids all fit 32 bits -> order ties by (distance, global id), the single-index canonical order;
+// otherwise by (distance, position in list order).
 template <int E>
-__global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restrict__ Din, const int64_t* __restrict__ Iin,
+__global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restrict__ Din, int64_t d_stride,
+                                                          const int64_t* __restrict__ Iin, int64_t i_stride, bool by_id,
                                                           int64_t nq, int n_lists, int k, float* __restrict__ D,
                                                           int64_t* __restrict__ I) {
     const int lane = threadIdx.x & 31;
     const int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
     uint64_t key[E];
-    auto addr = [&](int64_t i) { return (i / k) * nq * k + q * k + (i % k); };   // lists are [G][nq][k]
     warp_select_stream<E>(key, lane, k, static_cast<int64_t>(n_lists) * k, [&](int64_t i) {
-        const int64_t a = addr(i);
-        return Iin[a] < 0 ? kEmptyKey : pack_key(Din[a], static_cast<uint32_t>(i));
+        const int64_t g = i / k, r = i - g * k;
+        const int64_t id = Iin[g * i_stride + q * k + r];
+        if (id < 0) return kEmptyKey;
+        return pack_key(Din[g * d_stride + q * k + r], by_id ? static_cast<uint32_t>(id) : static_cast<uint32_t>(i));
     });
 #pragma unroll
     for (int j = 0; j < E; ++j) {
@@ -78,7 +83,12 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
         if (i < k) {
             const bool empty = key[j] == kEmptyKey;
             D[q * k + i] = empty ? kFltMax : key_dist(key[j]);
-            I[q * k + i] = empty ? -1 : Iin[addr(key_idx(key[j]))];
+            int64_t id = -1;
+            if (!empty) {
+                const uint32_t pl = key_idx(key[j]);
+                id = by_id ? static_cast<int64_t>(pl) : Iin[(pl / k) * i_stride + q * k + (pl % k)];
+            }
+            I[q * k + i] = id;
         }
     }
 }
@@ -92,10 +102,11 @@ cudaError_t launch_merge_keys(const uint64_t* partial, int64_t nq, int n_lists, 
 }
 
 template <int E>
-cudaError_t launch_merge_lists(const float* Din, const int64_t* Iin, int64_t nq, int n_lists, int k, float* D, int64_t* I,
-                               cudaStream_t st) {
+cudaError_t launch_merge_lists(const float* Din, int64_t d_stride, const int64_t* Iin, int64_t i_stride, bool by_id, int64_t nq,
+                               int n_lists, int k, float* D, int64_t* I, cudaStream_t st) {
     constexpr int warps = 4;
-    merge_lists_kernel<E><<<static_cast<unsigned>((nq + warps - 1) / warps), warps * 32, 0, st>>>(Din, Iin, nq, n_lists, k, D, I);
+    merge_lists_kernel<E><<<static_cast<unsigned>((nq + warps - 1) / warps), warps * 32, 0, st>>>(Din, d_stride, Iin, i_stride, by_id, nq,
+                                                                                                  n_lists, k, D, I);
     return cudaGetLastError();
 }
 

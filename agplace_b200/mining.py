@@ -1,0 +1,121 @@
+"""Host-side mirror of the reference's hard-negative mining helpers (call sites B and C).
+
+Restates, with an injectable index class, the faiss-backed pieces of
+``datasets/datasets_ws_kitti360.py`` (identical copies live in ``datasets_ws_nuscenes.py:1241-1258``
+and ``datasets_ws.py:689-706``):
+
+* ``get_best_positive_index``         kitti360:976-983   (fresh index, k = 1 over the hard positives)
+* ``get_hardest_negatives_indexes``   kitti360:985-993   (fresh index, k = negs_num_per_query)
+* the per-query loops of ``compute_triplets_partial[_sep]`` (kitti360:1056-1137) and
+  ``compute_triplets_full`` (kitti360:1022-1049), including the order of ``np.random`` draws, so
+  that the mined ``triplets_global_indexes`` are identical for identical descriptors.
+
+Feature extraction (``compute_cache*``) is the caller's business: ``cache`` is any object whose
+``cache[i]`` / ``cache[index_array]`` returns fp32 rows, e.g. :class:`RAMEfficient2DMatrix`
+(kitti360:1147-1167) or a plain ndarray.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .index import IndexFlatL2
+
+
+class RAMEfficient2DMatrix:
+    """List-of-rows matrix with numpy-style row gathers (reference kitti360:1147-1167)."""
+
+    def __init__(self, shape, dtype=np.float32):
+        self.shape = shape
+        self.dtype = dtype
+        self.matrix = [None] * shape[0]
+
+    def __setitem__(self, indexes, vals):
+        assert vals.shape[1] == self.shape[1], f"{vals.shape[1]} {self.shape[1]}"
+        for i, val in zip(indexes, vals):
+            self.matrix[i] = val.astype(self.dtype, copy=False)
+
+    def __getitem__(self, index):
+        if hasattr(index, "__len__"):
+            return np.array([self.matrix[i] for i in index])
+        return self.matrix[index]
+
+
+class TripletMiner:
+    """The mining state the reference keeps on its ``*TripletsDataset`` objects."""
+
+    def __init__(self, features_dim, database_num, queries_num, hard_positives_per_query, soft_positives_per_query,
+                 negs_num_per_query=10, neg_samples_num=1000, index_cls=None):
+        self.features_dim = int(features_dim)
+        self.database_num = int(database_num)
+        self.queries_num = int(queries_num)
+        self.hard_positives_per_query = hard_positives_per_query
+        self.soft_positives_per_query = soft_positives_per_query
+        self.negs_num_per_query = int(negs_num_per_query)
+        self.neg_samples_num = int(neg_samples_num)
+        self.index_cls = index_cls or IndexFlatL2
+        # compute_triplets_full keeps the previous hardest negatives per query (reference neg_cache)
+        self.neg_cache = [np.empty((0,), dtype=np.int32) for _ in range(self.queries_num)]
+        self.triplets_global_indexes = None
+
+    # ---- kitti360:965-974
+    def get_query_features(self, query_index, cache):
+        query_features = cache[query_index + self.database_num]
+        if query_features is None:
+            raise RuntimeError(f"For query with index {query_index} features have not been computed!\n"
+                               "There might be some bug with caching")
+        return query_features
+
+    # ---- kitti360:976-983
+    def get_best_positive_index(self, query_index, cache, query_features):
+        positives_features = cache[self.hard_positives_per_query[query_index]]
+        faiss_index = self.index_cls(self.features_dim)
+        faiss_index.add(positives_features)
+        # Search the best positive (within 10 meters AND nearest in features space)
+        _, best_positive_num = faiss_index.search(query_features.reshape(1, -1), 1)
+        best_positive_index = self.hard_positives_per_query[query_index][best_positive_num[0]].item()
+        return best_positive_index
+
+    # ---- kitti360:985-993
+    def get_hardest_negatives_indexes(self, cache, query_features, neg_samples):
+        neg_features = cache[neg_samples]
+        faiss_index = self.index_cls(self.features_dim)
+        faiss_index.add(neg_features)
+        # Search the 10 nearest negatives (further than 25 meters and nearest in features space)
+        _, neg_nums = faiss_index.search(query_features.reshape(1, -1), self.negs_num_per_query)
+        neg_nums = neg_nums.reshape(-1)
+        neg_indexes = neg_samples[neg_nums].astype(np.int32)
+        return neg_indexes
+
+    # ---- kitti360:1056-1093 / 1099-1137 (the loop after the cache has been computed)
+    def compute_triplets_partial(self, cache, cache_refresh_rate):
+        """``cache`` must hold every database row in ``sampled_database_indexes`` / the hard positives
+        and every sampled query; computing it is the caller's job.  Returns int64 [refresh, 2 + negs]."""
+        triplets = []
+        sampled_queries_indexes = np.random.choice(self.queries_num, cache_refresh_rate, replace=False)
+        sampled_database_indexes = np.random.choice(self.database_num, self.neg_samples_num, replace=False)
+        for query_index in sampled_queries_indexes:
+            query_features = self.get_query_features(query_index, cache)
+            best_positive_index = self.get_best_positive_index(query_index, cache, query_features)
+            soft_positives = self.soft_positives_per_query[query_index]
+            neg_indexes = np.setdiff1d(sampled_database_indexes, soft_positives, assume_unique=True)
+            neg_indexes = self.get_hardest_negatives_indexes(cache, query_features, neg_indexes)
+            triplets.append((query_index, best_positive_index, *neg_indexes))
+        self.triplets_global_indexes = np.asarray(triplets, dtype=np.int64)
+        return self.triplets_global_indexes
+
+    # ---- kitti360:1022-1049
+    def compute_triplets_full(self, cache, cache_refresh_rate):
+        triplets = []
+        sampled_queries_indexes = np.random.choice(self.queries_num, cache_refresh_rate, replace=False)
+        for query_index in sampled_queries_indexes:
+            query_features = self.get_query_features(query_index, cache)
+            best_positive_index = self.get_best_positive_index(query_index, cache, query_features)
+            neg_indexes = np.random.choice(self.database_num, self.neg_samples_num, replace=False)
+            soft_positives = self.soft_positives_per_query[query_index]
+            neg_indexes = np.setdiff1d(neg_indexes, soft_positives, assume_unique=True)
+            neg_indexes = np.unique(np.concatenate([self.neg_cache[query_index], neg_indexes]))
+            neg_indexes = self.get_hardest_negatives_indexes(cache, query_features, neg_indexes)
+            self.neg_cache[query_index] = neg_indexes
+            triplets.append((query_index, best_positive_index, *neg_indexes))
+        self.triplets_global_indexes = np.asarray(triplets, dtype=np.int64)
+        return self.triplets_global_indexes

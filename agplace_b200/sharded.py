@@ -1,0 +1,202 @@
+"""Row-sharded multi-GPU ``IndexFlatL2``: one process per GPU, one exchange step.
+
+North-star scheme (BASELINE.json): the database is split row-wise across the
+ranks of a ``torch.distributed`` group, every rank searches the (replicated) query batch against
+its shard with the single-GPU engine, the per-shard ``(D fp32, I int64 global)[nq, k]`` lists are
+exchanged with ONE all-gather of a packed byte buffer (NCCL over NVLink on GPUs, gloo in the CPU
+tests), and every rank runs the K4 merge kernel (``agp_merge_topk``) so all ranks return the same
+canonical (distance, id) ordered result as a single index would.
+
+``shard="query"`` is the zero-compute-redundancy alternative for databases that fit one GPU:
+every rank holds the whole database and searches only its slice of the queries; the all-gather
+then just concatenates.
+
+The reference has no multi-GPU retrieval (faiss-cpu, one process: SURVEY.md section 2), so this
+module extends the drop-in surface rather than mirroring a reference file.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .index import IndexFlatL2, _is_torch
+
+
+def _cuda_merge(D_lists, d_stride, I_lists, i_stride, nq, k, n_lists, id_bound):
+    """K4 across shards on the GPU through the C ABI (device tensors in, device tensors out)."""
+    import torch
+    if not D_lists.is_cuda:
+        raise RuntimeError("agplace_b200 has no CPU merge: per-shard lists must be CUDA tensors "
+                           "(tests inject a merge_fn for the gloo/CPU host-logic checks)")
+    dev = D_lists.device
+    D = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    I = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    lib = _lib.load()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(lib.agp_merge_topk(dev.index, ctypes.c_void_p(stream), nq, k, n_lists, ctypes.c_void_p(D_lists.data_ptr()), d_stride,
+                                  ctypes.c_void_p(I_lists.data_ptr()), i_stride, id_bound, ctypes.c_void_p(D.data_ptr()),
+                                  ctypes.c_void_p(I.data_ptr())), "agp_merge_topk")
+    return D, I
+
+
+def shard_bounds(n, world):
+    """Contiguous row ranges: shard g holds [g*ceil(n/G), min((g+1)*ceil(n/G), n))."""
+    per = -(-n // world) if n else 0
+    return [(min(g * per, n), min((g + 1) * per, n)) for g in range(world)]
+
+
+class ShardedIndexFlatL2:
+    def __init__(self, d, group=None, device=None, precision=None, shard="db", index_cls=None, merge_fn=None,
+                 result_device=None):
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
+        if shard not in ("db", "query"):
+            raise ValueError("shard must be 'db' or 'query'")
+        self.d = int(d)
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.shard = shard
+        self.is_trained = True
+        self.metric_type = 1
+        self._ntotal = 0
+        index_cls = index_cls or IndexFlatL2
+        kwargs = {}
+        if index_cls is IndexFlatL2:
+            kwargs = dict(device=device, precision=precision)
+        self.local = index_cls(self.d, **kwargs)
+        self._merge = merge_fn or _cuda_merge
+        self._chunks = []          # (local_start, global_start, count) of this rank's rows, add order
+        self._local_rows = 0
+        self._result_device = result_device   # torch device for the exchange (None: cuda:<index device>)
+
+    @property
+    def ntotal(self):
+        return self._ntotal
+
+    # ------------------------------------------------------------------ add
+    def add(self, x):
+        """Every rank passes the same full chunk; each keeps its contiguous slice of it."""
+        n, d = x.shape
+        assert d == self.d
+        if self.shard == "query":
+            self.local.add(x)
+            self._ntotal += n
+            return
+        lo, hi = shard_bounds(n, self.world)[self.rank]
+        if hi > lo:
+            self.local.add(x[lo:hi])
+            self._record_chunk(self._ntotal + lo, hi - lo)
+        self._ntotal += n
+
+    def _record_chunk(self, global_start, count):
+        if self._chunks and self._chunks[-1][1] + self._chunks[-1][2] == global_start:
+            ls, gs, c = self._chunks[-1]            # contiguous with the previous chunk: extend it
+            self._chunks[-1] = (ls, gs, c + count)
+        else:
+            self._chunks.append((self._local_rows, int(global_start), count))
+        self._local_rows += count
+
+    def add_local(self, x_local, global_start, n_global_added):
+        """Rank-local variant for databases that never exist in one piece (generated per shard):
+        this rank's rows get ids global_start.. ; ``n_global_added`` rows were added job-wide."""
+        assert self.shard == "db"
+        n, d = x_local.shape
+        assert d == self.d
+        if n:
+            self.local.add(x_local)
+            self._record_chunk(int(global_start), n)
+        self._ntotal += int(n_global_added)
+
+    def reset(self):
+        self.local.reset()
+        self._chunks = []
+        self._local_rows = 0
+        self._ntotal = 0
+
+    # ------------------------------------------------------------------ search
+    def _to_global(self, I_local):
+        """local row -> global id through the per-chunk bases (monotone, so tie order is preserved)."""
+        import torch
+        if len(self._chunks) == 1 and hasattr(self.local, "set_id_base"):
+            return I_local      # id_base already applied by the engine
+        starts = torch.tensor([c[0] for c in self._chunks] or [0], dtype=torch.int64, device=I_local.device)
+        gbase = torch.tensor([c[1] - c[0] for c in self._chunks] or [0], dtype=torch.int64, device=I_local.device)
+        which = torch.searchsorted(starts, I_local.clamp(min=0), right=True) - 1
+        return torch.where(I_local < 0, I_local, I_local + gbase[which.clamp(min=0)])
+
+    def search(self, x, k, *, params=None, D=None, I=None):
+        import torch
+        import torch.distributed as dist
+        nq, d = x.shape
+        assert d == self.d
+        assert k > 0
+        k = int(k)
+        as_numpy = not _is_torch(x)
+        if self.shard == "query":
+            lo, hi = shard_bounds(nq, self.world)[self.rank]
+            per = -(-nq // self.world) if nq else 0
+            xs = x[lo:hi]
+        else:
+            xs = x
+        if len(self._chunks) == 1 and hasattr(self.local, "set_id_base") and self.shard == "db":
+            self.local.set_id_base(self._chunks[0][1])
+        if isinstance(self.local, IndexFlatL2) and not (_is_torch(xs) and xs.is_cuda) and xs.shape[0]:
+            # host queries: one H2D copy, then everything (search, exchange, merge) stays on the GPU
+            xh = xs if _is_torch(xs) else torch.from_numpy(np.ascontiguousarray(xs, dtype=np.float32))
+            xs = xh.to(torch.device("cuda", self.local.device), dtype=torch.float32, non_blocking=True)
+        if xs.shape[0]:
+            D_loc, I_loc = self.local.search(xs, k)
+        else:
+            D_loc, I_loc = np.empty((0, k), np.float32), np.empty((0, k), np.int64)
+        if not _is_torch(D_loc):
+            dev = self._result_device
+            if dev is None:
+                dev = torch.device("cuda", self.local.device) if hasattr(self.local, "device") else torch.device("cpu")
+            D_loc = torch.from_numpy(np.ascontiguousarray(D_loc)).to(dev)
+            I_loc = torch.from_numpy(np.ascontiguousarray(I_loc)).to(dev)
+        dev = D_loc.device
+
+        if self.shard == "query":
+            # pad every slice to `per` rows, all-gather, drop the padding
+            rows = per
+        else:
+            I_loc = self._to_global(I_loc)
+            rows = nq
+        d_bytes = (rows * k * 4 + 7) // 8 * 8
+        i_bytes = rows * k * 8
+        send = torch.zeros(d_bytes + i_bytes, dtype=torch.uint8, device=dev)
+        n_loc = D_loc.shape[0] * k
+        send[: n_loc * 4].view(torch.float32).copy_(D_loc.reshape(-1))
+        send[d_bytes: d_bytes + n_loc * 8].view(torch.int64).copy_(I_loc.reshape(-1))
+        recv = torch.empty(self.world * (d_bytes + i_bytes), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(recv, send, group=self.group)        # the single exchange step
+        recv2 = recv.view(self.world, d_bytes + i_bytes)
+
+        if self.shard == "query":
+            bounds = shard_bounds(nq, self.world)
+            Dg = torch.cat([recv2[g, : (b - a) * k * 4].view(torch.float32).view(b - a, k) for g, (a, b) in enumerate(bounds)])
+            Ig = torch.cat([recv2[g, d_bytes: d_bytes + (b - a) * k * 8].view(torch.int64).view(b - a, k)
+                            for g, (a, b) in enumerate(bounds)])
+        else:
+            stride = d_bytes + i_bytes
+            D_lists = recv.view(torch.float32)                            # list g starts at g * stride / 4 floats
+            # int64 view must start 8-byte aligned: d_bytes is a multiple of 8
+            I_lists = recv.view(torch.int64)[d_bytes // 8:]
+            id_bound = self._ntotal
+            Dg, Ig = self._merge(D_lists, stride // 4, I_lists, stride // 8, nq, k, self.world, id_bound)
+
+        if D is not None:
+            (D if _is_torch(D) else torch.from_numpy(D)).copy_(Dg)
+            Dg = D
+        if I is not None:
+            (I if _is_torch(I) else torch.from_numpy(I)).copy_(Ig)
+            Ig = I
+        if as_numpy and D is None:
+            Dg = Dg.cpu().numpy()
+        if as_numpy and I is None:
+            Ig = Ig.cpu().numpy()
+        return Dg, Ig

@@ -93,10 +93,14 @@ AGP_API int agp_index_set_id_base(agp_index* idx, int64_t id_base);
 AGP_API int agp_index_set_profiling(agp_index* idx, int enable);
 AGP_API int agp_index_get_profile(agp_index* idx, double* kernel_ms, int64_t* kernel_launches, int reset);
 
-/* K4 across shards: merge n_lists per-shard results laid out [n_lists][nq][k] (device memory,
- * e.g. the output of one NCCL all-gather) into one canonical list per query.  Device in/out. */
+/* K4 across shards: merge n_lists per-shard results (device memory, e.g. the output of one NCCL
+ * all-gather) into one canonical list per query.  List g holds D at D_lists + g * d_list_stride
+ * (floats) and I at I_lists + g * i_list_stride (int64), each [nq][k].  If every id is below
+ * id_bound <= 2^32 ties are ordered by (distance, id) exactly like a single index; pass 0 to
+ * order ties by list position instead.  Device in/out, asynchronous on cuda_stream. */
 AGP_API int agp_merge_topk(int device, void* cuda_stream, int64_t nq, int k, int n_lists, const float* D_lists,
-                   const int64_t* I_lists, float* D_out, int64_t* I_out);
+                           int64_t d_list_stride, const int64_t* I_lists, int64_t i_list_stride, int64_t id_bound,
+                           float* D_out, int64_t* I_out);
 
 /* Recall@N  -- reference test.py:72-83.  I: nq x k int64 (host or device).  positives in CSR form:
  * pos_offsets[nq+1], pos_ids (unsorted, host or device like I).  hit_counts[i] = number of
