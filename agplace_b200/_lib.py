@@ -26,7 +26,7 @@ SIGNATURES = {
     "agp_index_ntotal": (c_int64, [c_void_p]),
     "agp_index_dim": (c_int, [c_void_p]),
     "agp_index_reserve": (c_int, [c_void_p, c_int64]),
-    "agp_index_set_stream": (c_int, [c_void_p, c_void_p]),
+    "agp_index_set_stream": (c_int, [c_void_p, c_void_p, c_int]),
     "agp_index_set_id_base": (c_int, [c_void_p, c_int64]),
     "agp_index_set_profiling": (c_int, [c_void_p, c_int]),
     "agp_index_get_profile": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), c_int]),

@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <new>
@@ -67,8 +68,9 @@ struct agp_index {
     float *xb = nullptr, *xb_hi = nullptr, *xb_lo = nullptr, *yn = nullptr;
     bool planes = false;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    Buf q_raw, q_hi, q_lo, qn, cand, partial, panel, d_out, i_out;
+    Buf q_raw, q_hi, q_lo, qn, cand, partial, panel, d_out, i_out, gthr, cand_d, cand_i;
     bool profile = false;
+    cudaEvent_t ev_order = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     double prof_ms = 0.0;
@@ -113,17 +115,18 @@ static int get_encode_fn(EncodeTiledFn* out) {
     return 0;
 }
 
-// fp32 [rows, d_pad] row-major plane -> boxes of (32 floats x box_rows), 128B swizzle, zero OOB fill
-static int make_plane_map(CUtensorMap* m, const float* base, int64_t rows, int d_pad, int box_rows) {
+// fp32 [rows, d_pad] row-major plane -> boxes of (bk floats x box_rows); the swizzle span equals the
+// box row (bk = 32: 128 B, bk = 16: 64 B); out-of-bounds rows are zero filled
+static int make_plane_map(CUtensorMap* m, const float* base, int64_t rows, int d_pad, int box_rows, int bk) {
     EncodeTiledFn fn;
     CKR(get_encode_fn(&fn));
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(d_pad), static_cast<cuuint64_t>(rows)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(d_pad) * sizeof(float)};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(TC_BK), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(AGP_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
     return 0;
 }
@@ -160,9 +163,17 @@ static int grow(agp_index* ix, int64_t need) {
 }
 
 // ------------------------------------------------------------------------------------------ dispatch helpers
+// register budget of the fused epilogue: 32*E candidate slots with enough slack above k that the
+// reservoir is compacted rarely (slots - 32 - k new admissions per sort); E <= 16
+static int tc_regs_for_k(int k) {
+    int e = 2;
+    while (32 * e < k + k / 2 + 32 && e < 16) e <<= 1;
+    return e;
+}
+
 #define DISPATCH_E(k, fn, ...)                                                                   \
     [&]() -> int {                                                                               \
-        switch (sel_regs_for_k(k)) {                                                             \
+        switch (tc_regs_for_k(k)) {                                                              \
             case 2: LAUNCH(fn<2>(__VA_ARGS__)); return 0;                                        \
             case 4: LAUNCH(fn<4>(__VA_ARGS__)); return 0;                                        \
             case 8: LAUNCH(fn<8>(__VA_ARGS__)); return 0;                                        \
@@ -289,13 +300,23 @@ static int search_simt(agp_index* ix, const float* xq_dev, int64_t nq, int k, fl
 
 static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, float* D, int64_t* I) {
     const int64_t n = ix->ntotal;
-    const int E = sel_regs_for_k(k);
-    if (E > 16) return search_simt(ix, xq_dev, nq, k, D, I);   // fused epilogue holds <= 512 candidates per query
+    if (k > 256) return search_simt(ix, xq_dev, nq, k, D, I);   // fused epilogue holds <= 512 candidates per query
+    const int E = tc_regs_for_k(k);
     const int n_dbtiles = static_cast<int>((n + TC_BN - 1) / TC_BN);
     const int64_t max_chunk = 65536;
+    // development knobs (not part of the ABI): K-chunk width and a TMA-only bandwidth probe
+    const char* env_bk = getenv("AGP_TC_BK");
+    const int bk = (env_bk && atoi(env_bk) == 16) ? 16 : 32;
+    const char* env_skip = getenv("AGP_TC_SKIP_MMA");
+    const int skip_mma = (env_skip && atoi(env_skip) != 0) ? 1 : 0;
+    // exact re-rank (default on): the tensor cores select the k candidates (3xTF32, expansion form),
+    // then their distances are recomputed in the fp32 difference form and re-sorted
+    const char* env_rr = getenv("AGP_TC_RERANK");
+    const bool rerank = !(env_rr && atoi(env_rr) == 0);
+    const int kc = k;
     CUtensorMap m_bhi, m_blo;
-    CKR(make_plane_map(&m_bhi, ix->xb_hi, n, ix->d_pad, TC_BN));
-    CKR(make_plane_map(&m_blo, ix->xb_lo, n, ix->d_pad, TC_BN));
+    CKR(make_plane_map(&m_bhi, ix->xb_hi, n, ix->d_pad, TC_BN, bk));
+    CKR(make_plane_map(&m_blo, ix->xb_lo, n, ix->d_pad, TC_BN, bk));
     for (int64_t q0 = 0; q0 < nq; q0 += max_chunk) {
         const int nqc = static_cast<int>(std::min<int64_t>(max_chunk, nq - q0));
         CKR(ensure(ix->q_hi, static_cast<size_t>(nqc) * ix->d_pad * sizeof(float)));
@@ -304,28 +325,48 @@ static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, floa
         LAUNCH(launch_prep_rows(true, xq_dev + q0 * ix->d, nqc, ix->d, ix->d_pad, static_cast<float*>(ix->qn.p),
                                 static_cast<float*>(ix->q_hi.p), static_cast<float*>(ix->q_lo.p), ix->num_sms * 32, ix->stream));
         CUtensorMap m_qhi, m_qlo;
-        CKR(make_plane_map(&m_qhi, static_cast<float*>(ix->q_hi.p), nqc, ix->d_pad, TC_BM));
-        CKR(make_plane_map(&m_qlo, static_cast<float*>(ix->q_lo.p), nqc, ix->d_pad, TC_BM));
+        CKR(make_plane_map(&m_qhi, static_cast<float*>(ix->q_hi.p), nqc, ix->d_pad, TC_BM, bk));
+        CKR(make_plane_map(&m_qlo, static_cast<float*>(ix->q_lo.p), nqc, ix->d_pad, TC_BM, bk));
         TcParams p;
+        p.bk = bk;
+        p.debug_skip_mma = skip_mma;
         p.nq = nqc;
         p.d_pad = ix->d_pad;
-        p.k = k;
+        p.k = kc;
         p.n_qtiles = (nqc + TC_BM - 1) / TC_BM;
         p.n_dbtiles = n_dbtiles;
         p.n_splits = choose_splits(p.n_qtiles, n_dbtiles, ix->num_sms);
         const int n_items = p.n_qtiles * p.n_splits;
         const int grid = std::min(n_items, ix->num_sms);
-        CKR(ensure(ix->cand, static_cast<size_t>(grid) * TC_BM * 32 * E * sizeof(uint64_t)));
-        CKR(ensure(ix->partial, static_cast<size_t>(nqc) * p.n_splits * k * sizeof(uint64_t)));
+        const int slots = 32 * E;
+        CKR(ensure(ix->cand, static_cast<size_t>(nqc) * p.n_splits * sizeof(int)));
+        CKR(ensure(ix->partial, static_cast<size_t>(nqc) * p.n_splits * slots * sizeof(uint64_t)));
         p.qn = static_cast<const float*>(ix->qn.p);
         p.yn = ix->yn;
-        p.cand = static_cast<uint64_t*>(ix->cand.p);
+        p.pcount = static_cast<int*>(ix->cand.p);
         p.partial = static_cast<uint64_t*>(ix->partial.p);
+        const char* env_share = getenv("AGP_TC_SHARE_BOUND");
+        p.gthr = nullptr;
+        if (!(env_share && atoi(env_share) == 0)) {
+            CKR(ensure(ix->gthr, static_cast<size_t>(nqc) * sizeof(uint32_t)));
+            LAUNCH(launch_fill_f32(static_cast<float*>(ix->gthr.p), nqc, HUGE_VALF, ix->stream));
+            p.gthr = static_cast<uint32_t*>(ix->gthr.p);
+        }
         ProfScope prof(ix);
         CKR(DISPATCH_E(k, launch_knn_tc, m_qhi, m_qlo, m_bhi, m_blo, p, grid, ix->stream));
         prof.stop();
-        CKR(DISPATCH_E32(k, launch_merge_keys, static_cast<const uint64_t*>(ix->partial.p), static_cast<int64_t>(nqc), p.n_splits, k,
-                         ix->id_base, D + q0 * k, I + q0 * k, ix->stream));
+        if (!rerank) {
+            CKR(DISPATCH_E32(k, launch_merge_ragged, static_cast<const uint64_t*>(ix->partial.p), static_cast<const int*>(ix->cand.p), slots,
+                             static_cast<int64_t>(nqc), p.n_splits, k, ix->id_base, D + q0 * k, I + q0 * k, ix->stream));
+        } else {
+            CKR(ensure(ix->cand_d, static_cast<size_t>(nqc) * kc * sizeof(float)));
+            CKR(ensure(ix->cand_i, static_cast<size_t>(nqc) * kc * sizeof(int64_t)));
+            CKR(DISPATCH_E32(kc, launch_merge_ragged, static_cast<const uint64_t*>(ix->partial.p), static_cast<const int*>(ix->cand.p), slots,
+                             static_cast<int64_t>(nqc), p.n_splits, kc, static_cast<int64_t>(0), static_cast<float*>(ix->cand_d.p),
+                             static_cast<int64_t*>(ix->cand_i.p), ix->stream));
+            CKR(DISPATCH_E32(kc, launch_rerank, xq_dev + q0 * ix->d, ix->xb, ix->d, static_cast<const int64_t*>(ix->cand_i.p), kc,
+                             static_cast<int64_t>(nqc), k, ix->id_base, D + q0 * k, I + q0 * k, ix->stream));
+        }
     }
     return 0;
 }
@@ -364,7 +405,7 @@ int agp_index_create(int d, int device, int precision_mode, agp_index** out) {
     agp_index* ix = new (std::nothrow) agp_index();
     if (!ix) return set_err(AGP_ENOMEM, "host allocation failed");
     ix->d = d;
-    ix->d_pad = static_cast<int>(round_up(d, TC_BK));
+    ix->d_pad = static_cast<int>(round_up(d, TC_KPAD));
     ix->device = device;
     ix->mode = precision_mode;
     ix->num_sms = prop.multiProcessorCount;
@@ -388,8 +429,9 @@ void agp_index_free(agp_index* ix) {
     if (ix->xb_lo) cudaFree(ix->xb_lo);
     if (ix->yn) cudaFree(ix->yn);
     free_buf(ix->q_raw); free_buf(ix->q_hi); free_buf(ix->q_lo); free_buf(ix->qn); free_buf(ix->cand);
-    free_buf(ix->partial); free_buf(ix->panel); free_buf(ix->d_out); free_buf(ix->i_out);
+    free_buf(ix->gthr); free_buf(ix->cand_d); free_buf(ix->cand_i); free_buf(ix->partial); free_buf(ix->panel); free_buf(ix->d_out); free_buf(ix->i_out);
     for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
+    if (ix->ev_order) cudaEventDestroy(ix->ev_order);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
     delete ix;
 }
@@ -397,9 +439,19 @@ void agp_index_free(agp_index* ix) {
 int64_t agp_index_ntotal(const agp_index* ix) { return ix ? ix->ntotal : -1; }
 int agp_index_dim(const agp_index* ix) { return ix ? ix->d : -1; }
 
-int agp_index_set_stream(agp_index* ix, void* s) {
+int agp_index_set_stream(agp_index* ix, void* s, int use_own_stream) {
     if (!ix) return set_err(AGP_EINVAL, "index is null");
-    ix->stream = s ? static_cast<cudaStream_t>(s) : ix->own_stream;
+    // a NULL cudaStream_t is the legacy default stream (what torch uses unless told otherwise)
+    cudaStream_t ns = use_own_stream ? ix->own_stream : static_cast<cudaStream_t>(s);
+    if (ns != ix->stream) {
+        // order everything already queued on the old stream (adds, searches that still own the
+        // scratch buffers) before anything the new stream will run
+        CK(cudaSetDevice(ix->device));
+        if (!ix->ev_order) CK(cudaEventCreateWithFlags(&ix->ev_order, cudaEventDisableTiming));
+        CK(cudaEventRecord(ix->ev_order, ix->stream));
+        CK(cudaStreamWaitEvent(ns, ix->ev_order, 0));
+        ix->stream = ns;
+    }
     return 0;
 }
 

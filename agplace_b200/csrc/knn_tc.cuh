@@ -3,17 +3,19 @@
 // One CTA (192 threads, 1 per SM) works through a static list of items; an item is one tile of
 // 128 queries against one contiguous range ("split") of 256-row database tiles.
 //
-//   warp 0    TMA producer : per 32-float K chunk loads Q_hi, Q_lo (128 x 128 B) and DB_hi, DB_lo
-//                            (256 x 128 B), 128B-swizzled K-major, into a 2-stage ring (96 KB/stage)
-//   warp 1    MMA issuer   : 3xTF32 -- hi*hi + hi*lo + lo*hi, 4 K-steps of 8 per chunk, fp32
-//                            accumulators in TMEM (128 lanes x 256 columns, double buffered = all 512)
+//   warp 0    TMA producer : per BK-float K chunk loads Q_hi, Q_lo (128 rows) and DB_hi, DB_lo
+//                            (256 rows), swizzled K-major, into an mbarrier ring
+//                            (BK = 32: 128B swizzle, 2 stages x 96 KB; BK = 16: 64B swizzle, 4 x 48 KB)
+//   warp 1    MMA issuer   : 3xTF32 -- lo*hi + hi*lo + hi*hi, K-steps of 8, fp32 accumulators in
+//                            TMEM (128 lanes x 256 columns, double buffered = all 512 columns)
 //   warps 2-5 epilogue     : tcgen05.ld 32 columns at a time; thread = one query (TMEM lane);
 //                            dis = max(0, (|q|^2 + |y|^2) - 2 ip)  (faiss exhaustive_L2sqr_blas formula);
 //                            compare against the query's running k-th best; the rare admissions are
 //                            appended to a per-query candidate buffer (L2-resident), which the warp
 //                            compacts with a register bitonic sort when it fills (reservoir select).
 //
-// The nq x N distance matrix never exists in HBM: only [nq, n_splits, k] partial lists leave the SM.
+// The nq x N distance matrix never exists in HBM: only the admitted candidates ([nq, n_splits, 32*E]
+// slots, mostly empty once the shared bound has tightened) leave the SM; K4 merges them.
 // Algorithmic work per item tile: 2 * 128 * 256 * d flop (x3 on the tensor pipe).
 #pragma once
 #include "common.cuh"
@@ -21,18 +23,43 @@
 
 namespace agp {
 
-constexpr int TC_STAGES = 2;
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
-constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 32 KB
-constexpr int TC_STAGE_BYTES = 2 * (TC_A_BYTES + TC_B_BYTES);
-constexpr int TC_SMEM_BYTES = 1024 + TC_STAGES * TC_STAGE_BYTES + 256;
+template <int BK>
+struct TcCfg {
+    static constexpr int kStages = (BK == 32) ? 2 : 4;
+    static constexpr int kABytes = TC_BM * BK * 4;
+    static constexpr int kBBytes = TC_BN * BK * 4;
+    static constexpr int kStageBytes = 2 * (kABytes + kBBytes);
+    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
+    // K-major swizzled operand descriptor: rows of BK*4 bytes, 8-row atoms, swizzle span = row size
+    static constexpr uint64_t kSbo = 8 * BK * 4;                       // bytes between 8-row atoms
+    static constexpr uint64_t kLayout = (BK == 32) ? 2 : 4;            // SWIZZLE_128B : SWIZZLE_64B
+};
 constexpr int TC_THREADS = 192;
+
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);   // start address
+    d |= static_cast<uint64_t>(1) << 16;                        // leading byte offset (unused: one swizzle span per row)
+    d |= static_cast<uint64_t>(TcCfg<BK>::kSbo >> 4) << 32;     // stride byte offset between 8-row atoms
+    d |= static_cast<uint64_t>(1) << 46;                        // descriptor version (sm_100)
+    d |= static_cast<uint64_t>(TcCfg<BK>::kLayout) << 61;       // swizzle mode
+    return d;
+}
 
 // Sort lane L's candidate buffer with the whole warp.  final == false: write the k best back and
 // refresh L's threshold; final == true: emit them to `out` (the partial list of L's query).
+// Shared pruning bound: gthr[q] holds (as fp32 bits) the smallest k-th-best distance any CTA has
+// established for query q over ITS split.  k rows at distance <= B exist somewhere, so a row at
+// distance > B can never reach the global top-k; rows at distance == B may still win the index
+// tie-break, hence the admission threshold derived from it is nextup(B) under a strict `<`.
+__device__ __forceinline__ float bound_to_thr(uint32_t bits) {
+    return __uint_as_float(bits >= 0x7f800000u ? 0x7f800000u : bits + 1u);
+}
+
 template <int E>
 __device__ __forceinline__ void tc_compact(int L, bool final, uint64_t* my_buf, int& cnt, float& thr, int lane, int k,
-                                           uint64_t* out) {
+                                           uint64_t* out, uint32_t* my_gthr) {
     uint64_t* buf = reinterpret_cast<uint64_t*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_buf), L));
     const int n = __shfl_sync(kFull, cnt, L);
     __syncwarp();
@@ -46,24 +73,29 @@ __device__ __forceinline__ void tc_compact(int L, bool final, uint64_t* my_buf, 
         if (j * 32 + lane < k) __stcg(dst + j * 32 + lane, key[j]);
     const float kth = key_dist(warp_get<E>(key, k - 1));
     if (lane == L) {
-        if (n >= k) thr = kth;
+        if (n >= k) {
+            thr = fminf(thr, kth);
+            if (my_gthr) atomicMin(my_gthr, __float_as_uint(kth));   // publish the bound to the other splits
+        }
         cnt = n < k ? n : k;
     }
     __syncwarp();
 }
 
-template <int E>
+template <int E, int BK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
               const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, const TcParams p) {
+    using Cfg = TcCfg<BK>;
     constexpr int CAP = 32 * E;
+    constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
-    uint64_t* full = bars;                    // [TC_STAGES]  TMA -> MMA
-    uint64_t* empty = bars + TC_STAGES;       // [TC_STAGES]  MMA -> TMA
-    uint64_t* tfull = bars + 2 * TC_STAGES;   // [2]          MMA -> epilogue
-    uint64_t* tempty = tfull + 2;             // [2]          epilogue -> MMA
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+    uint64_t* full = bars;                 // [STAGES]  TMA -> MMA
+    uint64_t* empty = bars + STAGES;       // [STAGES]  MMA -> TMA
+    uint64_t* tfull = bars + 2 * STAGES;   // [2]       MMA -> epilogue
+    uint64_t* tempty = tfull + 2;          // [2]       epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,7 +108,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < TC_STAGES; ++s) {
+            for (int s = 0; s < STAGES; ++s) {
                 mbar_init(&full[s], 1);
                 mbar_init(&empty[s], 1);
             }
@@ -95,7 +127,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
     const int n_items = p.n_qtiles * p.n_splits;
-    const int num_kc = p.d_pad / TC_BK;
+    const int num_kc = p.d_pad / BK;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -109,13 +141,13 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
                 for (int t = t0; t < t1; ++t) {
                     for (int kc = 0; kc < num_kc; ++kc) {
                         mbar_wait(&empty[stage], phase ^ 1);
-                        uint8_t* st = smem + stage * TC_STAGE_BYTES;
-                        mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
-                        tma_load_2d(st, &tm_qhi, &full[stage], kc * TC_BK, qt * TC_BM);
-                        tma_load_2d(st + TC_A_BYTES, &tm_qlo, &full[stage], kc * TC_BK, qt * TC_BM);
-                        tma_load_2d(st + 2 * TC_A_BYTES, &tm_bhi, &full[stage], kc * TC_BK, t * TC_BN);
-                        tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tm_blo, &full[stage], kc * TC_BK, t * TC_BN);
-                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                        uint8_t* st = smem + stage * Cfg::kStageBytes;
+                        mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+                        tma_load_2d(st, &tm_qhi, &full[stage], kc * BK, qt * TC_BM);
+                        tma_load_2d(st + Cfg::kABytes, &tm_qlo, &full[stage], kc * BK, qt * TC_BM);
+                        tma_load_2d(st + 2 * Cfg::kABytes, &tm_bhi, &full[stage], kc * BK, t * TC_BN);
+                        tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tm_blo, &full[stage], kc * BK, t * TC_BN);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -140,22 +172,26 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
                     for (int kc = 0; kc < num_kc; ++kc) {
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
-                        const uint64_t a_hi = make_sw128_desc(sa);
-                        const uint64_t a_lo = make_sw128_desc(sa + TC_A_BYTES);
-                        const uint64_t b_hi = make_sw128_desc(sa + 2 * TC_A_BYTES);
-                        const uint64_t b_lo = make_sw128_desc(sa + 2 * TC_A_BYTES + TC_B_BYTES);
+                        if (p.debug_skip_mma) {            // bandwidth probe: consume the stage without any MMA
+                            mbar_arrive(&empty[stage]);
+                        } else {
+                            const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                            const uint64_t a_hi = make_kmajor_desc<BK>(sa);
+                            const uint64_t a_lo = make_kmajor_desc<BK>(sa + Cfg::kABytes);
+                            const uint64_t b_hi = make_kmajor_desc<BK>(sa + 2 * Cfg::kABytes);
+                            const uint64_t b_lo = make_kmajor_desc<BK>(sa + 2 * Cfg::kABytes + Cfg::kBBytes);
 #pragma unroll
-                        for (int ks = 0; ks < TC_BK / 8; ++ks) {
-                            const uint64_t off = static_cast<uint64_t>(ks * 2);   // 8 tf32 = 32 B = 2 x 16 B
-                            umma_tf32(tmem_d, a_lo + off, b_hi + off, idesc, (kc | ks) != 0 ? 1u : 0u);
-                            umma_tf32(tmem_d, a_hi + off, b_lo + off, idesc, 1u);
-                            umma_tf32(tmem_d, a_hi + off, b_hi + off, idesc, 1u);
+                            for (int ks = 0; ks < BK / 8; ++ks) {
+                                const uint64_t off = static_cast<uint64_t>(ks * 2);   // 8 tf32 = 32 B = 2 x 16 B
+                                umma_tf32(tmem_d, a_lo + off, b_hi + off, idesc, (kc | ks) != 0 ? 1u : 0u);
+                                umma_tf32(tmem_d, a_hi + off, b_lo + off, idesc, 1u);
+                                umma_tf32(tmem_d, a_hi + off, b_hi + off, idesc, 1u);
+                            }
+                            tc_commit(&empty[stage]);
                         }
-                        tc_commit(&empty[stage]);
-                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(&tfull[acc]);
+                    if (p.debug_skip_mma) mbar_arrive(&tfull[acc]); else tc_commit(&tfull[acc]);
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1;
                 }
@@ -165,7 +201,6 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
         // ------------------------------------------------------------------ epilogue: fused top-k
         const int g = warp & 3;                     // TMEM lane group this warp may read
         const int q_local = g * 32 + lane;
-        uint64_t* my_buf = p.cand + (static_cast<size_t>(blockIdx.x) * TC_BM + q_local) * CAP;
         const float inf = __int_as_float(0x7f800000);
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -176,9 +211,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
             const int q = qt * TC_BM + q_local;
             const bool valid = q < p.nq;
             const float qn = valid ? __ldg(p.qn + q) : 0.f;
-            float thr = valid ? inf : -1.f;
+            float thr = (valid && !p.debug_skip_mma) ? inf : -1.f;
+            uint32_t* my_gthr = (valid && p.gthr) ? p.gthr + q : nullptr;
+            // the candidate buffer of (query, split) IS its partial list: 32*E slots, the first `cnt` valid
+            // (after a compaction the first k are sorted); invalid tail queries never admit anything
+            const size_t slot = static_cast<size_t>(valid ? q : 0) * p.n_splits + split;
+            uint64_t* my_buf = p.partial + slot * CAP;
             int cnt = 0;
             for (int t = t0; t < t1; ++t) {
+                // pick up bounds other splits of this query have published since the last tile
+                if (my_gthr) thr = fminf(thr, bound_to_thr(__ldcg(my_gthr)));
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
 #pragma unroll 1
@@ -215,7 +257,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
                     while (need) {
                         const int L = __ffs(need) - 1;
                         need &= need - 1;
-                        tc_compact<E>(L, false, my_buf, cnt, thr, lane, p.k, nullptr);
+                        tc_compact<E>(L, false, my_buf, cnt, thr, lane, p.k, nullptr, my_gthr);
                     }
                 }
                 tc_fence_before();
@@ -223,13 +265,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
-            // item done: emit each query's sorted k best as a partial list
-            const int q_warp0 = qt * TC_BM + g * 32;
-            for (int L = 0; L < 32; ++L) {
-                if (q_warp0 + L >= p.nq) break;
-                uint64_t* out = p.partial + (static_cast<size_t>(q_warp0 + L) * p.n_splits + split) * p.k;
-                tc_compact<E>(L, true, my_buf, cnt, thr, lane, p.k, out);
-            }
+            // item done: the buffer already sits in the partial array; publish how much of it is valid
+            if (valid) p.pcount[slot] = cnt;
         }
     }
     tc_fence_before();
@@ -240,9 +277,15 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
 template <int E>
 cudaError_t launch_knn_tc(const CUtensorMap& qhi, const CUtensorMap& qlo, const CUtensorMap& bhi, const CUtensorMap& blo,
                           const TcParams& p, int grid, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    knn_tc_kernel<E><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(qhi, qlo, bhi, blo, p);
+    if (p.bk == 16) {
+        cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<E, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16>::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        knn_tc_kernel<E, 16><<<grid, TC_THREADS, TcCfg<16>::kSmemBytes, st>>>(qhi, qlo, bhi, blo, p);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<E, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32>::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        knn_tc_kernel<E, 32><<<grid, TC_THREADS, TcCfg<32>::kSmemBytes, st>>>(qhi, qlo, bhi, blo, p);
+    }
     return cudaGetLastError();
 }
 

@@ -9,10 +9,12 @@ namespace agp {
 
 constexpr int TC_BM = 128;            // queries per tile (UMMA M, TMEM lanes)
 constexpr int TC_BN = 256;            // database rows per tile (UMMA N, TMEM columns)
-constexpr int TC_BK = 32;             // fp32 per K chunk = one 128-byte swizzle row
+constexpr int TC_KPAD = 32;           // descriptor dimension is zero-padded to a multiple of this (largest K chunk)
 constexpr int kMaxSmallNq = 20;       // faiss distance_compute_blas_threshold
 
 struct TcParams {
+    int bk;                 // fp32 per K chunk: 32 (128B swizzle, 2 stages) or 16 (64B swizzle, 4 stages)
+    int debug_skip_mma;     // bandwidth probe: TMA ring only, no MMA, no selection
     int nq;
     int d_pad;
     int k;
@@ -21,8 +23,9 @@ struct TcParams {
     int n_dbtiles;
     const float* qn;        // [nq]
     const float* yn;        // [n_dbtiles * 256], +inf beyond the last database row
-    uint64_t* cand;         // [gridDim.x][128][32*E]
-    uint64_t* partial;      // [nq][n_splits][k]
+    uint64_t* partial;      // [nq][n_splits][32*E] candidate slots (unsorted beyond the first k)
+    int* pcount;            // [nq][n_splits] valid slots
+    uint32_t* gthr;         // [nq] shared pruning bound (fp32 bits, +inf initially); nullptr disables sharing
 };
 
 // smallest power-of-two register count E with 32*E >= 2*k (>= 64 keys)
@@ -40,11 +43,18 @@ template <int E>
 cudaError_t launch_select_rows(const float* dist, int64_t ld, int64_t n, int k, int nq, int n_chunks, uint64_t* partial,
                                cudaStream_t st);
 template <int E>
+cudaError_t launch_merge_ragged(const uint64_t* partial, const int* pcount, int slot_stride, int64_t nq, int n_lists, int k,
+                                int64_t id_base, float* D, int64_t* I, cudaStream_t st);
+template <int E>
 cudaError_t launch_merge_keys(const uint64_t* partial, int64_t nq, int n_lists, int k, int64_t id_base, float* D, int64_t* I,
                               cudaStream_t st);
 template <int E>
 cudaError_t launch_merge_lists(const float* Din, int64_t d_stride, const int64_t* Iin, int64_t i_stride, bool by_id, int64_t nq,
                                int n_lists, int k, float* D, int64_t* I, cudaStream_t st);
+
+template <int E>
+cudaError_t launch_rerank(const float* xq, const float* xb, int d, const int64_t* Icand, int kc, int64_t nq, int k, int64_t id_base,
+                          float* D, int64_t* I, cudaStream_t st);
 
 // plain launchers (k_misc.cu)
 cudaError_t launch_prep_rows(bool split, const float* x, int64_t n, int d, int d_pad, float* norm, float* hi, float* lo, int max_blocks,

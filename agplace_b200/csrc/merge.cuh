@@ -110,4 +110,134 @@ cudaError_t launch_merge_lists(const float* Din, int64_t d_stride, const int64_t
     return cudaGetLastError();
 }
 
+// Ragged variant for the fused kernel's output: list (q, s) holds pcount[q*S+s] unsorted keys in a slot
+// of `slot_stride` entries.  One warp per query appends list after list into a 32*E-entry shared
+// staging buffer and sorts it (keeping the best k) whenever it is full.
+template <int E>
+__global__ void __launch_bounds__(128) merge_ragged_kernel(const uint64_t* __restrict__ partial, const int* __restrict__ pcount,
+                                                           int slot_stride, int64_t nq, int n_lists, int k, int64_t id_base,
+                                                           float* __restrict__ D, int64_t* __restrict__ I) {
+    constexpr int CAP = 32 * E;
+    extern __shared__ uint64_t sstage[];   // [warps][CAP]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
+    if (q >= nq) return;
+    uint64_t* buf = sstage + warp * CAP;
+    uint64_t key[E];
+    int fill = 0;
+    auto sort_keep = [&]() {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < E; ++j) key[j] = (j * 32 + lane < fill) ? buf[j * 32 + lane] : kEmptyKey;
+        warp_bitonic_sort<E>(key, lane);
+#pragma unroll
+        for (int j = 0; j < E; ++j)
+            if (j * 32 + lane < k) buf[j * 32 + lane] = key[j];
+        fill = fill < k ? fill : k;
+        __syncwarp();
+    };
+    for (int s = 0; s < n_lists; ++s) {
+        const int c = pcount[q * n_lists + s];
+        const uint64_t* src = partial + (q * n_lists + s) * slot_stride;
+        int off = 0;
+        while (off < c) {
+            if (fill == CAP) sort_keep();
+            const int take = min(CAP - fill, c - off);
+            for (int i = lane; i < take; i += 32) buf[fill + i] = __ldcg(src + off + i);
+            fill += take;
+            off += take;
+        }
+    }
+    sort_keep();
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+        const int i = j * 32 + lane;
+        if (i < k) {
+            const bool empty = (i >= fill) || key[j] == kEmptyKey;
+            D[q * k + i] = empty ? kFltMax : key_dist(key[j]);
+            I[q * k + i] = empty ? -1 : id_base + static_cast<int64_t>(key_idx(key[j]));
+        }
+    }
+}
+
+template <int E>
+cudaError_t launch_merge_ragged(const uint64_t* partial, const int* pcount, int slot_stride, int64_t nq, int n_lists, int k,
+                                int64_t id_base, float* D, int64_t* I, cudaStream_t st) {
+    constexpr int warps = 4;
+    merge_ragged_kernel<E><<<static_cast<unsigned>((nq + warps - 1) / warps), warps * 32, warps * 32 * E * sizeof(uint64_t), st>>>(
+        partial, pcount, slot_stride, nq, n_lists, k, id_base, D, I);
+    return cudaGetLastError();
+}
+
+// K6: exact re-rank.  The tensor-core pass selects kc >= k candidates per query with 3xTF32
+// (expansion form, round-toward-zero accumulation: ~1e-6 of |q|^2+|y|^2); this kernel recomputes each
+// candidate's distance in the exact fp32 difference form sum (x - y)^2 -- what faiss evaluates for
+// small batches -- sorts by (distance, id) and emits the best k.  One warp per query; HBM/L2-bound
+// gather of kc rows of d floats.
+template <int E>
+__global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ xq, const float* __restrict__ xb, int d,
+                                                     const int64_t* __restrict__ Icand, int kc, int64_t nq, int k, int64_t id_base,
+                                                     float* __restrict__ D, int64_t* __restrict__ I) {
+    extern __shared__ float sdist[];   // [warps][32*E]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
+    if (q >= nq) return;
+    float* sd = sdist + warp * 32 * E;
+    const float* qrow = xq + q * d;
+    const int64_t* cand = Icand + q * kc;
+    const bool vec = ((d & 3) == 0) && (((reinterpret_cast<uintptr_t>(xq) | reinterpret_cast<uintptr_t>(xb)) & 15) == 0);
+    for (int r = 0; r < kc; ++r) {
+        const int64_t id = cand[r];
+        float acc = 0.f;
+        if (id >= 0) {
+            const float* row = xb + id * d;
+            if (vec) {
+                for (int c = lane; c < (d >> 2); c += 32) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(qrow) + c);
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(row) + c);
+                    float t;
+                    t = a.x - b.x; acc = fmaf(t, t, acc);
+                    t = a.y - b.y; acc = fmaf(t, t, acc);
+                    t = a.z - b.z; acc = fmaf(t, t, acc);
+                    t = a.w - b.w; acc = fmaf(t, t, acc);
+                }
+            } else {
+                for (int c = lane; c < d; c += 32) {
+                    const float t = __ldg(qrow + c) - __ldg(row + c);
+                    acc = fmaf(t, t, acc);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+        }
+        if (lane == 0) sd[r] = acc;
+    }
+    __syncwarp();
+    uint64_t key[E];
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+        const int i = j * 32 + lane;
+        key[j] = (i < kc && cand[i] >= 0) ? pack_key(sd[i], static_cast<uint32_t>(cand[i])) : kEmptyKey;
+    }
+    warp_bitonic_sort<E>(key, lane);
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+        const int i = j * 32 + lane;
+        if (i < k) {
+            const bool empty = key[j] == kEmptyKey;
+            D[q * k + i] = empty ? kFltMax : key_dist(key[j]);
+            I[q * k + i] = empty ? -1 : id_base + static_cast<int64_t>(key_idx(key[j]));
+        }
+    }
+}
+
+template <int E>
+cudaError_t launch_rerank(const float* xq, const float* xb, int d, const int64_t* Icand, int kc, int64_t nq, int k, int64_t id_base,
+                          float* D, int64_t* I, cudaStream_t st) {
+    constexpr int warps = 4;
+    rerank_kernel<E><<<static_cast<unsigned>((nq + warps - 1) / warps), warps * 32, warps * 32 * E * sizeof(float), st>>>(
+        xq, xb, d, Icand, kc, nq, k, id_base, D, I);
+    return cudaGetLastError();
+}
+
 }  // namespace agp

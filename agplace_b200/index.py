@@ -76,10 +76,10 @@ class IndexFlatL2:
         if tensor.device.index != self.device:
             raise ValueError(f"tensor is on cuda:{tensor.device.index} but the index lives on cuda:{self.device}")
         stream = torch.cuda.current_stream(tensor.device).cuda_stream
-        _lib.check(self._lib.agp_index_set_stream(self._h, ctypes.c_void_p(stream)), "agp_index_set_stream")
+        _lib.check(self._lib.agp_index_set_stream(self._h, ctypes.c_void_p(stream), 0), "agp_index_set_stream")
 
     def _use_own_stream(self):
-        _lib.check(self._lib.agp_index_set_stream(self._h, None), "agp_index_set_stream")
+        _lib.check(self._lib.agp_index_set_stream(self._h, None, 1), "agp_index_set_stream")
 
     # ------------------------------------------------------------------ add / reset
     def add(self, x):

@@ -81,8 +81,9 @@ AGP_API int agp_index_dim(const agp_index* idx);
 AGP_API int agp_index_reserve(agp_index* idx, int64_t n);
 
 /* Run this index's work on an existing CUDA stream (cudaStream_t passed as void*), e.g. torch's
- * current stream; NULL restores the index's own stream. */
-AGP_API int agp_index_set_stream(agp_index* idx, void* cuda_stream);
+ * current stream.  A NULL handle is the legacy default stream; use_own_stream != 0 ignores cuda_stream
+ * and restores the index's private non-blocking stream. */
+AGP_API int agp_index_set_stream(agp_index* idx, void* cuda_stream, int use_own_stream);
 
 /* Global id of this shard's first row: I = id_base + local row.  Used by the row-sharded
  * multi-GPU index (one shard per rank). */

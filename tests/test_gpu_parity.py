@@ -75,7 +75,7 @@ def test_random_shapes_match_oracle(nq, n, d, k, precision):
 
 def test_unit_norm_descriptors_cfg1_shape_and_recall_identical():
     from agplace_b200 import recall, synth
-    ev = synth.make_eval_set("cfg1", correlated=0.5)
+    ev = synth.make_eval_set("cfg1", correlated=0.16)        # R@1 ~ 21 %, R@20 ~ 57 % on the CPU oracle
     args = SimpleNamespace(features_dim=256, recall_values=[1, 5, 10, 20])
     r_gpu, s_gpu = recall.compute_recall(args, ev.queries_features, ev.database_features, ev)
     r_dev, _ = recall.compute_recall(args, ev.queries_features, ev.database_features, ev, on_device_recall=True)
@@ -98,8 +98,11 @@ def test_near_duplicate_regime(sigma, precision):
     D, I = search(xb, xq, 10, precision)
     assert (I[:, 0] == src).all(), "the perturbed source row must be the nearest neighbour"
     Dr, Ir = orc.knn_fp32(xq, xb, 10)
-    # expansion form on both sides: absolute floor of 8 ulp of (|q|^2 + |x|^2)
-    ok, msg = orc.compare_knn(D, I, Dr, Ir, xq=xq, xb=xb, abs_floor_eps=8 * 2.0 ** -24)
+    # expansion form on both sides: absolute floor of 8 ulp of (|q|^2 + |x|^2) for fp32 FMA; the
+    # tensor-core path gets 32 ulp because tcgen05 accumulates with round-toward-zero (measured
+    # ~1e-6 relative to the norms over a 192-MMA chain, DESIGN.md "Numerics")
+    ulps = 8 if precision == "fp32_simt" else 32
+    ok, msg = orc.compare_knn(D, I, Dr, Ir, xq=xq, xb=xb, abs_floor_eps=ulps * 2.0 ** -24)
     assert ok, msg
     # small batches take the exact difference form (like faiss): tight agreement with fp64 truth
     D1, I1 = search(xb, xq[:7], 10, "auto")
@@ -281,7 +284,8 @@ def test_full_size_cfg2_properties():
     assert ok, msg
     simt = agp().IndexFlatL2(c["d"], precision="fp32_simt"); simt.add(xb)
     D2, I2 = simt.search(xq[:4096], c["k"])
-    ok, msg = orc.compare_knn(D[:4096], I[:4096], D2, I2, xq=xq[:4096], xb=xb, abs_floor_eps=8 * 2.0 ** -24)
+    # fp32 FMA expansion form over d = 512 is itself ~11 ulp of (|q|^2 + |x|^2) away from the exact value
+    ok, msg = orc.compare_knn(D[:4096], I[:4096], D2, I2, xq=xq[:4096], xb=xb, abs_floor_eps=32 * 2.0 ** -24)
     assert ok, "tensor-core vs fp32 SIMT: " + msg
     # idempotence: same call, same bits
     Db, Ib = ix.search(xq, c["k"])
