@@ -68,7 +68,7 @@ struct agp_index {
     float *xb = nullptr, *xb_hi = nullptr, *xb_lo = nullptr, *yn = nullptr;
     bool planes = false;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    Buf q_raw, q_hi, q_lo, qn, cand, partial, panel, d_out, i_out, gthr, cand_d, cand_i;
+    Buf q_raw, q_hi, q_lo, qn, cand, partial, panel, d_out, i_out, gthr, cand_d, cand_i, dbg;
     bool profile = false;
     cudaEvent_t ev_order = nullptr;
     std::vector<cudaEvent_t> ev_pool;
@@ -352,9 +352,28 @@ static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, floa
             LAUNCH(launch_fill_f32(static_cast<float*>(ix->gthr.p), nqc, HUGE_VALF, ix->stream));
             p.gthr = static_cast<uint32_t*>(ix->gthr.p);
         }
+        p.dbg = nullptr;
+        const char* env_dbg = getenv("AGP_TC_DEBUG");
+        const bool dbg = env_dbg && atoi(env_dbg) != 0;
+        if (dbg) {
+            CKR(ensure(ix->dbg, static_cast<size_t>(grid) * 8 * sizeof(long long)));
+            CK(cudaMemsetAsync(ix->dbg.p, 0, static_cast<size_t>(grid) * 8 * sizeof(long long), ix->stream));
+            p.dbg = static_cast<long long*>(ix->dbg.p);
+        }
         ProfScope prof(ix);
         CKR(DISPATCH_E(k, launch_knn_tc, m_qhi, m_qlo, m_bhi, m_blo, p, grid, ix->stream));
         prof.stop();
+        if (dbg) {
+            std::vector<long long> h(static_cast<size_t>(grid) * 8);
+            CK(cudaMemcpyAsync(h.data(), ix->dbg.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
+            CK(cudaStreamSynchronize(ix->stream));
+            double s[8] = {0};
+            for (int b = 0; b < grid; ++b)
+                for (int j = 0; j < 8; ++j) s[j] += static_cast<double>(h[b * 8 + j]) / grid;
+            fprintf(stderr, "[agp tc dbg] grid=%d splits=%d items=%d | mma: total=%.0f wait_full=%.0f wait_tempty=%.0f | epi(w2): total=%.0f "
+                            "wait_tfull=%.0f compact=%.0f n_compact=%.0f (cycles, mean per CTA)\n",
+                    grid, p.n_splits, n_items, s[0], s[1], s[2], s[3], s[4], s[5], s[6]);
+        }
         if (!rerank) {
             CKR(DISPATCH_E32(k, launch_merge_ragged, static_cast<const uint64_t*>(ix->partial.p), static_cast<const int*>(ix->cand.p), slots,
                              static_cast<int64_t>(nqc), p.n_splits, k, ix->id_base, D + q0 * k, I + q0 * k, ix->stream));
@@ -429,7 +448,7 @@ void agp_index_free(agp_index* ix) {
     if (ix->xb_lo) cudaFree(ix->xb_lo);
     if (ix->yn) cudaFree(ix->yn);
     free_buf(ix->q_raw); free_buf(ix->q_hi); free_buf(ix->q_lo); free_buf(ix->qn); free_buf(ix->cand);
-    free_buf(ix->gthr); free_buf(ix->cand_d); free_buf(ix->cand_i); free_buf(ix->partial); free_buf(ix->panel); free_buf(ix->d_out); free_buf(ix->i_out);
+    free_buf(ix->gthr); free_buf(ix->dbg); free_buf(ix->cand_d); free_buf(ix->cand_i); free_buf(ix->partial); free_buf(ix->panel); free_buf(ix->d_out); free_buf(ix->i_out);
     for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
     if (ix->ev_order) cudaEventDestroy(ix->ev_order);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);

@@ -161,16 +161,21 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            long long w_full = 0, w_tempty = 0, t_begin = p.dbg ? clock64() : 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int split = item / p.n_qtiles;
                 const int t0 = static_cast<int>(static_cast<int64_t>(split) * p.n_dbtiles / p.n_splits);
                 const int t1 = static_cast<int>(static_cast<int64_t>(split + 1) * p.n_dbtiles / p.n_splits);
                 for (int t = t0; t < t1; ++t) {
+                    long long c0 = p.dbg ? clock64() : 0;
                     mbar_wait(&tempty[acc], acc_phase ^ 1);
+                    if (p.dbg) w_tempty += clock64() - c0;
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + acc * TC_BN;
                     for (int kc = 0; kc < num_kc; ++kc) {
+                        long long c1 = p.dbg ? clock64() : 0;
                         mbar_wait(&full[stage], phase);
+                        if (p.dbg) w_full += clock64() - c1;
                         tc_fence_after();
                         if (p.debug_skip_mma) {            // bandwidth probe: consume the stage without any MMA
                             mbar_arrive(&empty[stage]);
@@ -196,6 +201,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
                     if (acc == 0) acc_phase ^= 1;
                 }
             }
+            if (p.dbg) {
+                p.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
+                p.dbg[blockIdx.x * 8 + 1] = w_full;
+                p.dbg[blockIdx.x * 8 + 2] = w_tempty;
+            }
         }
     } else {
         // ------------------------------------------------------------------ epilogue: fused top-k
@@ -204,6 +214,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
         const float inf = __int_as_float(0x7f800000);
         int acc = 0;
         uint32_t acc_phase = 0;
+        long long w_tfull = 0, t_compact = 0, n_compact = 0, e_begin = p.dbg ? clock64() : 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int split = item / p.n_qtiles, qt = item - split * p.n_qtiles;
             const int t0 = static_cast<int>(static_cast<int64_t>(split) * p.n_dbtiles / p.n_splits);
@@ -221,7 +232,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
             for (int t = t0; t < t1; ++t) {
                 // pick up bounds other splits of this query have published since the last tile
                 if (my_gthr) thr = fminf(thr, bound_to_thr(__ldcg(my_gthr)));
+                long long c2 = p.dbg ? clock64() : 0;
                 mbar_wait(&tfull[acc], acc_phase);
+                if (p.dbg) w_tfull += clock64() - c2;
                 tc_fence_after();
 #pragma unroll 1
                 for (int cc = 0; cc < TC_BN / 32; ++cc) {
@@ -254,11 +267,15 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
                         }
                     }
                     unsigned need = __ballot_sync(kFull, cnt > CAP - 32);
+                    long long c3 = (p.dbg && need) ? clock64() : 0;
+                    if (p.dbg && need) n_compact += __popc(need);
+                    const bool had = need != 0;
                     while (need) {
                         const int L = __ffs(need) - 1;
                         need &= need - 1;
                         tc_compact<E>(L, false, my_buf, cnt, thr, lane, p.k, nullptr, my_gthr);
                     }
+                    if (p.dbg && had) t_compact += clock64() - c3;
                 }
                 tc_fence_before();
                 mbar_arrive(&tempty[acc]);
@@ -267,6 +284,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
             }
             // item done: the buffer already sits in the partial array; publish how much of it is valid
             if (valid) p.pcount[slot] = cnt;
+        }
+        if (p.dbg && warp == 2 && lane == 0) {
+            p.dbg[blockIdx.x * 8 + 3] = clock64() - e_begin;
+            p.dbg[blockIdx.x * 8 + 4] = w_tfull;
+            p.dbg[blockIdx.x * 8 + 5] = t_compact;
+            p.dbg[blockIdx.x * 8 + 6] = n_compact;
         }
     }
     tc_fence_before();

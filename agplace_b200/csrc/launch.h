@@ -25,6 +25,7 @@ struct TcParams {
     const float* yn;        // [n_dbtiles * 256], +inf beyond the last database row
     uint64_t* partial;      // [nq][n_splits][32*E] candidate slots (unsorted beyond the first k)
     int* pcount;            // [nq][n_splits] valid slots
+    long long* dbg;         // [grid][8] cycle counters (development), nullptr = off
     uint32_t* gthr;         // [nq] shared pruning bound (fp32 bits, +inf initially); nullptr disables sharing
 };
 

@@ -1,0 +1,63 @@
+"""Row-sharded index over NCCL on real GPUs (skipped unless >= 2 devices are visible):
+ShardedIndexFlatL2 on 2 ranks must return exactly what one unsharded index returns."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, shard, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from agplace_b200.sharded import ShardedIndexFlatL2
+        rng = np.random.default_rng(5)
+        xb = rng.standard_normal((30011, 128)).astype(np.float32)
+        xq = rng.standard_normal((777, 128)).astype(np.float32)
+        ix = ShardedIndexFlatL2(128, device=rank, shard=shard)
+        ix.add(xb[:20000]); ix.add(xb[20000:])
+        D, I = ix.search(xq, 40)                                   # numpy in -> numpy out
+        Dt, It = ix.search(torch.from_numpy(xq).cuda(), 100)       # CUDA in -> CUDA out
+        np.savez(Path(out_dir) / f"r{rank}.npz", D=D, I=I, D2=Dt.cpu().numpy(), I2=It.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shard", ["db", "query"])
+def test_nccl_sharded_equals_single(tmp_path, shard):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, shard, str(tmp_path)), nprocs=world, join=True)
+    import agplace_b200 as agp
+    rng = np.random.default_rng(5)
+    xb = rng.standard_normal((30011, 128)).astype(np.float32)
+    xq = rng.standard_normal((777, 128)).astype(np.float32)
+    single = agp.IndexFlatL2(128, device=0)
+    single.add(xb)
+    Ds, Is = single.search(xq, 40)
+    Ds2, Is2 = single.search(xq, 100)
+    for r in range(world):
+        got = np.load(tmp_path / f"r{r}.npz")
+        np.testing.assert_array_equal(got["I"], Is)
+        np.testing.assert_array_equal(got["D"], Ds)
+        np.testing.assert_array_equal(got["I2"], Is2)
+        np.testing.assert_array_equal(got["D2"], Ds2)
