@@ -13,7 +13,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "libagpknn.so"
 
 MEM_HOST, MEM_DEVICE = 0, 1
-PRECISION = {"auto": 0, "fp32_simt": 1, "3xtf32": 2, "exact_diff": 3}
+PRECISION = {"auto": 0, "fp32_simt": 1, "3xtf32": 2, "exact_diff": 3, "3xfp16": 4}
 MAX_K = 512
 
 # every symbol include/agpknn.h declares: name -> (restype, argtypes)

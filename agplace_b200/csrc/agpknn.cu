@@ -2,8 +2,10 @@
 //
 // HBM layout of one index (one shard, one GPU):
 //   xb      fp32 [cap, d]        raw rows, add order            (difference-form / SIMT paths)
-//   xb_hi   fp32 [cap, d_pad]    rna_tf32(x), d_pad = ceil32(d)  (3xTF32 operand planes, TMA source)
-//   xb_lo   fp32 [cap, d_pad]    rna_tf32(x - hi)
+//   xb_hi   [cap, d_pad]  operand plane "hi", d_pad = ceil64(d), TMA source, K-major:
+//   xb_lo   [cap, d_pad]  operand plane "lo"   3xTF32: fp32 containers of rna_tf32(x), rna_tf32(x - hi)
+//                                              3xFP16: fp16 of the row scaled by 2^-ex (max|x'| in [0.5,1))
+//   wx      fp32 [cap]    3xFP16 only: -2 * 2^ex per row (undoes the scaling inside the epilogue FMA)
 //   yn      fp32 [cap]           |x|^2, +inf beyond ntotal (masks TMA zero-filled tail rows)
 // cap is a multiple of 256 and grows geometrically.  Scratch (query planes, candidate buffers,
 // partial lists, distance panels) is pooled per index and reused across searches.
@@ -65,10 +67,12 @@ struct Buf {
 struct agp_index {
     int d = 0, d_pad = 0, device = 0, mode = 0, num_sms = 0;
     int64_t ntotal = 0, cap = 0, id_base = 0;
-    float *xb = nullptr, *xb_hi = nullptr, *xb_lo = nullptr, *yn = nullptr;
+    float *xb = nullptr, *yn = nullptr, *wx = nullptr;
+    uint8_t *xb_hi = nullptr, *xb_lo = nullptr;
     bool planes = false;
+    int kind = KIND_TF32, elem_bytes = 4;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    Buf q_raw, q_hi, q_lo, qn, cand, partial, panel, d_out, i_out, gthr, cand_d, cand_i, dbg;
+    Buf q_raw, q_hi, q_lo, qn, sq, cand, partial, panel, d_out, i_out, gthr, cand_d, cand_i, dbg;
     bool profile = false;
     cudaEvent_t ev_order = nullptr;
     std::vector<cudaEvent_t> ev_pool;
@@ -115,18 +119,18 @@ static int get_encode_fn(EncodeTiledFn* out) {
     return 0;
 }
 
-// fp32 [rows, d_pad] row-major plane -> boxes of (bk floats x box_rows); the swizzle span equals the
-// box row (bk = 32: 128 B, bk = 16: 64 B); out-of-bounds rows are zero filled
-static int make_plane_map(CUtensorMap* m, const float* base, int64_t rows, int d_pad, int box_rows, int bk) {
+// [rows, d_pad] row-major operand plane -> boxes of (128 bytes x box_rows), 128B swizzle; out-of-bounds
+// rows are zero filled
+static int make_plane_map(CUtensorMap* m, const void* base, int64_t rows, int d_pad, int box_rows, int elem_bytes) {
     EncodeTiledFn fn;
     CKR(get_encode_fn(&fn));
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(d_pad), static_cast<cuuint64_t>(rows)};
-    cuuint64_t strides[1] = {static_cast<cuuint64_t>(d_pad) * sizeof(float)};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(box_rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(d_pad) * elem_bytes};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(TC_KCHUNK_BYTES / elem_bytes), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(AGP_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
     return 0;
 }
@@ -136,20 +140,27 @@ static int grow(agp_index* ix, int64_t need) {
     if (need <= ix->cap) return 0;
     int64_t ncap = std::max<int64_t>(need, ix->cap + ix->cap / 2);
     ncap = round_up(std::max<int64_t>(ncap, 256), 256);
-    float *nxb = nullptr, *nhi = nullptr, *nlo = nullptr, *nyn = nullptr;
+    float *nxb = nullptr, *nyn = nullptr, *nwx = nullptr;
+    uint8_t *nhi = nullptr, *nlo = nullptr;
+    const size_t plane_row = static_cast<size_t>(ix->d_pad) * ix->elem_bytes;
     CK(cudaMalloc(&nxb, static_cast<size_t>(ncap) * ix->d * sizeof(float)));
     CK(cudaMalloc(&nyn, static_cast<size_t>(ncap) * sizeof(float)));
     if (ix->planes) {
-        CK(cudaMalloc(&nhi, static_cast<size_t>(ncap) * ix->d_pad * sizeof(float)));
-        CK(cudaMalloc(&nlo, static_cast<size_t>(ncap) * ix->d_pad * sizeof(float)));
+        CK(cudaMalloc(&nhi, static_cast<size_t>(ncap) * plane_row));
+        CK(cudaMalloc(&nlo, static_cast<size_t>(ncap) * plane_row));
+        if (ix->kind == KIND_F16) {
+            CK(cudaMalloc(&nwx, static_cast<size_t>(ncap) * sizeof(float)));
+            LAUNCH(launch_fill_f32(nwx, ncap, 0.f, ix->stream));
+        }
     }
     LAUNCH(launch_fill_f32(nyn, ncap, HUGE_VALF, ix->stream));
     if (ix->ntotal > 0) {
         CK(cudaMemcpyAsync(nxb, ix->xb, static_cast<size_t>(ix->ntotal) * ix->d * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
         CK(cudaMemcpyAsync(nyn, ix->yn, static_cast<size_t>(ix->ntotal) * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
         if (ix->planes) {
-            CK(cudaMemcpyAsync(nhi, ix->xb_hi, static_cast<size_t>(ix->ntotal) * ix->d_pad * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
-            CK(cudaMemcpyAsync(nlo, ix->xb_lo, static_cast<size_t>(ix->ntotal) * ix->d_pad * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+            CK(cudaMemcpyAsync(nhi, ix->xb_hi, static_cast<size_t>(ix->ntotal) * plane_row, cudaMemcpyDeviceToDevice, ix->stream));
+            CK(cudaMemcpyAsync(nlo, ix->xb_lo, static_cast<size_t>(ix->ntotal) * plane_row, cudaMemcpyDeviceToDevice, ix->stream));
+            if (nwx) CK(cudaMemcpyAsync(nwx, ix->wx, static_cast<size_t>(ix->ntotal) * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
         }
     }
     CK(cudaStreamSynchronize(ix->stream));
@@ -157,7 +168,8 @@ static int grow(agp_index* ix, int64_t need) {
     if (ix->yn) cudaFree(ix->yn);
     if (ix->xb_hi) cudaFree(ix->xb_hi);
     if (ix->xb_lo) cudaFree(ix->xb_lo);
-    ix->xb = nxb; ix->yn = nyn; ix->xb_hi = nhi; ix->xb_lo = nlo;
+    if (ix->wx) cudaFree(ix->wx);
+    ix->xb = nxb; ix->yn = nyn; ix->xb_hi = nhi; ix->xb_lo = nlo; ix->wx = nwx;
     ix->cap = ncap;
     return 0;
 }
@@ -301,34 +313,42 @@ static int search_simt(agp_index* ix, const float* xq_dev, int64_t nq, int k, fl
 static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, float* D, int64_t* I) {
     const int64_t n = ix->ntotal;
     if (k > 256) return search_simt(ix, xq_dev, nq, k, D, I);   // fused epilogue holds <= 512 candidates per query
-    const int E = tc_regs_for_k(k);
-    const int n_dbtiles = static_cast<int>((n + TC_BN - 1) / TC_BN);
-    const int64_t max_chunk = 65536;
-    // development knobs (not part of the ABI): K-chunk width and a TMA-only bandwidth probe
-    const char* env_bk = getenv("AGP_TC_BK");
-    const int bk = (env_bk && atoi(env_bk) == 16) ? 16 : 32;
-    const char* env_skip = getenv("AGP_TC_SKIP_MMA");
-    const int skip_mma = (env_skip && atoi(env_skip) != 0) ? 1 : 0;
-    // exact re-rank (default on): the tensor cores select the k candidates (3xTF32, expansion form),
-    // then their distances are recomputed in the fp32 difference form and re-sorted
+    // exact re-rank (default on): the tensor cores select kc = k + margin candidates (split-operand product,
+    // expansion form), then their distances are recomputed in the fp32 difference form and the best k kept.
+    // The margin absorbs selection flips at the k-th boundary caused by the ~1e-6 tensor-core error.
     const char* env_rr = getenv("AGP_TC_RERANK");
     const bool rerank = !(env_rr && atoi(env_rr) == 0);
-    const int kc = k;
+    const int kc = rerank ? k + std::max(8, k / 8) : k;
+    const int E = tc_regs_for_k(kc);
+    const int n_dbtiles = static_cast<int>((n + TC_BN - 1) / TC_BN);
+    const int64_t max_chunk = 65536;
+    // development knob (not part of the ABI): TMA-only bandwidth probe
+    const int eb = ix->elem_bytes;
+    const char* env_skip = getenv("AGP_TC_SKIP_MMA");
+    const int skip_mma = (env_skip && atoi(env_skip) != 0) ? 1 : 0;
     CUtensorMap m_bhi, m_blo;
-    CKR(make_plane_map(&m_bhi, ix->xb_hi, n, ix->d_pad, TC_BN, bk));
-    CKR(make_plane_map(&m_blo, ix->xb_lo, n, ix->d_pad, TC_BN, bk));
+    CKR(make_plane_map(&m_bhi, ix->xb_hi, n, ix->d_pad, TC_BN, eb));
+    CKR(make_plane_map(&m_blo, ix->xb_lo, n, ix->d_pad, TC_BN, eb));
     for (int64_t q0 = 0; q0 < nq; q0 += max_chunk) {
         const int nqc = static_cast<int>(std::min<int64_t>(max_chunk, nq - q0));
-        CKR(ensure(ix->q_hi, static_cast<size_t>(nqc) * ix->d_pad * sizeof(float)));
-        CKR(ensure(ix->q_lo, static_cast<size_t>(nqc) * ix->d_pad * sizeof(float)));
+        CKR(ensure(ix->q_hi, static_cast<size_t>(nqc) * ix->d_pad * eb));
+        CKR(ensure(ix->q_lo, static_cast<size_t>(nqc) * ix->d_pad * eb));
         CKR(ensure(ix->qn, static_cast<size_t>(nqc) * sizeof(float)));
-        LAUNCH(launch_prep_rows(true, xq_dev + q0 * ix->d, nqc, ix->d, ix->d_pad, static_cast<float*>(ix->qn.p),
-                                static_cast<float*>(ix->q_hi.p), static_cast<float*>(ix->q_lo.p), ix->num_sms * 32, ix->stream));
+        CKR(ensure(ix->sq, static_cast<size_t>(nqc) * sizeof(float)));
+        if (ix->kind == KIND_F16) {
+            LAUNCH(launch_prep_rows_f16(xq_dev + q0 * ix->d, nqc, ix->d, ix->d_pad, static_cast<float*>(ix->qn.p), ix->q_hi.p, ix->q_lo.p,
+                                        static_cast<float*>(ix->sq.p), 1.f, ix->num_sms * 32, ix->stream));
+        } else {
+            LAUNCH(launch_prep_rows(true, xq_dev + q0 * ix->d, nqc, ix->d, ix->d_pad, static_cast<float*>(ix->qn.p),
+                                    static_cast<float*>(ix->q_hi.p), static_cast<float*>(ix->q_lo.p), ix->num_sms * 32, ix->stream));
+        }
         CUtensorMap m_qhi, m_qlo;
-        CKR(make_plane_map(&m_qhi, static_cast<float*>(ix->q_hi.p), nqc, ix->d_pad, TC_BM, bk));
-        CKR(make_plane_map(&m_qlo, static_cast<float*>(ix->q_lo.p), nqc, ix->d_pad, TC_BM, bk));
+        CKR(make_plane_map(&m_qhi, ix->q_hi.p, nqc, ix->d_pad, TC_BM, eb));
+        CKR(make_plane_map(&m_qlo, ix->q_lo.p, nqc, ix->d_pad, TC_BM, eb));
         TcParams p;
-        p.bk = bk;
+        p.kind = ix->kind;
+        p.sq = static_cast<const float*>(ix->sq.p);
+        p.wx = ix->wx;
         p.debug_skip_mma = skip_mma;
         p.nq = nqc;
         p.d_pad = ix->d_pad;
@@ -339,8 +359,9 @@ static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, floa
         const int n_items = p.n_qtiles * p.n_splits;
         const int grid = std::min(n_items, ix->num_sms);
         const int slots = 32 * E;
-        CKR(ensure(ix->cand, static_cast<size_t>(nqc) * p.n_splits * sizeof(int)));
-        CKR(ensure(ix->partial, static_cast<size_t>(nqc) * p.n_splits * slots * sizeof(uint64_t)));
+        const int n_lists = 2 * p.n_splits;        // (split, column half) lists per query
+        CKR(ensure(ix->cand, static_cast<size_t>(nqc) * n_lists * sizeof(int)));
+        CKR(ensure(ix->partial, static_cast<size_t>(nqc) * n_lists * slots * sizeof(uint64_t)));
         p.qn = static_cast<const float*>(ix->qn.p);
         p.yn = ix->yn;
         p.pcount = static_cast<int*>(ix->cand.p);
@@ -361,7 +382,7 @@ static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, floa
             p.dbg = static_cast<long long*>(ix->dbg.p);
         }
         ProfScope prof(ix);
-        CKR(DISPATCH_E(k, launch_knn_tc, m_qhi, m_qlo, m_bhi, m_blo, p, grid, ix->stream));
+        CKR(DISPATCH_E(kc, launch_knn_tc, m_qhi, m_qlo, m_bhi, m_blo, p, grid, ix->stream));
         prof.stop();
         if (dbg) {
             std::vector<long long> h(static_cast<size_t>(grid) * 8);
@@ -376,12 +397,12 @@ static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, floa
         }
         if (!rerank) {
             CKR(DISPATCH_E32(k, launch_merge_ragged, static_cast<const uint64_t*>(ix->partial.p), static_cast<const int*>(ix->cand.p), slots,
-                             static_cast<int64_t>(nqc), p.n_splits, k, ix->id_base, D + q0 * k, I + q0 * k, ix->stream));
+                             static_cast<int64_t>(nqc), n_lists, k, ix->id_base, D + q0 * k, I + q0 * k, ix->stream));
         } else {
             CKR(ensure(ix->cand_d, static_cast<size_t>(nqc) * kc * sizeof(float)));
             CKR(ensure(ix->cand_i, static_cast<size_t>(nqc) * kc * sizeof(int64_t)));
             CKR(DISPATCH_E32(kc, launch_merge_ragged, static_cast<const uint64_t*>(ix->partial.p), static_cast<const int*>(ix->cand.p), slots,
-                             static_cast<int64_t>(nqc), p.n_splits, kc, static_cast<int64_t>(0), static_cast<float*>(ix->cand_d.p),
+                             static_cast<int64_t>(nqc), n_lists, kc, static_cast<int64_t>(0), static_cast<float*>(ix->cand_d.p),
                              static_cast<int64_t*>(ix->cand_i.p), ix->stream));
             CKR(DISPATCH_E32(kc, launch_rerank, xq_dev + q0 * ix->d, ix->xb, ix->d, static_cast<const int64_t*>(ix->cand_i.p), kc,
                              static_cast<int64_t>(nqc), k, ix->id_base, D + q0 * k, I + q0 * k, ix->stream));
@@ -410,7 +431,7 @@ int agp_index_create(int d, int device, int precision_mode, agp_index** out) {
     if (!out) return set_err(AGP_EINVAL, "out is null");
     *out = nullptr;
     if (d <= 0) return set_err(AGP_EINVAL, "d must be positive, got %d", d);
-    if (precision_mode < 0 || precision_mode > 3) return set_err(AGP_EINVAL, "unknown precision_mode %d", precision_mode);
+    if (precision_mode < 0 || precision_mode > 4) return set_err(AGP_EINVAL, "unknown precision_mode %d", precision_mode);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -428,7 +449,11 @@ int agp_index_create(int d, int device, int precision_mode, agp_index** out) {
     ix->device = device;
     ix->mode = precision_mode;
     ix->num_sms = prop.multiProcessorCount;
-    ix->planes = (precision_mode == AGP_PRECISION_AUTO || precision_mode == AGP_PRECISION_3XTF32);
+    ix->planes = (precision_mode == AGP_PRECISION_AUTO || precision_mode == AGP_PRECISION_3XTF32 || precision_mode == AGP_PRECISION_3XFP16);
+    ix->kind = (precision_mode == AGP_PRECISION_3XTF32) ? KIND_TF32 : KIND_F16;
+    const char* env_kind = getenv("AGP_TC_KIND");          // development override: "tf32" | "f16"
+    if (env_kind && precision_mode == AGP_PRECISION_AUTO) ix->kind = (strcmp(env_kind, "tf32") == 0) ? KIND_TF32 : KIND_F16;
+    ix->elem_bytes = ix->kind == KIND_TF32 ? 4 : 2;
     cudaError_t e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete ix;
@@ -447,6 +472,8 @@ void agp_index_free(agp_index* ix) {
     if (ix->xb_hi) cudaFree(ix->xb_hi);
     if (ix->xb_lo) cudaFree(ix->xb_lo);
     if (ix->yn) cudaFree(ix->yn);
+    if (ix->wx) cudaFree(ix->wx);
+    free_buf(ix->sq);
     free_buf(ix->q_raw); free_buf(ix->q_hi); free_buf(ix->q_lo); free_buf(ix->qn); free_buf(ix->cand);
     free_buf(ix->gthr); free_buf(ix->dbg); free_buf(ix->cand_d); free_buf(ix->cand_i); free_buf(ix->partial); free_buf(ix->panel); free_buf(ix->d_out); free_buf(ix->i_out);
     for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
@@ -527,9 +554,13 @@ int agp_index_add(agp_index* ix, int64_t n, const float* x, int mem_kind) {
     float* dst = ix->xb + ix->ntotal * ix->d;
     CK(cudaMemcpyAsync(dst, x, static_cast<size_t>(n) * ix->d * sizeof(float),
                        mem_kind == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ix->stream));
-    if (ix->planes) {
-        LAUNCH(launch_prep_rows(true, dst, n, ix->d, ix->d_pad, ix->yn + ix->ntotal, ix->xb_hi + ix->ntotal * ix->d_pad,
-                                ix->xb_lo + ix->ntotal * ix->d_pad, ix->num_sms * 32, ix->stream));
+    const size_t plane_off = static_cast<size_t>(ix->ntotal) * ix->d_pad * ix->elem_bytes;
+    if (ix->planes && ix->kind == KIND_F16) {
+        LAUNCH(launch_prep_rows_f16(dst, n, ix->d, ix->d_pad, ix->yn + ix->ntotal, ix->xb_hi + plane_off, ix->xb_lo + plane_off,
+                                    ix->wx + ix->ntotal, -2.f, ix->num_sms * 32, ix->stream));
+    } else if (ix->planes) {
+        LAUNCH(launch_prep_rows(true, dst, n, ix->d, ix->d_pad, ix->yn + ix->ntotal, reinterpret_cast<float*>(ix->xb_hi + plane_off),
+                                reinterpret_cast<float*>(ix->xb_lo + plane_off), ix->num_sms * 32, ix->stream));
     } else {
         LAUNCH(launch_prep_rows(false, dst, n, ix->d, ix->d_pad, ix->yn + ix->ntotal, nullptr, nullptr, ix->num_sms * 32, ix->stream));
     }
@@ -571,7 +602,8 @@ int agp_index_search(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, 
             case AGP_PRECISION_AUTO:
                 rc = (nq < kMaxSmallNq) ? search_diff(ix, xq_dev, nq, k, D_dev, I_dev) : search_tc(ix, xq_dev, nq, k, D_dev, I_dev);
                 break;
-            case AGP_PRECISION_3XTF32: rc = search_tc(ix, xq_dev, nq, k, D_dev, I_dev); break;
+            case AGP_PRECISION_3XTF32:
+            case AGP_PRECISION_3XFP16: rc = search_tc(ix, xq_dev, nq, k, D_dev, I_dev); break;
             case AGP_PRECISION_FP32_SIMT: rc = search_simt(ix, xq_dev, nq, k, D_dev, I_dev); break;
             default: rc = search_diff(ix, xq_dev, nq, k, D_dev, I_dev); break;
         }

@@ -22,6 +22,8 @@
 // and K5, recall_kernel: first rank r with I[q,r] in positives[q] (reference test.py:72-83).
 #include <algorithm>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -66,6 +68,49 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const float* __restrict_
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
         if (lane == 0) norm[r] = acc;
+    }
+}
+
+// K1 for the fp16 split ("3xFP16"): one warp per row, two passes over the (cached) row.
+//   x' = x * 2^-ex with max|x'| in [0.5, 1)   (power-of-two scaling: exact)
+//   hi = fp16(x'), lo = fp16(x' - hi)          -> x' = hi + lo up to ~2^-24 absolute (row max = 1)
+//   scale[r] = factor * 2^ex                   (factor 1 for queries, -2 for database rows)
+__global__ void __launch_bounds__(256) prep_rows_f16_kernel(const float* __restrict__ x, int64_t n, int d, int d_pad,
+                                                            float* __restrict__ norm, __half* __restrict__ hi,
+                                                            __half* __restrict__ lo, float* __restrict__ scale, float factor) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_per_grid = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += warps_per_grid) {
+        const float* row = x + r * d;
+        float acc = 0.f, amax = 0.f;
+        for (int c = lane; c < d; c += 32) {
+            const float v = __ldg(row + c);
+            acc = fmaf(v, v, acc);
+            amax = fmaxf(amax, fabsf(v));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(kFull, acc, o);
+            amax = fmaxf(amax, __shfl_xor_sync(kFull, amax, o));
+        }
+        int ex = 0;
+        if (amax > 0.f && amax < __int_as_float(0x7f800000)) frexpf(amax, &ex);
+        const float inv = ldexpf(1.f, -ex);
+        __half2* hrow = reinterpret_cast<__half2*>(hi + r * d_pad);
+        __half2* lrow = reinterpret_cast<__half2*>(lo + r * d_pad);
+        for (int c2 = lane; c2 < (d_pad >> 1); c2 += 32) {
+            const int c = 2 * c2;
+            const float v0 = (c < d ? __ldg(row + c) : 0.f) * inv;
+            const float v1 = (c + 1 < d ? __ldg(row + c + 1) : 0.f) * inv;
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+            hrow[c2] = __halves2half2(h0, h1);
+            lrow[c2] = __halves2half2(l0, l1);
+        }
+        if (lane == 0) {
+            norm[r] = acc;
+            scale[r] = factor * ldexpf(1.f, ex);
+        }
     }
 }
 
@@ -214,6 +259,14 @@ cudaError_t launch_prep_rows(bool split, const float* x, int64_t n, int d, int d
         prep_rows_kernel<true><<<blocks, 256, 0, st>>>(x, n, d, d_pad, norm, hi, lo);
     else
         prep_rows_kernel<false><<<blocks, 256, 0, st>>>(x, n, d, d_pad, norm, nullptr, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prep_rows_f16(const float* x, int64_t n, int d, int d_pad, float* norm, void* hi, void* lo, float* scale, float factor,
+                                 int max_blocks, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const unsigned blocks = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, max_blocks)));
+    prep_rows_f16_kernel<<<blocks, 256, 0, st>>>(x, n, d, d_pad, norm, static_cast<__half*>(hi), static_cast<__half*>(lo), scale, factor);
     return cudaGetLastError();
 }
 

@@ -1,14 +1,18 @@
 // knn_tc.cuh -- K2 + K3: tcgen05 distance tiles with the top-k selection fused into the epilogue.
 //
-// One CTA (192 threads, 1 per SM) works through a static list of items; an item is one tile of
+// One CTA (320 threads, 1 per SM) works through a static list of items; an item is one tile of
 // 128 queries against one contiguous range ("split") of 256-row database tiles.
 //
-//   warp 0    TMA producer : per BK-float K chunk loads Q_hi, Q_lo (128 rows) and DB_hi, DB_lo
-//                            (256 rows), swizzled K-major, into an mbarrier ring
-//                            (BK = 32: 128B swizzle, 2 stages x 96 KB; BK = 16: 64B swizzle, 4 x 48 KB)
-//   warp 1    MMA issuer   : 3xTF32 -- lo*hi + hi*lo + hi*hi, K-steps of 8, fp32 accumulators in
-//                            TMEM (128 lanes x 256 columns, double buffered = all 512 columns)
-//   warps 2-5 epilogue     : tcgen05.ld 32 columns at a time; thread = one query (TMEM lane);
+//   warp 0    TMA producer : per 128-byte K chunk loads Q_hi, Q_lo (128 rows) and DB_hi, DB_lo (256 rows),
+//                            128B-swizzled K-major, into a 2-stage x 96 KB mbarrier ring
+//   warp 1    MMA issuer   : split-operand product lo*hi + hi*lo + hi*hi per 32-byte K step, fp32 accumulators
+//                            in TMEM (128 lanes x 256 columns, double buffered = all 512 columns).
+//                            KIND_TF32: planes are rna_tf32(x), rna_tf32(x-hi)   (kind::tf32, K = 8,  "3xTF32")
+//                            KIND_F16 : planes are fp16 of the row scaled by a power of two so that
+//                                       max|x'| is in [0.5, 1): hi = fp16(x'), lo = fp16(x'-hi)
+//                                       (kind::f16, K = 16, half the tensor work and bytes per flop, "3xFP16")
+//   warps 2-9 epilogue     : warp w reads TMEM lane group w%4 (32 queries) and column half (w-2)/4 (128 database
+//                            rows) of each tile, tcgen05.ld 32 columns at a time; thread = one query;
 //                            dis = max(0, (|q|^2 + |y|^2) - 2 ip)  (faiss exhaustive_L2sqr_blas formula);
 //                            compare against the query's running k-th best; the rare admissions are
 //                            appended to a per-query candidate buffer (L2-resident), which the warp
@@ -16,6 +20,7 @@
 //
 // The nq x N distance matrix never exists in HBM: only the admitted candidates ([nq, n_splits, 32*E]
 // slots, mostly empty once the shared bound has tightened) leave the SM; K4 merges them.
+// Slot lists are indexed (query, split, column half): 2 * n_splits lists per query.
 // Algorithmic work per item tile: 2 * 128 * 256 * d flop (x3 on the tensor pipe).
 #pragma once
 #include "common.cuh"
@@ -23,27 +28,27 @@
 
 namespace agp {
 
-template <int BK>
+template <int KIND>
 struct TcCfg {
-    static constexpr int kStages = (BK == 32) ? 2 : 4;
-    static constexpr int kABytes = TC_BM * BK * 4;
-    static constexpr int kBBytes = TC_BN * BK * 4;
-    static constexpr int kStageBytes = 2 * (kABytes + kBBytes);
+    static constexpr int kElemBytes = (KIND == KIND_TF32) ? 4 : 2;
+    static constexpr int kBK = TC_KCHUNK_BYTES / kElemBytes;          // elements per K chunk (32 tf32 / 64 fp16)
+    static constexpr int kStages = 2;
+    static constexpr int kABytes = TC_BM * TC_KCHUNK_BYTES;           // 16 KB
+    static constexpr int kBBytes = TC_BN * TC_KCHUNK_BYTES;           // 32 KB
+    static constexpr int kStageBytes = 2 * (kABytes + kBBytes);       // hi + lo planes of A and B: 96 KB
     static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
-    // K-major swizzled operand descriptor: rows of BK*4 bytes, 8-row atoms, swizzle span = row size
-    static constexpr uint64_t kSbo = 8 * BK * 4;                       // bytes between 8-row atoms
-    static constexpr uint64_t kLayout = (BK == 32) ? 2 : 4;            // SWIZZLE_128B : SWIZZLE_64B
 };
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;                       // 2 per SM sub-partition: (TMEM lane group) x (column half)
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;    // TMA warp + MMA warp + epilogue warps
 
-template <int BK>
+// K-major operand tile, rows of 128 B, 128B swizzle: 8-row atoms 1024 B apart
 __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);   // start address
     d |= static_cast<uint64_t>(1) << 16;                        // leading byte offset (unused: one swizzle span per row)
-    d |= static_cast<uint64_t>(TcCfg<BK>::kSbo >> 4) << 32;     // stride byte offset between 8-row atoms
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;                // stride byte offset between 8-row atoms
     d |= static_cast<uint64_t>(1) << 46;                        // descriptor version (sm_100)
-    d |= static_cast<uint64_t>(TcCfg<BK>::kLayout) << 61;       // swizzle mode
+    d |= static_cast<uint64_t>(2) << 61;                        // SWIZZLE_128B
     return d;
 }
 
@@ -82,11 +87,12 @@ __device__ __forceinline__ void tc_compact(int L, bool final, uint64_t* my_buf, 
     __syncwarp();
 }
 
-template <int E, int BK>
+template <int E, int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
               const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, const TcParams p) {
-    using Cfg = TcCfg<BK>;
+    using Cfg = TcCfg<KIND>;
+    constexpr int BK = Cfg::kBK;
     constexpr int CAP = 32 * E;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -114,7 +120,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(&tfull[a], 1);
-                mbar_init(&tempty[a], 128);
+                mbar_init(&tempty[a], 32 * TC_EPI_WARPS);
             }
             fence_barrier_init();
         }
@@ -155,8 +161,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            // instruction descriptor: D fp32, A/B tf32, both K-major, N = 256, M = 128
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
+            // instruction descriptor: D fp32, A/B tf32 (format 2) or fp16 (format 0), both K-major, N = 256, M = 128
+            constexpr uint32_t fmt = (KIND == KIND_TF32) ? 2u : 0u;
+            constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -181,16 +188,22 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
                             mbar_arrive(&empty[stage]);
                         } else {
                             const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-                            const uint64_t a_hi = make_kmajor_desc<BK>(sa);
-                            const uint64_t a_lo = make_kmajor_desc<BK>(sa + Cfg::kABytes);
-                            const uint64_t b_hi = make_kmajor_desc<BK>(sa + 2 * Cfg::kABytes);
-                            const uint64_t b_lo = make_kmajor_desc<BK>(sa + 2 * Cfg::kABytes + Cfg::kBBytes);
+                            const uint64_t a_hi = make_kmajor_desc(sa);
+                            const uint64_t a_lo = make_kmajor_desc(sa + Cfg::kABytes);
+                            const uint64_t b_hi = make_kmajor_desc(sa + 2 * Cfg::kABytes);
+                            const uint64_t b_lo = make_kmajor_desc(sa + 2 * Cfg::kABytes + Cfg::kBBytes);
 #pragma unroll
-                            for (int ks = 0; ks < BK / 8; ++ks) {
-                                const uint64_t off = static_cast<uint64_t>(ks * 2);   // 8 tf32 = 32 B = 2 x 16 B
-                                umma_tf32(tmem_d, a_lo + off, b_hi + off, idesc, (kc | ks) != 0 ? 1u : 0u);
-                                umma_tf32(tmem_d, a_hi + off, b_lo + off, idesc, 1u);
-                                umma_tf32(tmem_d, a_hi + off, b_hi + off, idesc, 1u);
+                            for (int ks = 0; ks < TC_KCHUNK_BYTES / 32; ++ks) {
+                                const uint64_t off = static_cast<uint64_t>(ks * 2);   // one K step = 32 B = 2 x 16 B
+                                if (KIND == KIND_TF32) {
+                                    umma_tf32(tmem_d, a_lo + off, b_hi + off, idesc, (kc | ks) != 0 ? 1u : 0u);
+                                    umma_tf32(tmem_d, a_hi + off, b_lo + off, idesc, 1u);
+                                    umma_tf32(tmem_d, a_hi + off, b_hi + off, idesc, 1u);
+                                } else {
+                                    umma_f16(tmem_d, a_lo + off, b_hi + off, idesc, (kc | ks) != 0 ? 1u : 0u);
+                                    umma_f16(tmem_d, a_hi + off, b_lo + off, idesc, 1u);
+                                    umma_f16(tmem_d, a_hi + off, b_hi + off, idesc, 1u);
+                                }
                             }
                             tc_commit(&empty[stage]);
                         }
@@ -210,6 +223,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
     } else {
         // ------------------------------------------------------------------ epilogue: fused top-k
         const int g = warp & 3;                     // TMEM lane group this warp may read
+        const int half = (warp - 2) >> 2;           // which 128 of the tile's 256 database rows this warp scans
         const int q_local = g * 32 + lane;
         const float inf = __int_as_float(0x7f800000);
         int acc = 0;
@@ -222,11 +236,13 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
             const int q = qt * TC_BM + q_local;
             const bool valid = q < p.nq;
             const float qn = valid ? __ldg(p.qn + q) : 0.f;
+            // KIND_F16: operands were scaled per row by powers of two; ip = acc * sq * sx[col]
+            const float sq = (KIND == KIND_F16 && valid) ? __ldg(p.sq + q) : 1.f;
             float thr = (valid && !p.debug_skip_mma) ? inf : -1.f;
             uint32_t* my_gthr = (valid && p.gthr) ? p.gthr + q : nullptr;
             // the candidate buffer of (query, split) IS its partial list: 32*E slots, the first `cnt` valid
             // (after a compaction the first k are sorted); invalid tail queries never admit anything
-            const size_t slot = static_cast<size_t>(valid ? q : 0) * p.n_splits + split;
+            const size_t slot = (static_cast<size_t>(valid ? q : 0) * p.n_splits + split) * 2 + half;
             uint64_t* my_buf = p.partial + slot * CAP;
             int cnt = 0;
             for (int t = t0; t < t1; ++t) {
@@ -237,7 +253,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
                 if (p.dbg) w_tfull += clock64() - c2;
                 tc_fence_after();
 #pragma unroll 1
-                for (int cc = 0; cc < TC_BN / 32; ++cc) {
+                for (int cc = half * (TC_BN / 64); cc < (half + 1) * (TC_BN / 64); ++cc) {
                     uint32_t r[32];
                     tmem_ld32(tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * TC_BN + cc * 32, r);
                     const int col0 = t * TC_BN + cc * 32;
@@ -248,11 +264,22 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
                         const float4 yy = __ldg(y4 + v);
                         y[4 * v] = yy.x; y[4 * v + 1] = yy.y; y[4 * v + 2] = yy.z; y[4 * v + 3] = yy.w;
                     }
+                    float w[32];
+                    if (KIND == KIND_F16) {
+                        const float4* w4 = reinterpret_cast<const float4*>(p.wx + col0);     // -2 * 2^ex per column
+#pragma unroll
+                        for (int v = 0; v < 8; ++v) {
+                            const float4 ww = __ldg(w4 + v);
+                            w[4 * v] = ww.x; w[4 * v + 1] = ww.y; w[4 * v + 2] = ww.z; w[4 * v + 3] = ww.w;
+                        }
+                    }
                     tmem_ld_wait();
                     float m = inf;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
-                        float dis = fmaf(-2.f, __uint_as_float(r[c]), qn + y[c]);
+                        float dis;
+                        if (KIND == KIND_F16) dis = fmaf(__uint_as_float(r[c]) * sq, w[c], qn + y[c]);
+                        else dis = fmaf(-2.f, __uint_as_float(r[c]), qn + y[c]);
                         dis = fmaxf(dis, 0.f);
                         y[c] = dis;
                         m = fminf(m, dis);
@@ -300,14 +327,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
 template <int E>
 cudaError_t launch_knn_tc(const CUtensorMap& qhi, const CUtensorMap& qlo, const CUtensorMap& bhi, const CUtensorMap& blo,
                           const TcParams& p, int grid, cudaStream_t st) {
-    if (p.bk == 16) {
-        cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<E, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16>::kSmemBytes);
+    if (p.kind == KIND_F16) {
+        cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<E, KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<KIND_F16>::kSmemBytes);
         if (e != cudaSuccess) return e;
-        knn_tc_kernel<E, 16><<<grid, TC_THREADS, TcCfg<16>::kSmemBytes, st>>>(qhi, qlo, bhi, blo, p);
+        knn_tc_kernel<E, KIND_F16><<<grid, TC_THREADS, TcCfg<KIND_F16>::kSmemBytes, st>>>(qhi, qlo, bhi, blo, p);
     } else {
-        cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<E, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32>::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<E, KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<KIND_TF32>::kSmemBytes);
         if (e != cudaSuccess) return e;
-        knn_tc_kernel<E, 32><<<grid, TC_THREADS, TcCfg<32>::kSmemBytes, st>>>(qhi, qlo, bhi, blo, p);
+        knn_tc_kernel<E, KIND_TF32><<<grid, TC_THREADS, TcCfg<KIND_TF32>::kSmemBytes, st>>>(qhi, qlo, bhi, blo, p);
     }
     return cudaGetLastError();
 }

@@ -9,11 +9,14 @@ namespace agp {
 
 constexpr int TC_BM = 128;            // queries per tile (UMMA M, TMEM lanes)
 constexpr int TC_BN = 256;            // database rows per tile (UMMA N, TMEM columns)
-constexpr int TC_KPAD = 32;           // descriptor dimension is zero-padded to a multiple of this (largest K chunk)
+constexpr int TC_KCHUNK_BYTES = 128;  // one K chunk = one 128-byte swizzle row per operand row
+constexpr int TC_KPAD = 64;           // descriptor dimension is zero-padded to a multiple of this (64 fp16 = 128 B)
+constexpr int KIND_TF32 = 0;          // operand planes hold TF32 values in fp32 containers ("3xTF32")
+constexpr int KIND_F16 = 1;           // operand planes hold fp16 of the power-of-two scaled row ("3xFP16")
 constexpr int kMaxSmallNq = 20;       // faiss distance_compute_blas_threshold
 
 struct TcParams {
-    int bk;                 // fp32 per K chunk: 32 (128B swizzle, 2 stages) or 16 (64B swizzle, 4 stages)
+    int kind;               // KIND_TF32 or KIND_F16
     int debug_skip_mma;     // bandwidth probe: TMA ring only, no MMA, no selection
     int nq;
     int d_pad;
@@ -23,8 +26,10 @@ struct TcParams {
     int n_dbtiles;
     const float* qn;        // [nq]
     const float* yn;        // [n_dbtiles * 256], +inf beyond the last database row
-    uint64_t* partial;      // [nq][n_splits][32*E] candidate slots (unsorted beyond the first k)
-    int* pcount;            // [nq][n_splits] valid slots
+    const float* sq;        // KIND_F16: [nq] query row scale 2^ex (x = x' * 2^ex)
+    const float* wx;        // KIND_F16: [n_dbtiles * 256] -2 * 2^ex of each database row
+    uint64_t* partial;      // [nq][n_splits][2][32*E] candidate slots (unsorted beyond the first k)
+    int* pcount;            // [nq][n_splits][2] valid slots
     long long* dbg;         // [grid][8] cycle counters (development), nullptr = off
     uint32_t* gthr;         // [nq] shared pruning bound (fp32 bits, +inf initially); nullptr disables sharing
 };
@@ -60,6 +65,9 @@ cudaError_t launch_rerank(const float* xq, const float* xb, int d, const int64_t
 // plain launchers (k_misc.cu)
 cudaError_t launch_prep_rows(bool split, const float* x, int64_t n, int d, int d_pad, float* norm, float* hi, float* lo, int max_blocks,
                              cudaStream_t st);
+// fp16 planes of the power-of-two scaled rows; scale[r] = factor * 2^ex (factor = 1 for queries, -2 for database rows)
+cudaError_t launch_prep_rows_f16(const float* x, int64_t n, int d, int d_pad, float* norm, void* hi, void* lo, float* scale, float factor,
+                                 int max_blocks, cudaStream_t st);
 cudaError_t launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st);
 cudaError_t launch_diff_small(const float* xq, int nq, const float* xb, int64_t n, int d, float* dist, int64_t ld, int num_sms,
                               cudaStream_t st);

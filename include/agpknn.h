@@ -35,10 +35,11 @@ typedef struct agp_index agp_index;
 enum agp_mem_kind { AGP_MEM_HOST = 0, AGP_MEM_DEVICE = 1 };
 
 enum agp_precision {
-    AGP_PRECISION_AUTO = 0,       /* faiss's own switch: nq < 20 exact difference form, else 3xTF32 tensor cores */
+    AGP_PRECISION_AUTO = 0,       /* faiss's own switch: nq < 20 exact difference form, else tensor cores (3xFP16) */
     AGP_PRECISION_FP32_SIMT = 1,  /* fp32 FMA on CUDA cores, expansion form (reference/cross-check mode)       */
     AGP_PRECISION_3XTF32 = 2,     /* always the tcgen05 3xTF32 fused kernel                                    */
-    AGP_PRECISION_EXACT_DIFF = 3  /* always the difference form (nq processed in groups of < 20)               */
+    AGP_PRECISION_EXACT_DIFF = 3, /* always the difference form (nq processed in groups of < 20)               */
+    AGP_PRECISION_3XFP16 = 4      /* always the tcgen05 kernel on fp16 hi/lo planes of power-of-two scaled rows */
 };
 
 enum agp_error {

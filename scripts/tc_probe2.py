@@ -10,7 +10,7 @@ def run(cfg, reps=5):
     c = synth.CONFIGS[cfg]
     xb = synth.descriptors(c["n"], c["d"], c["seed"], "db")
     xq = synth.descriptors(c["nq"], c["d"], c["seed"] + 7, "q")
-    ix = agp.IndexFlatL2(c["d"], precision="3xtf32")
+    ix = agp.IndexFlatL2(c["d"], precision=os.environ.get("PREC", "3xtf32"))
     ix.add(xb)
     xq_dev = torch.from_numpy(xq).cuda()
     ix.search(xq_dev, c["k"]); torch.cuda.synchronize()

@@ -16,7 +16,7 @@ from oracle import flatl2_oracle as orc
 from tests.helpers import make_mining_problem, reference_recall_loop
 
 GOLDEN = sorted((Path(__file__).parent / "golden").glob("*.npz"))
-MODES = ["auto", "3xtf32", "fp32_simt", "exact_diff"]
+MODES = ["auto", "3xtf32", "3xfp16", "fp32_simt", "exact_diff"]
 FLT_MAX = np.float32(3.4028234663852886e38)
 
 
@@ -53,7 +53,7 @@ SHAPES = [  # nq, n, d, k
 ]
 
 
-@pytest.mark.parametrize("precision", ["auto", "3xtf32", "fp32_simt"])
+@pytest.mark.parametrize("precision", ["auto", "3xtf32", "3xfp16", "fp32_simt"])
 @pytest.mark.parametrize("nq,n,d,k", SHAPES)
 def test_random_shapes_match_oracle(nq, n, d, k, precision):
     rng = np.random.default_rng(nq * 7 + n * 3 + d + k)
