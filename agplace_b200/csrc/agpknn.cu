@@ -178,6 +178,11 @@ static int grow(agp_index* ix, int64_t need) {
 // register budget of the fused epilogue: 32*E candidate slots with enough slack above k that the
 // reservoir is compacted rarely (slots - 32 - k new admissions per sort); E <= 16
 static int tc_regs_for_k(int k) {
+    const char* env_e = getenv("AGP_TC_E");      // development override
+    if (env_e) {
+        const int e = atoi(env_e);
+        if ((e == 2 || e == 4 || e == 8 || e == 16) && 32 * e - 32 > k) return e;
+    }
     int e = 2;
     while (32 * e < k + k / 2 + 32 && e < 16) e <<= 1;
     return e;
@@ -355,16 +360,23 @@ static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, floa
         p.k = kc;
         p.n_qtiles = (nqc + TC_BM - 1) / TC_BM;
         p.n_dbtiles = n_dbtiles;
-        p.n_splits = choose_splits(p.n_qtiles, n_dbtiles, ix->num_sms);
-        const int n_items = p.n_qtiles * p.n_splits;
-        const int grid = std::min(n_items, ix->num_sms);
+        // whole waves of query tiles sweep the database unsplit; the last partial wave is split to fill the SMs
+        const int sms = ix->num_sms;
+        p.n_full_items = (p.n_qtiles / sms) * sms;
+        const int rem_tiles = p.n_qtiles - p.n_full_items;
+        p.rem_splits = rem_tiles > 0 ? std::max(1, std::min({sms / rem_tiles, n_dbtiles, 64})) : 1;
+        p.list_splits = rem_tiles > 0 ? p.rem_splits : 1;
+        p.n_items = p.n_full_items + rem_tiles * p.rem_splits;
+        const int n_items = p.n_items;
+        const int grid = std::min(n_items, sms);
         const int slots = 32 * E;
-        const int n_lists = 2 * p.n_splits;        // (split, column half) lists per query
+        const int n_lists = 2 * p.list_splits;     // (split, column half) lists per query
         CKR(ensure(ix->cand, static_cast<size_t>(nqc) * n_lists * sizeof(int)));
         CKR(ensure(ix->partial, static_cast<size_t>(nqc) * n_lists * slots * sizeof(uint64_t)));
         p.qn = static_cast<const float*>(ix->qn.p);
         p.yn = ix->yn;
         p.pcount = static_cast<int*>(ix->cand.p);
+        CK(cudaMemsetAsync(ix->cand.p, 0, static_cast<size_t>(nqc) * n_lists * sizeof(int), ix->stream));
         p.partial = static_cast<uint64_t*>(ix->partial.p);
         const char* env_share = getenv("AGP_TC_SHARE_BOUND");
         p.gthr = nullptr;
@@ -391,9 +403,20 @@ static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, floa
             double s[8] = {0};
             for (int b = 0; b < grid; ++b)
                 for (int j = 0; j < 8; ++j) s[j] += static_cast<double>(h[b * 8 + j]) / grid;
+            std::vector<int> pc(static_cast<size_t>(nqc) * n_lists);
+            CK(cudaMemcpy(pc.data(), ix->cand.p, pc.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            double tot = 0; int mx = 0; std::vector<double> per_list(n_lists, 0.0);
+            for (int qq = 0; qq < nqc; ++qq) {
+                int t = 0;
+                for (int l = 0; l < n_lists; ++l) { t += pc[static_cast<size_t>(qq) * n_lists + l]; per_list[l] += pc[static_cast<size_t>(qq) * n_lists + l]; }
+                tot += t; mx = std::max(mx, t);
+            }
+            fprintf(stderr, "[agp tc dbg] candidates per query: mean=%.1f max=%d; per list:", tot / nqc, mx);
+            for (int l = 0; l < n_lists; ++l) fprintf(stderr, " %.0f", per_list[l] / nqc);
+            fprintf(stderr, "\n");
             fprintf(stderr, "[agp tc dbg] grid=%d splits=%d items=%d | mma: total=%.0f wait_full=%.0f wait_tempty=%.0f | epi(w2): total=%.0f "
                             "wait_tfull=%.0f compact=%.0f n_compact=%.0f (cycles, mean per CTA)\n",
-                    grid, p.n_splits, n_items, s[0], s[1], s[2], s[3], s[4], s[5], s[6]);
+                    grid, p.rem_splits, n_items, s[0], s[1], s[2], s[3], s[4], s[5], s[6]);
         }
         if (!rerank) {
             CKR(DISPATCH_E32(k, launch_merge_ragged, static_cast<const uint64_t*>(ix->partial.p), static_cast<const int*>(ix->cand.p), slots,

@@ -18,9 +18,9 @@
 //                            appended to a per-query candidate buffer (L2-resident), which the warp
 //                            compacts with a register bitonic sort when it fills (reservoir select).
 //
-// The nq x N distance matrix never exists in HBM: only the admitted candidates ([nq, n_splits, 32*E]
+// The nq x N distance matrix never exists in HBM: only the admitted candidates ([nq, list_splits, 2, 32*E]
 // slots, mostly empty once the shared bound has tightened) leave the SM; K4 merges them.
-// Slot lists are indexed (query, split, column half): 2 * n_splits lists per query.
+// Slot lists are indexed (query, split, column half); unsplit query tiles only ever use split 0.
 // Algorithmic work per item tile: 2 * 128 * 256 * d flop (x3 on the tensor pipe).
 #pragma once
 #include "common.cuh"
@@ -38,6 +38,30 @@ struct TcCfg {
     static constexpr int kStageBytes = 2 * (kABytes + kBBytes);       // hi + lo planes of A and B: 96 KB
     static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
 };
+// Work item = (query tile, range of database tiles).  Query tiles that fill whole waves of CTAs are NOT
+// split: one CTA sweeps the entire database for them, so a query's running top-k (and its threshold)
+// lives in one thread for the whole sweep.  Only the last partial wave of query tiles is split into
+// `rem_splits` database ranges so that it, too, occupies every SM.
+struct TcItem {
+    int qt, split, t0, t1;
+};
+__device__ __forceinline__ TcItem tc_decode_item(const TcParams& p, int item) {
+    TcItem it;
+    int nsp = 1;
+    if (item < p.n_full_items) {
+        it.qt = item;
+        it.split = 0;
+    } else {
+        const int r = item - p.n_full_items;
+        it.qt = p.n_full_items + r / p.rem_splits;
+        it.split = r - (r / p.rem_splits) * p.rem_splits;
+        nsp = p.rem_splits;
+    }
+    it.t0 = static_cast<int>(static_cast<int64_t>(it.split) * p.n_dbtiles / nsp);
+    it.t1 = static_cast<int>(static_cast<int64_t>(it.split + 1) * p.n_dbtiles / nsp);
+    return it;
+}
+
 constexpr int TC_EPI_WARPS = 8;                       // 2 per SM sub-partition: (TMEM lane group) x (column half)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;    // TMA warp + MMA warp + epilogue warps
 
@@ -132,7 +156,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-    const int n_items = p.n_qtiles * p.n_splits;
+    const int n_items = p.n_items;
     const int num_kc = p.d_pad / BK;
 
     if (warp == 0) {
@@ -141,9 +165,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int split = item / p.n_qtiles, qt = item - split * p.n_qtiles;
-                const int t0 = static_cast<int>(static_cast<int64_t>(split) * p.n_dbtiles / p.n_splits);
-                const int t1 = static_cast<int>(static_cast<int64_t>(split + 1) * p.n_dbtiles / p.n_splits);
+                const TcItem it = tc_decode_item(p, item);
+                const int qt = it.qt, t0 = it.t0, t1 = it.t1;
                 for (int t = t0; t < t1; ++t) {
                     for (int kc = 0; kc < num_kc; ++kc) {
                         mbar_wait(&empty[stage], phase ^ 1);
@@ -170,9 +193,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
             uint32_t acc_phase = 0;
             long long w_full = 0, w_tempty = 0, t_begin = p.dbg ? clock64() : 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int split = item / p.n_qtiles;
-                const int t0 = static_cast<int>(static_cast<int64_t>(split) * p.n_dbtiles / p.n_splits);
-                const int t1 = static_cast<int>(static_cast<int64_t>(split + 1) * p.n_dbtiles / p.n_splits);
+                const TcItem it = tc_decode_item(p, item);
+                const int t0 = it.t0, t1 = it.t1;
                 for (int t = t0; t < t1; ++t) {
                     long long c0 = p.dbg ? clock64() : 0;
                     mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -230,9 +252,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
         uint32_t acc_phase = 0;
         long long w_tfull = 0, t_compact = 0, n_compact = 0, e_begin = p.dbg ? clock64() : 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int split = item / p.n_qtiles, qt = item - split * p.n_qtiles;
-            const int t0 = static_cast<int>(static_cast<int64_t>(split) * p.n_dbtiles / p.n_splits);
-            const int t1 = static_cast<int>(static_cast<int64_t>(split + 1) * p.n_dbtiles / p.n_splits);
+            const TcItem it = tc_decode_item(p, item);
+            const int split = it.split, qt = it.qt, t0 = it.t0, t1 = it.t1;
             const int q = qt * TC_BM + q_local;
             const bool valid = q < p.nq;
             const float qn = valid ? __ldg(p.qn + q) : 0.f;
@@ -242,7 +263,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
             uint32_t* my_gthr = (valid && p.gthr) ? p.gthr + q : nullptr;
             // the candidate buffer of (query, split) IS its partial list: 32*E slots, the first `cnt` valid
             // (after a compaction the first k are sorted); invalid tail queries never admit anything
-            const size_t slot = (static_cast<size_t>(valid ? q : 0) * p.n_splits + split) * 2 + half;
+            const size_t slot = (static_cast<size_t>(valid ? q : 0) * p.list_splits + split) * 2 + half;
             uint64_t* my_buf = p.partial + slot * CAP;
             int cnt = 0;
             for (int t = t0; t < t1; ++t) {

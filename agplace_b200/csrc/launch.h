@@ -22,14 +22,17 @@ struct TcParams {
     int d_pad;
     int k;
     int n_qtiles;
-    int n_splits;
+    int n_full_items;       // query tiles swept unsplit (multiple of the grid size); item i < n_full_items <-> query tile i
+    int rem_splits;         // database ranges each remaining query tile is split into
+    int list_splits;        // candidate lists are indexed [q][list_splits][2]
+    int n_items;            // n_full_items + (n_qtiles - n_full_items) * rem_splits
     int n_dbtiles;
     const float* qn;        // [nq]
     const float* yn;        // [n_dbtiles * 256], +inf beyond the last database row
     const float* sq;        // KIND_F16: [nq] query row scale 2^ex (x = x' * 2^ex)
     const float* wx;        // KIND_F16: [n_dbtiles * 256] -2 * 2^ex of each database row
-    uint64_t* partial;      // [nq][n_splits][2][32*E] candidate slots (unsorted beyond the first k)
-    int* pcount;            // [nq][n_splits][2] valid slots
+    uint64_t* partial;      // [nq][list_splits][2][32*E] candidate slots (unsorted beyond the first k)
+    int* pcount;            // [nq][list_splits][2] valid slots (zeroed before launch)
     long long* dbg;         // [grid][8] cycle counters (development), nullptr = off
     uint32_t* gthr;         // [nq] shared pruning bound (fp32 bits, +inf initially); nullptr disables sharing
 };

@@ -110,19 +110,43 @@ cudaError_t launch_merge_lists(const float* Din, int64_t d_stride, const int64_t
     return cudaGetLastError();
 }
 
-// Ragged variant for the fused kernel's output: list (q, s) holds pcount[q*S+s] unsorted keys in a slot
-// of `slot_stride` entries.  One warp per query appends list after list into a 32*E-entry shared
-// staging buffer and sorts it (keeping the best k) whenever it is full.
+// Ragged variant for the fused kernel's output: list (q, l) holds pcount[q*L+l] unsorted keys in a slot of
+// `slot_stride` entries.  One warp per query: the counts are scanned into a shared prefix array, then the
+// concatenation of all lists is gathered lane-parallel (binary search of the prefix per entry, so all global
+// loads are independent and in flight together) into a 32*E-entry staging buffer that is sorted -- keeping
+// the best k -- whenever it fills.
+constexpr int kMaxRaggedLists = 256;
+
 template <int E>
 __global__ void __launch_bounds__(128) merge_ragged_kernel(const uint64_t* __restrict__ partial, const int* __restrict__ pcount,
                                                            int slot_stride, int64_t nq, int n_lists, int k, int64_t id_base,
                                                            float* __restrict__ D, int64_t* __restrict__ I) {
     constexpr int CAP = 32 * E;
-    extern __shared__ uint64_t sstage[];   // [warps][CAP]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
+    extern __shared__ uint64_t sstage[];   // [warps][CAP] keys, then [warps][kMaxRaggedLists + 1] prefix
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int64_t q = static_cast<int64_t>(blockIdx.x) * warps + warp;
     if (q >= nq) return;
     uint64_t* buf = sstage + warp * CAP;
+    int* prefix = reinterpret_cast<int*>(sstage + warps * CAP) + warp * (kMaxRaggedLists + 1);
+    // exclusive scan of the list lengths (n_lists <= 256: 8 per lane)
+    int running = 0;
+    for (int base = 0; base < n_lists; base += 32) {
+        const int l = base + lane;
+        const int c = (l < n_lists) ? pcount[q * n_lists + l] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (l < n_lists) prefix[l] = running + incl - c;
+        running += __shfl_sync(kFull, incl, 31);
+    }
+    if (lane == 0) prefix[n_lists] = running;
+    __syncwarp();
+    const int total = running;
+    const uint64_t* src = partial + q * n_lists * static_cast<int64_t>(slot_stride);
+
     uint64_t key[E];
     int fill = 0;
     auto sort_keep = [&]() {
@@ -136,17 +160,21 @@ __global__ void __launch_bounds__(128) merge_ragged_kernel(const uint64_t* __res
         fill = fill < k ? fill : k;
         __syncwarp();
     };
-    for (int s = 0; s < n_lists; ++s) {
-        const int c = pcount[q * n_lists + s];
-        const uint64_t* src = partial + (q * n_lists + s) * slot_stride;
-        int off = 0;
-        while (off < c) {
-            if (fill == CAP) sort_keep();
-            const int take = min(CAP - fill, c - off);
-            for (int i = lane; i < take; i += 32) buf[fill + i] = __ldcg(src + off + i);
-            fill += take;
-            off += take;
+    int done = 0;
+    while (done < total) {
+        const int take = min(CAP - fill, total - done);
+        for (int i = lane; i < take; i += 32) {
+            const int e = done + i;
+            int lo = 0, hi = n_lists;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (prefix[mid] <= e) lo = mid; else hi = mid;
+            }
+            buf[fill + i] = __ldcg(src + static_cast<int64_t>(lo) * slot_stride + (e - prefix[lo]));
         }
+        fill += take;
+        done += take;
+        if (done < total) sort_keep();
     }
     sort_keep();
 #pragma unroll
@@ -164,8 +192,10 @@ template <int E>
 cudaError_t launch_merge_ragged(const uint64_t* partial, const int* pcount, int slot_stride, int64_t nq, int n_lists, int k,
                                 int64_t id_base, float* D, int64_t* I, cudaStream_t st) {
     constexpr int warps = 4;
-    merge_ragged_kernel<E><<<static_cast<unsigned>((nq + warps - 1) / warps), warps * 32, warps * 32 * E * sizeof(uint64_t), st>>>(
-        partial, pcount, slot_stride, nq, n_lists, k, id_base, D, I);
+    if (n_lists > kMaxRaggedLists) return cudaErrorInvalidValue;
+    const size_t smem = warps * 32 * E * sizeof(uint64_t) + warps * (kMaxRaggedLists + 1) * sizeof(int);
+    merge_ragged_kernel<E><<<static_cast<unsigned>((nq + warps - 1) / warps), warps * 32, smem, st>>>(partial, pcount, slot_stride, nq,
+                                                                                                    n_lists, k, id_base, D, I);
     return cudaGetLastError();
 }
 
