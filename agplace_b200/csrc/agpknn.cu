@@ -355,6 +355,7 @@ static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, floa
         p.sq = static_cast<const float*>(ix->sq.p);
         p.wx = ix->wx;
         p.debug_skip_mma = skip_mma;
+        { const char* e = getenv("AGP_TC_COMPACT"); p.compact_mode = (e && strcmp(e, "sort") == 0) ? 1 : 0; }
         p.nq = nqc;
         p.d_pad = ix->d_pad;
         p.k = kc;
@@ -372,7 +373,7 @@ static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, floa
         const int slots = 32 * E;
         const int n_lists = 2 * p.list_splits;     // (split, column half) lists per query
         CKR(ensure(ix->cand, static_cast<size_t>(nqc) * n_lists * sizeof(int)));
-        CKR(ensure(ix->partial, static_cast<size_t>(nqc) * n_lists * slots * sizeof(uint64_t)));
+        CKR(ensure(ix->partial, static_cast<size_t>(p.n_qtiles) * TC_BM * n_lists * slots * sizeof(uint64_t)));
         p.qn = static_cast<const float*>(ix->qn.p);
         p.yn = ix->yn;
         p.pcount = static_cast<int*>(ix->cand.p);

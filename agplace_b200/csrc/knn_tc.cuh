@@ -86,20 +86,22 @@ __device__ __forceinline__ float bound_to_thr(uint32_t bits) {
     return __uint_as_float(bits >= 0x7f800000u ? 0x7f800000u : bits + 1u);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Candidate slots of the 32 queries of one epilogue warp are interleaved: entry i of lane l lives at
+// wbuf[i * 32 + l], so "every lane touches its own entry i" is one coalesced 256-byte access.
+
+// Exact fallback: the whole warp sorts lane L's slots (register bitonic network) and keeps the k best.
 template <int E>
-__device__ __forceinline__ void tc_compact(int L, bool final, uint64_t* my_buf, int& cnt, float& thr, int lane, int k,
-                                           uint64_t* out, uint32_t* my_gthr) {
-    uint64_t* buf = reinterpret_cast<uint64_t*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_buf), L));
+__device__ __noinline__ void tc_compact_sort(int L, uint64_t* wbuf, int& cnt, float& thr, int lane, int k, uint32_t* my_gthr) {
     const int n = __shfl_sync(kFull, cnt, L);
     __syncwarp();
     uint64_t key[E];
 #pragma unroll
-    for (int j = 0; j < E; ++j) key[j] = (j * 32 + lane < n) ? __ldcg(buf + j * 32 + lane) : kEmptyKey;
+    for (int j = 0; j < E; ++j) key[j] = (j * 32 + lane < n) ? __ldcg(wbuf + (j * 32 + lane) * 32 + L) : kEmptyKey;
     warp_bitonic_sort<E>(key, lane);
-    uint64_t* dst = final ? out : buf;
 #pragma unroll
     for (int j = 0; j < E; ++j)
-        if (j * 32 + lane < k) __stcg(dst + j * 32 + lane, key[j]);
+        if (j * 32 + lane < k) __stcg(wbuf + (j * 32 + lane) * 32 + L, key[j]);
     const float kth = key_dist(warp_get<E>(key, k - 1));
     if (lane == L) {
         if (n >= k) {
@@ -109,6 +111,95 @@ __device__ __forceinline__ void tc_compact(int L, bool final, uint64_t* my_buf, 
         cnt = n < k ? n : k;
     }
     __syncwarp();
+}
+
+__device__ __forceinline__ void sort16_f32(float (&s)[16]) {
+#pragma unroll
+    for (int size = 2; size <= 16; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool asc = ((i & size) == 0);
+                    const float a = s[i], b = s[j];
+                    s[i] = asc ? fminf(a, b) : fmaxf(a, b);
+                    s[j] = asc ? fmaxf(a, b) : fminf(a, b);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float slot_dist(const uint64_t* p) {     // high word of a packed key
+    return __uint_as_float(__ldcg(reinterpret_cast<const uint32_t*>(p) + 1));
+}
+
+// Lane-parallel compaction: every lane with more than k + 8 candidates shrinks ITS OWN list at the same
+// time (SIMT), so a burst in which all 32 queries of the warp overflow together costs one pass instead
+// of 32 warp-wide sorts.  Per lane: sample 16 distances of its list, sort the sample in registers, count in
+// ONE pass over the list how many entries lie at or below each sample value, pick the smallest sample value
+// with count >= k as the new pruning distance, and drop everything above it in place.  Any such value is a
+// valid bound (k entries at or below it exist; later rows at exactly that distance lose the index
+// tie-break), and its rank is within ~n/16 of k.  Lanes that still cannot free enough slots (pathological
+// ties) fall back to the exact sort.
+template <int E>
+__device__ __noinline__ void tc_compact_lanes(uint64_t* wbuf, int& cnt, float& thr, int lane, int k, uint32_t* my_gthr) {
+    constexpr int CAP = 32 * E;
+    const float inf = __int_as_float(0x7f800000);
+    const bool act = cnt > k + 8;
+    const int n = act ? cnt : 0;
+    const int nmax = __reduce_max_sync(kFull, n);
+    const uint64_t* mine = wbuf + lane;
+    float s[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s[j] = act ? slot_dist(mine + ((j * n) >> 4) * 32) : inf;
+    sort16_f32(s);
+    int c[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) c[j] = 0;
+    for (int i0 = 0; i0 < nmax; i0 += 32) {     // 32 independent loads in flight per round trip
+        float d[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) d[u] = (i0 + u < n) ? slot_dist(mine + (i0 + u) * 32) : inf;
+#pragma unroll
+        for (int u = 0; u < 32; ++u)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) c[j] += (d[u] <= s[j]) ? 1 : 0;
+    }
+    // smallest sample value that still keeps at least k entries
+    float pd = inf;
+    int pc = n;
+#pragma unroll
+    for (int j = 15; j >= 0; --j)
+        if (c[j] >= k) { pd = s[j]; pc = c[j]; }
+    const bool shrink = act && pc < n;
+    int w = 0;
+    for (int i0 = 0; i0 < nmax; i0 += 16) {
+        uint64_t key[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) key[u] = (shrink && i0 + u < n) ? __ldcg(mine + (i0 + u) * 32) : kEmptyKey;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            if (shrink && i0 + u < n && key_dist(key[u]) <= pd) {
+                __stcg(wbuf + w * 32 + lane, key[u]);
+                ++w;
+            }
+        }
+    }
+    if (shrink) {
+        cnt = pc;
+        thr = fminf(thr, pd);
+        if (my_gthr) atomicMin(my_gthr, __float_as_uint(pd));
+    }
+    // anything still too full gets the exact treatment
+    unsigned need = __ballot_sync(kFull, cnt > CAP - 32);
+    while (need) {
+        const int L = __ffs(need) - 1;
+        need &= need - 1;
+        tc_compact_sort<E>(L, wbuf, cnt, thr, lane, k, my_gthr);
+    }
 }
 
 template <int E, int KIND>
@@ -261,10 +352,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
             const float sq = (KIND == KIND_F16 && valid) ? __ldg(p.sq + q) : 1.f;
             float thr = (valid && !p.debug_skip_mma) ? inf : -1.f;
             uint32_t* my_gthr = (valid && p.gthr) ? p.gthr + q : nullptr;
-            // the candidate buffer of (query, split) IS its partial list: 32*E slots, the first `cnt` valid
-            // (after a compaction the first k are sorted); invalid tail queries never admit anything
-            const size_t slot = (static_cast<size_t>(valid ? q : 0) * p.list_splits + split) * 2 + half;
-            uint64_t* my_buf = p.partial + slot * CAP;
+            // the candidate slots of (query, split, half) ARE its partial list: 32*E slots, the first `cnt` valid,
+            // unsorted; invalid tail queries never admit anything
+            const size_t slot = (static_cast<size_t>(valid ? q : 0) * p.list_splits + split) * 2 + half;      // pcount index
+            const size_t bundle = (static_cast<size_t>((qt * TC_BM + g * 32) >> 5) * p.list_splits + split) * 2 + half;
+            uint64_t* wbuf = p.partial + bundle * (32 * CAP);     // this warp's 32 interleaved slot lists
             int cnt = 0;
             for (int t = t0; t < t1; ++t) {
                 // pick up bounds other splits of this query have published since the last tile
@@ -309,19 +401,25 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant_
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
                             if (y[c] < thr) {
-                                __stcg(my_buf + cnt, pack_key(y[c], static_cast<uint32_t>(col0 + c)));
+                                __stcg(wbuf + cnt * 32 + lane, pack_key(y[c], static_cast<uint32_t>(col0 + c)));
                                 ++cnt;
                             }
                         }
                     }
-                    unsigned need = __ballot_sync(kFull, cnt > CAP - 32);
-                    long long c3 = (p.dbg && need) ? clock64() : 0;
-                    if (p.dbg && need) n_compact += __popc(need);
-                    const bool had = need != 0;
-                    while (need) {
-                        const int L = __ffs(need) - 1;
-                        need &= need - 1;
-                        tc_compact<E>(L, false, my_buf, cnt, thr, lane, p.k, nullptr, my_gthr);
+                    const bool had = __any_sync(kFull, cnt > CAP - 32);
+                    long long c3 = (p.dbg && had) ? clock64() : 0;
+                    if (had) {
+                        if (p.dbg) n_compact += 1;
+                        if (p.compact_mode == 0) {
+                            tc_compact_lanes<E>(wbuf, cnt, thr, lane, p.k, my_gthr);
+                        } else {
+                            unsigned need = __ballot_sync(kFull, cnt > CAP - 32);
+                            while (need) {
+                                const int L = __ffs(need) - 1;
+                                need &= need - 1;
+                                tc_compact_sort<E>(L, wbuf, cnt, thr, lane, p.k, my_gthr);
+                            }
+                        }
                     }
                     if (p.dbg && had) t_compact += clock64() - c3;
                 }

@@ -17,6 +17,7 @@ constexpr int kMaxSmallNq = 20;       // faiss distance_compute_blas_threshold
 
 struct TcParams {
     int kind;               // KIND_TF32 or KIND_F16
+    int compact_mode;       // 0 = lane-parallel pivot compaction (+ exact fallback), 1 = exact warp sort only
     int debug_skip_mma;     // bandwidth probe: TMA ring only, no MMA, no selection
     int nq;
     int d_pad;
@@ -31,7 +32,7 @@ struct TcParams {
     const float* yn;        // [n_dbtiles * 256], +inf beyond the last database row
     const float* sq;        // KIND_F16: [nq] query row scale 2^ex (x = x' * 2^ex)
     const float* wx;        // KIND_F16: [n_dbtiles * 256] -2 * 2^ex of each database row
-    uint64_t* partial;      // [nq][list_splits][2][32*E] candidate slots (unsorted beyond the first k)
+    uint64_t* partial;      // [nq/32][list_splits][2][32*E][32] candidate slots, interleaved over the 32 queries of a warp
     int* pcount;            // [nq][list_splits][2] valid slots (zeroed before launch)
     long long* dbg;         // [grid][8] cycle counters (development), nullptr = off
     uint32_t* gthr;         // [nq] shared pruning bound (fp32 bits, +inf initially); nullptr disables sharing

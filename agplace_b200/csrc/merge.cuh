@@ -110,8 +110,9 @@ cudaError_t launch_merge_lists(const float* Din, int64_t d_stride, const int64_t
     return cudaGetLastError();
 }
 
-// Ragged variant for the fused kernel's output: list (q, l) holds pcount[q*L+l] unsorted keys in a slot of
-// `slot_stride` entries.  One warp per query: the counts are scanned into a shared prefix array, then the
+// Ragged variant for the fused kernel's output: list (q, l) holds pcount[q*L+l] unsorted keys.  Lists are
+// stored in bundles of 32 consecutive queries, interleaved: entry e of list l of query q sits at
+// ((q/32) * L + l) * 32 * slot_stride + e * 32 + (q % 32)   (slot_stride = slots per list).  One warp per query: the counts are scanned into a shared prefix array, then the
 // concatenation of all lists is gathered lane-parallel (binary search of the prefix per entry, so all global
 // loads are independent and in flight together) into a 32*E-entry staging buffer that is sorted -- keeping
 // the best k -- whenever it fills.
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(128) merge_ragged_kernel(const uint64_t* __res
     if (lane == 0) prefix[n_lists] = running;
     __syncwarp();
     const int total = running;
-    const uint64_t* src = partial + q * n_lists * static_cast<int64_t>(slot_stride);
+    const uint64_t* src = partial + (q >> 5) * n_lists * (32 * static_cast<int64_t>(slot_stride)) + (q & 31);
 
     uint64_t key[E];
     int fill = 0;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(128) merge_ragged_kernel(const uint64_t* __res
                 const int mid = (lo + hi) >> 1;
                 if (prefix[mid] <= e) lo = mid; else hi = mid;
             }
-            buf[fill + i] = __ldcg(src + static_cast<int64_t>(lo) * slot_stride + (e - prefix[lo]));
+            buf[fill + i] = __ldcg(src + static_cast<int64_t>(lo) * (32 * slot_stride) + (e - prefix[lo]) * 32);
         }
         fill += take;
         done += take;
