@@ -13,7 +13,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "libagpknn.so"
 
 MEM_HOST, MEM_DEVICE = 0, 1
-PRECISION = {"auto": 0, "fp32_simt": 1, "3xtf32": 2, "exact_diff": 3, "3xfp16": 4}
+PRECISION = {"auto": 0, "fp32_simt": 1, "3xtf32": 2, "exact_diff": 3, "3xfp16": 4, "fp16_screen": 5}
 MAX_K = 512
 
 # every symbol include/agpknn.h declares: name -> (restype, argtypes)
@@ -30,6 +30,7 @@ SIGNATURES = {
     "agp_index_set_id_base": (c_int, [c_void_p, c_int64]),
     "agp_index_set_profiling": (c_int, [c_void_p, c_int]),
     "agp_index_get_profile": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), c_int]),
+    "agp_index_get_stats": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
     "agp_merge_topk": (c_int, [c_int, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "agp_recall_at_n": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "agp_last_error": (c_char_p, []),

@@ -69,10 +69,15 @@ struct agp_index {
     int64_t ntotal = 0, cap = 0, id_base = 0;
     float *xb = nullptr, *yn = nullptr, *wx = nullptr;
     uint8_t *xb_hi = nullptr, *xb_lo = nullptr;
-    bool planes = false;
+    uint8_t* xs = nullptr;        // single-pass screen plane [cap, d_pad + 64] fp16 (scaled rows + aux chunk)
+    bool planes = false, screen = false, scale_set = false;
     int kind = KIND_TF32, elem_bytes = 4;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     Buf q_raw, q_hi, q_lo, qn, sq, cand, partial, panel, d_out, i_out, gthr, cand_d, cand_i, dbg;
+    Buf dq, ovf, ovf_list, ovf_x, ovf_d, ovf_i;     // single-pass screen: residual norms, overflow flags / list / fallback scratch
+    uint32_t* dbstats = nullptr;                     // [4] max |y|^2, max |y - fp16(y)| over the database (fp32 bits)
+    int* h_count = nullptr;                          // pinned host word for the overflow count
+    int64_t stat_screened = 0, stat_fallback = 0;
     bool profile = false;
     cudaEvent_t ev_order = nullptr;
     std::vector<cudaEvent_t> ev_pool;
@@ -121,11 +126,12 @@ static int get_encode_fn(EncodeTiledFn* out) {
 
 // [rows, d_pad] row-major operand plane -> boxes of (128 bytes x box_rows), 128B swizzle; out-of-bounds
 // rows are zero filled
-static int make_plane_map(CUtensorMap* m, const void* base, int64_t rows, int d_pad, int box_rows, int elem_bytes) {
+static int make_plane_map(CUtensorMap* m, const void* base, int64_t rows, int d_pad, int box_rows, int elem_bytes, int ld_elems = 0) {
     EncodeTiledFn fn;
     CKR(get_encode_fn(&fn));
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(d_pad), static_cast<cuuint64_t>(rows)};
-    cuuint64_t strides[1] = {static_cast<cuuint64_t>(d_pad) * elem_bytes};
+    if (ld_elems == 0) ld_elems = d_pad;      // row pitch in elements (screen planes: d_pad + 64)
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(ld_elems), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * elem_bytes};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(TC_KCHUNK_BYTES / elem_bytes), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims,
@@ -153,7 +159,15 @@ static int grow(agp_index* ix, int64_t need) {
             LAUNCH(launch_fill_f32(nwx, ncap, 0.f, ix->stream));
         }
     }
+    uint8_t* nxs = nullptr;
+    const size_t screen_row = static_cast<size_t>(ix->d_pad + 64) * 2;
+    if (ix->screen) CK(cudaMalloc(&nxs, static_cast<size_t>(ncap) * screen_row));
     LAUNCH(launch_fill_f32(nyn, ncap, HUGE_VALF, ix->stream));
+    if (ix->screen) {
+        if (ix->ntotal > 0)
+            CK(cudaMemcpyAsync(nxs, ix->xs, static_cast<size_t>(ix->ntotal) * screen_row, cudaMemcpyDeviceToDevice, ix->stream));
+        LAUNCH(launch_init_aux(nxs, ix->d_pad, ix->ntotal, ncap, ix->stream));      // rows without a vector: aux = -inf
+    }
     if (ix->ntotal > 0) {
         CK(cudaMemcpyAsync(nxb, ix->xb, static_cast<size_t>(ix->ntotal) * ix->d * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
         CK(cudaMemcpyAsync(nyn, ix->yn, static_cast<size_t>(ix->ntotal) * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
@@ -169,6 +183,8 @@ static int grow(agp_index* ix, int64_t need) {
     if (ix->xb_hi) cudaFree(ix->xb_hi);
     if (ix->xb_lo) cudaFree(ix->xb_lo);
     if (ix->wx) cudaFree(ix->wx);
+    if (ix->xs) cudaFree(ix->xs);
+    ix->xs = nxs;
     ix->xb = nxb; ix->yn = nyn; ix->xb_hi = nhi; ix->xb_lo = nlo; ix->wx = nwx;
     ix->cap = ncap;
     return 0;
@@ -342,7 +358,7 @@ static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, floa
         CKR(ensure(ix->sq, static_cast<size_t>(nqc) * sizeof(float)));
         if (ix->kind == KIND_F16) {
             LAUNCH(launch_prep_rows_f16(xq_dev + q0 * ix->d, nqc, ix->d, ix->d_pad, static_cast<float*>(ix->qn.p), ix->q_hi.p, ix->q_lo.p,
-                                        static_cast<float*>(ix->sq.p), 1.f, ix->num_sms * 32, ix->stream));
+                                        static_cast<float*>(ix->sq.p), 1.f, nullptr, nullptr, ix->num_sms * 32, ix->stream));
         } else {
             LAUNCH(launch_prep_rows(true, xq_dev + q0 * ix->d, nqc, ix->d, ix->d_pad, static_cast<float*>(ix->qn.p),
                                     static_cast<float*>(ix->q_hi.p), static_cast<float*>(ix->q_lo.p), ix->num_sms * 32, ix->stream));
@@ -435,6 +451,155 @@ static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, floa
     return 0;
 }
 
+// register budget of the single-pass screen: slots for k + the certified band, with room to admit between compactions
+static int screen_regs_for_k(int k) {
+    const char* env_e = getenv("AGP_SCREEN_E");      // development override
+    const int kc_est = k + std::max(16, k / 4);
+    if (env_e) {
+        const int e = atoi(env_e);
+        if ((e == 2 || e == 4 || e == 8 || e == 16) && 32 * e - 64 >= kc_est + 16) return e;
+    }
+    int e = 2;
+    while ((32 * e < kc_est + kc_est / 2 + 32 || 32 * e - 64 < kc_est + 16) && e < 16) e <<= 1;
+    return e;
+}
+
+#define DISPATCH_EV(e, fn, ...)                                                                  \
+    [&]() -> int {                                                                               \
+        switch (e) {                                                                             \
+            case 2: LAUNCH(fn<2>(__VA_ARGS__)); return 0;                                        \
+            case 4: LAUNCH(fn<4>(__VA_ARGS__)); return 0;                                        \
+            case 8: LAUNCH(fn<8>(__VA_ARGS__)); return 0;                                        \
+            case 16: LAUNCH(fn<16>(__VA_ARGS__)); return 0;                                      \
+            default: return set_err(AGP_EINVAL, "unsupported register budget %d", e);            \
+        }                                                                                        \
+    }()
+
+// Single-pass certified screen on CTA pairs (knn_screen.cuh), exact finish, fp32 SIMT fallback for flagged queries.
+static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, float* D, int64_t* I) {
+    const int64_t n = ix->ntotal;
+    if (k > 256 || !ix->screen || (ix->num_sms & 1)) return search_simt(ix, xq_dev, nq, k, D, I);
+    const int E = screen_regs_for_k(k);
+    const int slots = 32 * E;
+    const int n_dbtiles = static_cast<int>((n + TC_BN - 1) / TC_BN);
+    const int ld = ix->d_pad + 64;                 // plane row pitch: scaled row + aux chunk
+    const int num_kc = ld / 64;
+    const int resident = num_kc <= 9 ? 1 : 0;
+    const int chunk_bytes = TC_BM * TC_KCHUNK_BYTES;
+    const int q_bytes = resident ? num_kc * chunk_bytes : 0;
+    const int stage_bytes = resident ? chunk_bytes : 2 * chunk_bytes;
+    const int smem_max = 227 * 1024;
+    int n_stages = std::min(8, (smem_max - 1024 - 512 - q_bytes) / stage_bytes);
+    { const char* e = getenv("AGP_SCREEN_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= n_stages) n_stages = atoi(e); }
+    const size_t smem = 1024 + static_cast<size_t>(q_bytes) + static_cast<size_t>(n_stages) * stage_bytes + 512;
+    CUtensorMap m_b;
+    // whole 256-row tiles: rows between ntotal and the tile end are storage padding masked by yn = +inf
+    CKR(make_plane_map(&m_b, ix->xs, static_cast<int64_t>(n_dbtiles) * TC_BN, ix->d_pad, TC_BM, 2, ld));
+    if (!ix->h_count) CK(cudaMallocHost(&ix->h_count, sizeof(int)));
+    const int clusters = ix->num_sms / 2;
+    const int64_t max_chunk = 65536;
+    for (int64_t q0 = 0; q0 < nq; q0 += max_chunk) {
+        const int nqc = static_cast<int>(std::min<int64_t>(max_chunk, nq - q0));
+        ScreenParams p;
+        p.nq = nqc;
+        p.d_pad = ix->d_pad;
+        p.k = k;
+        p.n_ptiles = (nqc + 2 * TC_BM - 1) / (2 * TC_BM);
+        const int64_t rows_pad = static_cast<int64_t>(p.n_ptiles) * 2 * TC_BM;
+        CKR(ensure(ix->q_hi, static_cast<size_t>(rows_pad) * ld * 2));
+        CKR(ensure(ix->qn, static_cast<size_t>(nqc) * sizeof(float)));
+        CKR(ensure(ix->sq, static_cast<size_t>(nqc) * sizeof(float)));
+        CKR(ensure(ix->dq, static_cast<size_t>(nqc) * sizeof(float)));
+        LAUNCH(launch_prep_rows_screen(xq_dev + q0 * ix->d, nqc, ix->d, ix->d_pad, ix->q_hi.p, static_cast<float*>(ix->qn.p),
+                                       static_cast<float*>(ix->sq.p), static_cast<float*>(ix->dq.p), nullptr, 0, ix->num_sms * 32, ix->stream));
+        if (rows_pad > nqc)
+            CK(cudaMemsetAsync(static_cast<uint8_t*>(ix->q_hi.p) + static_cast<size_t>(nqc) * ld * 2, 0,
+                               static_cast<size_t>(rows_pad - nqc) * ld * 2, ix->stream));
+        CUtensorMap m_q;
+        CKR(make_plane_map(&m_q, ix->q_hi.p, rows_pad, ix->d_pad, TC_BM, 2, ld));
+        // whole waves of pair tiles sweep the database unsplit; the last partial wave is split to fill every pair
+        p.n_dbtiles = n_dbtiles;
+        p.n_full_items = (p.n_ptiles / clusters) * clusters;
+        const int rem_tiles = p.n_ptiles - p.n_full_items;
+        p.rem_splits = rem_tiles > 0 ? std::max(1, std::min({clusters / rem_tiles, n_dbtiles, 64})) : 1;
+        p.list_splits = p.rem_splits;
+        p.n_items = p.n_full_items + rem_tiles * p.rem_splits;
+        p.q_resident = resident;
+        p.n_stages = n_stages;
+        p.sched_mul = 2;
+        { const char* e = getenv("AGP_SCREEN_SCHED"); if (e && atoi(e) >= 2) p.sched_mul = atoi(e); }
+        const int grid = 2 * std::min(p.n_items, clusters);
+        const size_t n_lists_total = static_cast<size_t>(p.n_full_items) * 2 * TC_BM * 2 + static_cast<size_t>(rem_tiles) * 2 * TC_BM * 2 * p.rem_splits;
+        CKR(ensure(ix->cand, n_lists_total * sizeof(int)));
+        CKR(ensure(ix->partial, n_lists_total * slots * sizeof(uint64_t)));
+        CKR(ensure(ix->gthr, static_cast<size_t>(nqc) * sizeof(uint32_t)));
+        CKR(ensure(ix->ovf, static_cast<size_t>(nqc) * sizeof(int)));
+        CKR(ensure(ix->ovf_list, static_cast<size_t>(nqc + 1) * sizeof(int)));
+        CK(cudaMemsetAsync(ix->cand.p, 0, n_lists_total * sizeof(int), ix->stream));
+        CK(cudaMemsetAsync(ix->ovf.p, 0, static_cast<size_t>(nqc) * sizeof(int), ix->stream));
+        CK(cudaMemsetAsync(ix->ovf_list.p, 0, sizeof(int), ix->stream));
+        LAUNCH(launch_fill_f32(static_cast<float*>(ix->gthr.p), nqc, HUGE_VALF, ix->stream));
+        p.qn = static_cast<const float*>(ix->qn.p);
+        p.sq = static_cast<const float*>(ix->sq.p);
+        p.dq = static_cast<const float*>(ix->dq.p);
+        p.dbstats = ix->dbstats;
+        p.partial = static_cast<uint64_t*>(ix->partial.p);
+        p.pcount = static_cast<int*>(ix->cand.p);
+        p.gthr = static_cast<uint32_t*>(ix->gthr.p);
+        p.ovf = static_cast<int*>(ix->ovf.p);
+        p.dbg = nullptr;
+        const char* env_dbg = getenv("AGP_TC_DEBUG");
+        const bool dbg = env_dbg && atoi(env_dbg) != 0;
+        if (dbg) {
+            CKR(ensure(ix->dbg, static_cast<size_t>(grid) * 8 * sizeof(long long)));
+            CK(cudaMemsetAsync(ix->dbg.p, 0, static_cast<size_t>(grid) * 8 * sizeof(long long), ix->stream));
+            p.dbg = static_cast<long long*>(ix->dbg.p);
+        }
+        int* ovf_count = static_cast<int*>(ix->ovf_list.p);
+        int* ovf_list = ovf_count + 1;
+        ProfScope prof(ix);
+        CKR(DISPATCH_EV(E, launch_knn_screen, m_q, m_b, p, grid, smem, ix->stream));
+        prof.stop();
+        CKR(DISPATCH_EV(E, launch_screen_finalize, static_cast<const uint64_t*>(ix->partial.p), static_cast<const int*>(ix->cand.p), slots,
+                        static_cast<int64_t>(nqc), p.n_full_items, p.rem_splits, k, xq_dev + q0 * ix->d, ix->xb, ix->d, ix->d_pad,
+                        static_cast<const float*>(ix->qn.p), static_cast<const float*>(ix->dq.p), ix->dbstats,
+                        static_cast<const int*>(ix->ovf.p), ovf_count, ovf_list, ix->id_base, D + q0 * k, I + q0 * k, ix->stream));
+        CK(cudaMemcpyAsync(ix->h_count, ovf_count, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+        if (dbg) {
+            std::vector<long long> h(static_cast<size_t>(grid) * 8);
+            CK(cudaMemcpyAsync(h.data(), ix->dbg.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
+            CK(cudaStreamSynchronize(ix->stream));
+            double sl[8] = {0}, sa[8] = {0};
+            for (int b = 0; b < grid; ++b)
+                for (int j = 0; j < 8; ++j) { sa[j] += static_cast<double>(h[b * 8 + j]) / grid; if ((b & 1) == 0) sl[j] += static_cast<double>(h[b * 8 + j]) / (grid / 2); }
+            std::vector<int> pc(n_lists_total);
+            CK(cudaMemcpy(pc.data(), ix->cand.p, pc.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            double tot = 0; int mx = 0;
+            for (size_t i = 0; i < pc.size(); ++i) { tot += pc[i]; mx = std::max(mx, pc[i]); }
+            fprintf(stderr, "[agp screen dbg] E=%d stages=%d grid=%d items=%d (full %d + %d x %d) | candidates/query mean=%.1f, max list=%d\n", E,
+                    n_stages, grid, p.n_items, p.n_full_items, rem_tiles, p.rem_splits, tot / nqc, mx);
+            fprintf(stderr, "[agp screen dbg] mma(leader): total=%.0f wait_full=%.0f wait_tempty=%.0f | epi(w2, all CTAs): total=%.0f wait_tfull=%.0f "
+                            "compact=%.0f n_compact=%.0f (cycles, mean)\n", sl[0], sl[1], sl[2], sa[3], sa[4], sa[5], sa[6]);
+        }
+        CK(cudaStreamSynchronize(ix->stream));
+        const int n_ovf = *ix->h_count;
+        ix->stat_screened += nqc;
+        if (n_ovf > 0) {
+            // certified band did not fit (or a row was not representable): answer those queries with fp32 FMA tiles instead
+            ix->stat_fallback += n_ovf;
+            CKR(ensure(ix->ovf_x, static_cast<size_t>(n_ovf) * ix->d * sizeof(float)));
+            CKR(ensure(ix->ovf_d, static_cast<size_t>(n_ovf) * k * sizeof(float)));
+            CKR(ensure(ix->ovf_i, static_cast<size_t>(n_ovf) * k * sizeof(int64_t)));
+            LAUNCH(launch_gather_rows(xq_dev + q0 * ix->d, ovf_list, n_ovf, ix->d, static_cast<float*>(ix->ovf_x.p), ix->stream));
+            CKR(search_simt(ix, static_cast<const float*>(ix->ovf_x.p), n_ovf, k, static_cast<float*>(ix->ovf_d.p),
+                            static_cast<int64_t*>(ix->ovf_i.p)));
+            LAUNCH(launch_scatter_results(static_cast<const float*>(ix->ovf_d.p), static_cast<const int64_t*>(ix->ovf_i.p), ovf_list, n_ovf, k,
+                                          D + q0 * k, I + q0 * k, ix->stream));
+        }
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------ C ABI
 extern "C" {
 
@@ -455,7 +620,7 @@ int agp_index_create(int d, int device, int precision_mode, agp_index** out) {
     if (!out) return set_err(AGP_EINVAL, "out is null");
     *out = nullptr;
     if (d <= 0) return set_err(AGP_EINVAL, "d must be positive, got %d", d);
-    if (precision_mode < 0 || precision_mode > 4) return set_err(AGP_EINVAL, "unknown precision_mode %d", precision_mode);
+    if (precision_mode < 0 || precision_mode > 5) return set_err(AGP_EINVAL, "unknown precision_mode %d", precision_mode);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -473,10 +638,9 @@ int agp_index_create(int d, int device, int precision_mode, agp_index** out) {
     ix->device = device;
     ix->mode = precision_mode;
     ix->num_sms = prop.multiProcessorCount;
-    ix->planes = (precision_mode == AGP_PRECISION_AUTO || precision_mode == AGP_PRECISION_3XTF32 || precision_mode == AGP_PRECISION_3XFP16);
+    ix->planes = (precision_mode == AGP_PRECISION_3XTF32 || precision_mode == AGP_PRECISION_3XFP16);
+    ix->screen = (precision_mode == AGP_PRECISION_AUTO || precision_mode == AGP_PRECISION_FP16_SCREEN);
     ix->kind = (precision_mode == AGP_PRECISION_3XTF32) ? KIND_TF32 : KIND_F16;
-    const char* env_kind = getenv("AGP_TC_KIND");          // development override: "tf32" | "f16"
-    if (env_kind && precision_mode == AGP_PRECISION_AUTO) ix->kind = (strcmp(env_kind, "tf32") == 0) ? KIND_TF32 : KIND_F16;
     ix->elem_bytes = ix->kind == KIND_TF32 ? 4 : 2;
     cudaError_t e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -484,6 +648,11 @@ int agp_index_create(int d, int device, int precision_mode, agp_index** out) {
         return set_err(AGP_ECUDA, "stream creation failed: %s", cudaGetErrorString(e));
     }
     ix->stream = ix->own_stream;
+    if (cudaMalloc(&ix->dbstats, 4 * sizeof(uint32_t)) != cudaSuccess || cudaMemset(ix->dbstats, 0, 4 * sizeof(uint32_t)) != cudaSuccess) {
+        cudaStreamDestroy(ix->own_stream);
+        delete ix;
+        return set_err(AGP_ENOMEM, "device allocation failed");
+    }
     *out = ix;
     return 0;
 }
@@ -497,7 +666,11 @@ void agp_index_free(agp_index* ix) {
     if (ix->xb_lo) cudaFree(ix->xb_lo);
     if (ix->yn) cudaFree(ix->yn);
     if (ix->wx) cudaFree(ix->wx);
+    if (ix->xs) cudaFree(ix->xs);
     free_buf(ix->sq);
+    free_buf(ix->dq); free_buf(ix->ovf); free_buf(ix->ovf_list); free_buf(ix->ovf_x); free_buf(ix->ovf_d); free_buf(ix->ovf_i);
+    if (ix->dbstats) cudaFree(ix->dbstats);
+    if (ix->h_count) cudaFreeHost(ix->h_count);
     free_buf(ix->q_raw); free_buf(ix->q_hi); free_buf(ix->q_lo); free_buf(ix->qn); free_buf(ix->cand);
     free_buf(ix->gthr); free_buf(ix->dbg); free_buf(ix->cand_d); free_buf(ix->cand_i); free_buf(ix->partial); free_buf(ix->panel); free_buf(ix->d_out); free_buf(ix->i_out);
     for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
@@ -563,7 +736,17 @@ int agp_index_reset(agp_index* ix) {
     if (ix->cap > 0) {
         LAUNCH(launch_fill_f32(ix->yn, ix->cap, HUGE_VALF, ix->stream));
     }
+    CK(cudaMemsetAsync(ix->dbstats, 0, 4 * sizeof(uint32_t), ix->stream));
+    if (ix->screen && ix->cap > 0) LAUNCH(launch_init_aux(ix->xs, ix->d_pad, 0, ix->cap, ix->stream));
+    ix->scale_set = false;
     ix->ntotal = 0;
+    return 0;
+}
+
+int agp_index_get_stats(const agp_index* ix, int64_t* screened_queries, int64_t* fallback_queries) {
+    if (!ix) return set_err(AGP_EINVAL, "index is null");
+    if (screened_queries) *screened_queries = ix->stat_screened;
+    if (fallback_queries) *fallback_queries = ix->stat_fallback;
     return 0;
 }
 
@@ -579,9 +762,16 @@ int agp_index_add(agp_index* ix, int64_t n, const float* x, int mem_kind) {
     CK(cudaMemcpyAsync(dst, x, static_cast<size_t>(n) * ix->d * sizeof(float),
                        mem_kind == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ix->stream));
     const size_t plane_off = static_cast<size_t>(ix->ntotal) * ix->d_pad * ix->elem_bytes;
-    if (ix->planes && ix->kind == KIND_F16) {
+    if (ix->screen) {
+        if (!ix->scale_set) {      // database-wide fp16 scale: fixed by the first batch after create / reset
+            LAUNCH(launch_fix_db_scale(dst, n * ix->d, ix->dbstats, ix->num_sms * 8, ix->stream));
+            ix->scale_set = true;
+        }
+        LAUNCH(launch_prep_rows_screen(dst, n, ix->d, ix->d_pad, ix->xs + static_cast<size_t>(ix->ntotal) * (ix->d_pad + 64) * 2,
+                                       ix->yn + ix->ntotal, nullptr, nullptr, ix->dbstats, 1, ix->num_sms * 32, ix->stream));
+    } else if (ix->planes && ix->kind == KIND_F16) {
         LAUNCH(launch_prep_rows_f16(dst, n, ix->d, ix->d_pad, ix->yn + ix->ntotal, ix->xb_hi + plane_off, ix->xb_lo + plane_off,
-                                    ix->wx + ix->ntotal, -2.f, ix->num_sms * 32, ix->stream));
+                                    ix->wx + ix->ntotal, -2.f, nullptr, ix->dbstats, ix->num_sms * 32, ix->stream));
     } else if (ix->planes) {
         LAUNCH(launch_prep_rows(true, dst, n, ix->d, ix->d_pad, ix->yn + ix->ntotal, reinterpret_cast<float*>(ix->xb_hi + plane_off),
                                 reinterpret_cast<float*>(ix->xb_lo + plane_off), ix->num_sms * 32, ix->stream));
@@ -624,8 +814,9 @@ int agp_index_search(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, 
     } else {
         switch (ix->mode) {
             case AGP_PRECISION_AUTO:
-                rc = (nq < kMaxSmallNq) ? search_diff(ix, xq_dev, nq, k, D_dev, I_dev) : search_tc(ix, xq_dev, nq, k, D_dev, I_dev);
+                rc = (nq < kMaxSmallNq) ? search_diff(ix, xq_dev, nq, k, D_dev, I_dev) : search_screen(ix, xq_dev, nq, k, D_dev, I_dev);
                 break;
+            case AGP_PRECISION_FP16_SCREEN: rc = search_screen(ix, xq_dev, nq, k, D_dev, I_dev); break;
             case AGP_PRECISION_3XTF32:
             case AGP_PRECISION_3XFP16: rc = search_tc(ix, xq_dev, nq, k, D_dev, I_dev); break;
             case AGP_PRECISION_FP32_SIMT: rc = search_simt(ix, xq_dev, nq, k, D_dev, I_dev); break;

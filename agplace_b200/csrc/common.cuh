@@ -110,6 +110,82 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- load batching
+// ptxas tends to interleave "load one element, use it" even when the source asks for a batch of independent
+// loads, which turns a batch into one L2 round trip PER ELEMENT.  batch_fence() pins the order: every load
+// written before it has been issued, and no consumer of the named registers can be scheduled above it.
+__device__ __forceinline__ void batch_fence(float (&d)[32]) {
+    asm volatile("" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i += 8)
+        asm volatile("" : "+f"(d[i]), "+f"(d[i + 1]), "+f"(d[i + 2]), "+f"(d[i + 3]), "+f"(d[i + 4]), "+f"(d[i + 5]), "+f"(d[i + 6]), "+f"(d[i + 7]));
+}
+__device__ __forceinline__ void batch_fence(float (&d)[8]) {
+    asm volatile("" ::: "memory");
+    asm volatile("" : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]), "+f"(d[4]), "+f"(d[5]), "+f"(d[6]), "+f"(d[7]));
+}
+__device__ __forceinline__ void batch_fence(uint64_t (&d)[16]) {
+    asm volatile("" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i += 8)
+        asm volatile("" : "+l"(d[i]), "+l"(d[i + 1]), "+l"(d[i + 2]), "+l"(d[i + 3]), "+l"(d[i + 4]), "+l"(d[i + 5]), "+l"(d[i + 6]), "+l"(d[i + 7]));
+}
+
+// ---------------------------------------------------------------- CTA pair (cta_group::2) helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of the same shared-memory object in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on an mbarrier that may live in the peer CTA (address from mapa_u32)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default .release.cta semantics: what the barrier orders here is TMEM/smem traffic of the async proxy (tcgen05 fences),
+    // and a cluster-scope release costs a MEMBAR + ERRBAR per arrival
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// NOTE: waits on barriers signalled from the peer CTA use the plain mbar_wait (cta-scope acquire): a cluster-scope
+// acquire makes ptxas emit CCTL.IVALL -- an L1 invalidate per successful wait -- which evicts the epilogue's lines.
+// TMA tile load into THIS CTA's shared memory whose completion bytes are signalled on an mbarrier that
+// may live in the pair's leader CTA (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// completion of all prior tcgen05.mma of the pair -> one arrival on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+// M = 256 (128 rows from each CTA of the pair) x N x 16, fp16 operands, issued by the leader CTA only
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // K-major, 128-byte-swizzled operand tile descriptor (rows of 128 B, 8-row atoms 1024 B apart)
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     uint64_t d = 0;

@@ -75,9 +75,14 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const float* __restrict_
 //   x' = x * 2^-ex with max|x'| in [0.5, 1)   (power-of-two scaling: exact)
 //   hi = fp16(x'), lo = fp16(x' - hi)          -> x' = hi + lo up to ~2^-24 absolute (row max = 1)
 //   scale[r] = factor * 2^ex                   (factor 1 for queries, -2 for database rows)
+//   dres[r]  = |x - hi * 2^ex| (the fp16 rounding residual, original units, rounded up)   [optional]
+//   stats[0] = max over rows of |x|^2, stats[1] = max over rows of dres (fp32 bits, atomicMax)   [optional]
+// The residual norms make the single-pass screen (knn_screen.cuh) a CERTIFIED filter: the tensor-core
+// inner product of the hi planes differs from the true one by at most |dq||y| + |q||dy| (Cauchy-Schwarz).
 __global__ void __launch_bounds__(256) prep_rows_f16_kernel(const float* __restrict__ x, int64_t n, int d, int d_pad,
                                                             float* __restrict__ norm, __half* __restrict__ hi,
-                                                            __half* __restrict__ lo, float* __restrict__ scale, float factor) {
+                                                            __half* __restrict__ lo, float* __restrict__ scale, float factor,
+                                                            float* __restrict__ dres, uint32_t* __restrict__ stats) {
     const int lane = threadIdx.x & 31;
     const int64_t warps_per_grid = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
     for (int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += warps_per_grid) {
@@ -97,21 +102,146 @@ __global__ void __launch_bounds__(256) prep_rows_f16_kernel(const float* __restr
         if (amax > 0.f && amax < __int_as_float(0x7f800000)) frexpf(amax, &ex);
         const float inv = ldexpf(1.f, -ex);
         __half2* hrow = reinterpret_cast<__half2*>(hi + r * d_pad);
-        __half2* lrow = reinterpret_cast<__half2*>(lo + r * d_pad);
+        __half2* lrow = lo ? reinterpret_cast<__half2*>(lo + r * d_pad) : nullptr;
+        float res = 0.f;
         for (int c2 = lane; c2 < (d_pad >> 1); c2 += 32) {
             const int c = 2 * c2;
             const float v0 = (c < d ? __ldg(row + c) : 0.f) * inv;
             const float v1 = (c + 1 < d ? __ldg(row + c + 1) : 0.f) * inv;
             const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-            const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+            const float r0 = v0 - __half2float(h0), r1 = v1 - __half2float(h1);   // exact in fp32
             hrow[c2] = __halves2half2(h0, h1);
-            lrow[c2] = __halves2half2(l0, l1);
+            if (lrow) lrow[c2] = __halves2half2(__float2half_rn(r0), __float2half_rn(r1));
+            res = fmaf(r0, r0, res);
+            res = fmaf(r1, r1, res);
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) res += __shfl_xor_sync(kFull, res, o);
         if (lane == 0) {
             norm[r] = acc;
             scale[r] = factor * ldexpf(1.f, ex);
+            // residual norm back in the row's own units, rounded up generously (fp32 summation error << 1e-3)
+            float dr = sqrtf(res) * ldexpf(1.f, ex) * 1.001f;
+            if (!(dr < __int_as_float(0x7f800000))) dr = __int_as_float(0x7f800000);   // inf/nan rows: unbounded error -> exact fallback
+            if (dres) dres[r] = dr;
+            if (stats) {
+                atomicMax(stats + 0, __float_as_uint(acc < __int_as_float(0x7f800000) ? acc : __int_as_float(0x7f800000)));
+                atomicMax(stats + 1, __float_as_uint(dr));
+            }
         }
     }
+}
+
+// K1 for the single-pass screen (knn_screen.cuh).  One warp per row; the plane row is d_pad fp16 values of the
+// scaled row followed by one 64-element AUX chunk that folds the norm term into the tensor-core contraction:
+//   database row y (GLOBAL scale sy = 2^eg, fixed at the first add):  [fp16(y / sy) ... | h1 h2 h3 0 ...],
+//        h1 + h2 + h3 = -|y|^2 / (2 sy)   (three fp16 pieces: 33 significant bits)
+//   query row q (per-row scale sq = 2^eq):                           [fp16(q / sq) ... | 1/sq 1/sq 1/sq 0 ...]
+// so that the accumulator of K = d_pad + 16 is  acc' = (q.y - |y|^2 / 2) / (sq sy)  and the screened distance is
+// |q|^2 - 2 sq sy acc' -- no per-column term is left for the epilogue.  Also measured here: |x|^2 (fp32, like faiss
+// fvec_norms_L2sqr) and the norm of the fp16 rounding residual (certifies the screen, see launch.h:screen_band).
+// Rows that cannot be represented (fp16 overflow of the scaled row, of 1/sq or of the aux value) get an infinite
+// residual, which sends the affected queries to the exact fallback instead of risking a wrong answer.
+__global__ void __launch_bounds__(256) prep_rows_screen_kernel(const float* __restrict__ x, int64_t n, int d, int d_pad,
+                                                               __half* __restrict__ plane, float* __restrict__ norm,
+                                                               float* __restrict__ scale_out, float* __restrict__ dres,
+                                                               uint32_t* __restrict__ stats, int is_db) {
+    const int lane = threadIdx.x & 31;
+    const int ld = d_pad + 64;
+    const float inf = __int_as_float(0x7f800000);
+    const int64_t warps_per_grid = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+    const float gs = is_db ? __uint_as_float(stats[2]) : 0.f;
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += warps_per_grid) {
+        const float* row = x + r * d;
+        float acc = 0.f, amax = 0.f;
+        for (int c = lane; c < d; c += 32) {
+            const float v = __ldg(row + c);
+            acc = fmaf(v, v, acc);
+            amax = fmaxf(amax, fabsf(v));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(kFull, acc, o);
+            amax = fmaxf(amax, __shfl_xor_sync(kFull, amax, o));
+        }
+        float s = gs;
+        if (!is_db) {
+            int ex = 0;
+            if (amax > 0.f && amax < inf) frexpf(amax, &ex);
+            s = ldexpf(1.f, ex);
+        }
+        const float inv = 1.f / s;                     // power of two: exact
+        __half2* prow = reinterpret_cast<__half2*>(plane + r * ld);
+        float res = 0.f;
+        bool bad = !(amax * inv < 65504.f);            // also catches inf / nan rows
+        for (int c2 = lane; c2 < (d_pad >> 1); c2 += 32) {
+            const int c = 2 * c2;
+            const float v0 = (c < d ? __ldg(row + c) : 0.f) * inv;
+            const float v1 = (c + 1 < d ? __ldg(row + c + 1) : 0.f) * inv;
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            const float r0 = v0 - __half2float(h0), r1 = v1 - __half2float(h1);   // exact in fp32
+            prow[c2] = __halves2half2(h0, h1);
+            res = fmaf(r0, r0, res);
+            res = fmaf(r1, r1, res);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) res += __shfl_xor_sync(kFull, res, o);
+        // aux chunk
+        float a0, a1, a2;
+        if (is_db) {
+            const float v = -0.5f * acc * inv;
+            bad = bad || !(fabsf(v) < 65504.f);
+            const __half p1 = __float2half_rn(v);
+            const float e1 = v - __half2float(p1);
+            const __half p2 = __float2half_rn(e1);
+            const float e2 = e1 - __half2float(p2);
+            a0 = __half2float(p1); a1 = __half2float(p2); a2 = __half2float(__float2half_rn(e2));
+        } else {
+            bad = bad || !(inv >= 6.103515625e-05f && inv <= 32768.f);
+            a0 = a1 = a2 = bad ? 0.f : inv;
+        }
+        __half2 aux = __floats2half2_rn(0.f, 0.f);
+        if (lane == 0) aux = __floats2half2_rn(a0, a1);
+        if (lane == 1) aux = __floats2half2_rn(a2, 0.f);
+        prow[(d_pad >> 1) + lane] = aux;
+        if (lane == 0) {
+            norm[r] = acc;
+            if (scale_out) scale_out[r] = s;
+            float dr = sqrtf(res) * s * 1.001f;        // residual norm in the row's own units, rounded up
+            if (bad || !(dr < inf)) dr = inf;
+            if (dres) dres[r] = dr;
+            if (is_db) {
+                atomicMax(stats + 0, __float_as_uint(acc < inf ? acc : inf));
+                atomicMax(stats + 1, __float_as_uint(dr));
+            }
+        }
+    }
+}
+
+// database-wide scale of the screen plane: fixed once, from the first batch added after create/reset
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t count, uint32_t* __restrict__ stats) {
+    float m = 0.f;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float v = fabsf(x[i]);
+        if (v < __int_as_float(0x7f800000)) m = fmaxf(m, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(stats + 3, __float_as_uint(m));
+}
+__global__ void fix_scale_kernel(uint32_t* __restrict__ stats) {
+    const float amax = __uint_as_float(stats[3]);
+    int ex = 0;
+    if (amax > 0.f) frexpf(amax, &ex);
+    stats[2] = __float_as_uint(ldexpf(1.f, ex));       // amax / scale in [0.5, 1): 2^16 of fp16 headroom for later batches
+}
+// storage rows that hold no vector must never be admitted: aux h1 = -inf makes their accumulator -inf
+__global__ void init_aux_kernel(__half* __restrict__ plane, int ld, int d_pad, int64_t row0, int64_t row1) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t r = row0 + (i >> 6);
+    if (r >= row1) return;
+    const int c = static_cast<int>(i & 63);
+    plane[r * ld + d_pad + c] = c == 0 ? __ushort_as_half(0xfc00) : __ushort_as_half(0);
 }
 
 __global__ void fill_f32_kernel(float* __restrict__ p, int64_t n, float v) {
@@ -250,7 +380,38 @@ __global__ void __launch_bounds__(128) recall_kernel(const int64_t* __restrict__
 }
 
 
+__global__ void gather_rows_kernel(const float* __restrict__ x, const int* __restrict__ list, int n, int d, float* __restrict__ out) {
+    const int r = blockIdx.x;
+    if (r >= n) return;
+    const float* src = x + static_cast<int64_t>(list[r]) * d;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) out[static_cast<int64_t>(r) * d + c] = src[c];
+}
+
+__global__ void scatter_results_kernel(const float* __restrict__ Dt, const int64_t* __restrict__ It, const int* __restrict__ list, int n,
+                                       int k, float* __restrict__ D, int64_t* __restrict__ I) {
+    const int r = blockIdx.x;
+    if (r >= n) return;
+    const int64_t q = list[r];
+    for (int c = threadIdx.x; c < k; c += blockDim.x) {
+        D[q * k + c] = Dt[static_cast<int64_t>(r) * k + c];
+        I[q * k + c] = It[static_cast<int64_t>(r) * k + c];
+    }
+}
+
 // ------------------------------------------------------------------------------------------ launchers
+cudaError_t launch_gather_rows(const float* x, const int* list, int n, int d, float* out, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    gather_rows_kernel<<<n, 128, 0, st>>>(x, list, n, d, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_results(const float* Dt, const int64_t* It, const int* list, int n, int k, float* D, int64_t* I,
+                                   cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    scatter_results_kernel<<<n, 64, 0, st>>>(Dt, It, list, n, k, D, I);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_prep_rows(bool split, const float* x, int64_t n, int d, int d_pad, float* norm, float* hi, float* lo, int max_blocks,
                              cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
@@ -263,10 +424,33 @@ cudaError_t launch_prep_rows(bool split, const float* x, int64_t n, int d, int d
 }
 
 cudaError_t launch_prep_rows_f16(const float* x, int64_t n, int d, int d_pad, float* norm, void* hi, void* lo, float* scale, float factor,
-                                 int max_blocks, cudaStream_t st) {
+                                 float* dres, uint32_t* stats, int max_blocks, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     const unsigned blocks = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, max_blocks)));
-    prep_rows_f16_kernel<<<blocks, 256, 0, st>>>(x, n, d, d_pad, norm, static_cast<__half*>(hi), static_cast<__half*>(lo), scale, factor);
+    prep_rows_f16_kernel<<<blocks, 256, 0, st>>>(x, n, d, d_pad, norm, static_cast<__half*>(hi), static_cast<__half*>(lo), scale, factor,
+                                                 dres, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prep_rows_screen(const float* x, int64_t n, int d, int d_pad, void* plane, float* norm, float* scale_out, float* dres,
+                                    uint32_t* stats, int is_db, int max_blocks, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const unsigned blocks = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, max_blocks)));
+    prep_rows_screen_kernel<<<blocks, 256, 0, st>>>(x, n, d, d_pad, static_cast<__half*>(plane), norm, scale_out, dres, stats, is_db);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fix_db_scale(const float* x, int64_t count, uint32_t* stats, int max_blocks, cudaStream_t st) {
+    const unsigned blocks = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((count + 1023) / 1024, max_blocks)));
+    absmax_kernel<<<blocks, 256, 0, st>>>(x, count, stats);
+    fix_scale_kernel<<<1, 1, 0, st>>>(stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_init_aux(void* plane, int d_pad, int64_t row0, int64_t row1, cudaStream_t st) {
+    if (row1 <= row0) return cudaSuccess;
+    const int64_t count = (row1 - row0) * 64;
+    init_aux_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, st>>>(static_cast<__half*>(plane), d_pad + 64, d_pad, row0, row1);
     return cudaGetLastError();
 }
 

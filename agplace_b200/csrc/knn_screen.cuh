@@ -1,0 +1,663 @@
+// knn_screen.cuh -- K2 + K3, single-pass form: a CERTIFIED fp16 screen on CTA pairs, then an exact finish.
+//
+// The 3xFP16 kernel (knn_tc.cuh) spends three tensor-core products per algorithmic multiply-add to get an
+// fp32-grade inner product.  This kernel spends ONE: both operands are a single fp16 plane (rows scaled by a
+// power of two so that max|x'| is in [0.5, 1)), which makes the screened distance
+//     dis~ = |q|^2 + |y|^2 - 2 sq sy sum_i hq_i hy_i          (sq = 2^eq per query, sy = 2^eg for the whole database)
+// wrong by at most  band(q) = 2 (|dq| max|y| + |q| max|dy|) + accumulation/epilogue terms  (launch.h:screen_band;
+// |dq|, |dy| are the MEASURED norms of the fp16 rounding residuals, K1).  Selection keeps every database row with
+//     dis~ < (k-th smallest dis~ seen so far) + 2 band(q),
+// a superset of the true top-k: k rows have dis~ <= kth~, hence true distance <= kth~ + band, hence the true
+// k-th distance tau <= kth~ + band, hence any true top-k row has dis~ <= tau + band <= kth~ + 2 band.
+// screen_finalize_kernel then picks the exact band around the final kth~, recomputes those rows in the fp32
+// difference form sum (x - y)^2 (what faiss evaluates for small batches) and returns the best k by (distance, id).
+// A query whose band does not fit its candidate slots (heavily duplicated databases) is flagged in ovf[] and
+// re-run through the 3xFP16 path by the host -- never answered from an incomplete candidate set.
+//
+// Hardware mapping (one CTA per SM, CTA pairs = clusters of 2, 320 threads each):
+//   * cta_group::2 UMMA, M = 256 (128 queries from each CTA) x N = 256 database rows x K = 16; every CTA stages
+//     only HALF of each database tile (128 rows x 64 fp16 = 16 KB per K chunk), so the L2 -> SM operand stream is
+//     1/256 B per flop -- inside the chip's ~6.3 KB/clk L2 ceiling at full tensor rate (cta_group::1 is not).
+//   * the CTA's 128-query tile (d_pad <= 512: <= 128 KB) is loaded once per work item and stays in shared
+//     memory; only database chunks flow through the mbarrier ring (d_pad > 512: queries stream too).
+//   * accumulators: 128 lanes x 256 fp32 columns in each CTA's TMEM, double buffered (all 512 columns);
+//     8 epilogue warps per CTA scan them (thread = query) exactly as in knn_tc.cuh.
+// Barriers: full[s] / qfull live in the leader (rank 0) and collect the TMA bytes of BOTH CTAs; empty[s], qempty
+// and tfull[a] are signalled in both CTAs by multicast tcgen05.commit; tempty[a] (leader) counts one arrival per
+// epilogue warp of both CTAs.
+// The norm term rides in the contraction: every plane row carries one extra 64-element "aux" chunk (K1,
+// k_misc.cu:prep_rows_screen_kernel) of which one K = 16 step is issued, so the accumulator already holds
+//     acc' = (q.y - |y|^2 / 2) / (sq sy)      and      dis~ = |q|^2 - 2 sq sy acc',
+// and the epilogue is a 3-input max tree over raw accumulator columns against one per-thread threshold -- no
+// per-column loads, one FMNMX3 per three elements.  Storage rows without a vector carry aux = -inf.
+// Algorithmic work per pair tile step: 2 * 256 * 256 * d flop, issued once (+ 16/d for the aux step).
+#pragma once
+#include "common.cuh"
+#include "knn_tc.cuh"
+#include "merge.cuh"
+#include "sortnet.cuh"
+
+namespace agp {
+
+constexpr int SC_CHUNK_BYTES = TC_BM * TC_KCHUNK_BYTES;      // 128 rows x 128 B = 16 KB (query chunk, or half a database chunk)
+constexpr int SC_MAX_STAGES = 8;
+constexpr int SC_BAR_BYTES = 512;
+
+struct ScItem {
+    int pt, split, t0, t1;
+};
+__device__ __forceinline__ ScItem sc_decode_item(const ScreenParams& p, int item) {
+    ScItem it;
+    int nsp = 1;
+    if (item < p.n_full_items) {
+        it.pt = item;
+        it.split = 0;
+    } else {
+        const int r = item - p.n_full_items;
+        it.pt = p.n_full_items + r / p.rem_splits;
+        it.split = r - (r / p.rem_splits) * p.rem_splits;
+        nsp = p.rem_splits;
+    }
+    it.t0 = static_cast<int>(static_cast<int64_t>(it.split) * p.n_dbtiles / nsp);
+    it.t1 = static_cast<int>(static_cast<int64_t>(it.split + 1) * p.n_dbtiles / nsp);
+    return it;
+}
+
+// Candidate lists: queries of unsplit pair tiles own 2 lists (column halves), queries of the split remainder
+// own 2 * rem_splits.  List l of query q counts its entries in pcount[sc_list_base(q) + l]; its slots are the
+// interleaved bundle  partial + (sc_list_base(q / 32 (bundle), 8) + l) * 32 * CAP  (+ q % 32, stride 32).
+__host__ __device__ __forceinline__ size_t sc_list_base(int n_full_items, int rem_splits, int64_t unit, int units_per_ptile) {
+    const int64_t nf = static_cast<int64_t>(n_full_items) * units_per_ptile;
+    return unit < nf ? static_cast<size_t>(unit) * 2 : static_cast<size_t>(nf) * 2 + static_cast<size_t>(unit - nf) * 2 * rem_splits;
+}
+__device__ __forceinline__ size_t sc_list_base(const ScreenParams& p, int64_t unit, int units_per_ptile = 2 * TC_BM) {
+    return sc_list_base(p.n_full_items, p.rem_splits, unit, units_per_ptile);
+}
+
+__device__ __forceinline__ float sc_inf() { return __int_as_float(0x7f800000); }
+
+// Exact compaction of lane L's slots by the whole warp: sort, find the k-th, keep the certified band below
+// (k-th + 2 band).  If even that does not fit, the query is flagged and degraded to a plain top-k so the sweep
+// can continue; the host recomputes flagged queries.
+template <int E>
+__device__ __noinline__ void sc_compact_sort(int L, uint64_t* wbuf, int& cnt, float& lim, float band2, int lane, int k,
+                                             uint32_t* my_gthr, int* my_ovf) {
+    constexpr int CAP = 32 * E;
+    const int n = __shfl_sync(kFull, cnt, L);
+    const float limL = __shfl_sync(kFull, lim, L);
+    const float bandL = __shfl_sync(kFull, band2, L);
+    __syncwarp();
+    uint64_t key[E];
+#pragma unroll
+    for (int j = 0; j < E; ++j) key[j] = (j * 32 + lane < n) ? __ldcg(wbuf + (j * 32 + lane) * 32 + L) : kEmptyKey;
+    warp_bitonic_sort<E>(key, lane);
+    const bool have_k = n >= k;
+    const float kth = have_k ? key_dist(warp_get<E>(key, k - 1)) : sc_inf();
+    float flim = fminf(limL, kth + bandL);
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < E; ++j) mine += (key[j] != kEmptyKey && key_dist(key[j]) < flim) ? 1 : 0;
+    int nkeep = __reduce_add_sync(kFull, mine);
+    bool over = false;
+    if (nkeep > CAP - 64) {          // the certified band itself is wider than the slots
+        over = true;
+        nkeep = k;
+        flim = kth;
+    }
+#pragma unroll
+    for (int j = 0; j < E; ++j)
+        if (j * 32 + lane < nkeep) __stcg(wbuf + (j * 32 + lane) * 32 + L, key[j]);
+    if (lane == L) {
+        cnt = nkeep;
+        lim = flim;
+        if (have_k && my_gthr) atomicMin(my_gthr, __float_as_uint(kth));
+        if (over && my_ovf) *my_ovf = 1;
+    }
+    __syncwarp();
+}
+
+// Lane-parallel compaction: every lane shrinks ITS OWN list at the same time (SIMT), so a tile at which all 32
+// queries of the warp compact costs one pass, not 32 warp-wide sorts.  Per lane:
+//   1. 8 samples of the list give a range [lo, hi] (hi = the admission limit once one exists);
+//   2. ONE pass over the distances builds a 16-bucket histogram of that range in packed 64-bit registers
+//      (8-bit counters while a list holds at most 256 slots, 16-bit beyond);
+//   3. the first bucket edge with at least k entries at or below it is a valid bound pd of the k-th best
+//      (entries below lo count in bucket 0, entries above hi in bucket 15, so the cumulative counts are exact);
+//   4. a second pass keeps, in place, the entries below min(lim, pd + 2 band).
+// Lanes that still cannot free enough slots (pathological ties) get the exact warp sort.
+template <int E>
+__device__ __noinline__ void sc_compact_lanes(uint64_t* wbuf, int& cnt, float& lim, float band2, int lane, int k, uint32_t* my_gthr,
+                                              int* my_ovf) {
+    constexpr int CAP = 32 * E;
+    const float inf = sc_inf();
+    constexpr int BITS = E > 4 && E <= 8 ? 8 : (E <= 4 ? 8 : 16);     // counter width: lists hold < 2^BITS entries
+    constexpr int PER = 64 / BITS, NREG = 16 / PER;
+    const bool act = cnt > k + 8;
+    const int n = act ? cnt : 0;
+    const int nmax = __reduce_max_sync(kFull, n);
+    const uint64_t* mine = wbuf + lane;
+    float lo = inf, hi = 0.f;
+    {
+        float sv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sv[j] = act ? slot_dist(mine + ((j * n) >> 3) * 32) : 0.f;
+        batch_fence(sv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            lo = fminf(lo, sv[j]);
+            hi = fmaxf(hi, sv[j]);
+        }
+    }
+    if (lim < inf) hi = lim;
+    const float scale = 16.f / fmaxf(hi - lo, 1e-30f);
+    unsigned long long h0 = 0, h1 = 0, h2 = 0, h3 = 0;      // 16 packed bucket counters (h2, h3 only when BITS == 16)
+    for (int i0 = 0; i0 < nmax; i0 += 32) {     // 32 independent loads in flight per round trip
+        float d[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) d[u] = (i0 + u < n) ? slot_dist(mine + (i0 + u) * 32) : -1.f;
+        batch_fence(d);
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+            const int b = min(max(__float2int_rd((d[u] - lo) * scale), 0), 15);
+            const unsigned long long one = (d[u] >= 0.f) ? (1ull << ((b % PER) * BITS)) : 0ull;
+            const int r = b / PER;
+            h0 += (r == 0) ? one : 0ull;
+            h1 += (r == 1) ? one : 0ull;
+            if (NREG > 2) {
+                h2 += (r == 2) ? one : 0ull;
+                h3 += (r == 3) ? one : 0ull;
+            }
+        }
+    }
+    // smallest bucket edge with at least k entries at or below it
+    float pd = inf;
+    int cum = 0;
+    bool found = false;
+#pragma unroll
+    for (int b = 0; b < 15; ++b) {              // the last bucket is open-ended: its edge bounds nothing
+        const unsigned long long hr = (b / PER == 0) ? h0 : (b / PER == 1) ? h1 : (b / PER == 2) ? h2 : h3;
+        cum += static_cast<int>((hr >> ((b % PER) * BITS)) & ((1ull << BITS) - 1));
+        if (!found && cum >= k) {
+            found = true;
+            // upper edge of bucket b, nudged up so that rounding in the bucket index can never put an entry above it
+            pd = (lo + static_cast<float>(b + 1) / scale) * 1.000001f + 1e-30f;
+        }
+    }
+    const float flim = fminf(lim, pd + band2);
+    int w = 0;
+    for (int i0 = 0; i0 < nmax; i0 += 16) {
+        uint64_t key[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) key[u] = (i0 + u < n) ? __ldcg(mine + (i0 + u) * 32) : kEmptyKey;
+        batch_fence(key);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            if (i0 + u < n && key_dist(key[u]) < flim) {
+                __stcg(wbuf + w * 32 + lane, key[u]);
+                ++w;
+            }
+        }
+    }
+    if (act) {
+        cnt = w;
+        lim = flim;
+        if (pd < inf && my_gthr) atomicMin(my_gthr, __float_as_uint(pd));
+    }
+    unsigned need = __ballot_sync(kFull, cnt > CAP - 32);
+    while (need) {
+        const int L = __ffs(need) - 1;
+        need &= need - 1;
+        sc_compact_sort<E>(L, wbuf, cnt, lim, band2, lane, k, my_gthr, my_ovf);
+    }
+}
+
+template <int E>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_b, const ScreenParams p) {
+    constexpr int CAP = 32 * E;
+    extern __shared__ uint8_t smem_raw[];
+    // identical carve-up in both CTAs of the pair (the dynamic window starts at the same offset in each)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const int num_kc = p.d_pad / 64 + 1;                                 // 64 fp16 = one 128-byte swizzle row; last chunk = aux
+    const int q_bytes = p.q_resident ? num_kc * SC_CHUNK_BYTES : 0;
+    const int stage_bytes = p.q_resident ? SC_CHUNK_BYTES : 2 * SC_CHUNK_BYTES;
+    const int n_stages = p.n_stages;
+    uint8_t* q_region = smem;
+    uint8_t* ring = smem + q_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + n_stages * stage_bytes);
+    uint64_t* full = bars;                              // [8]  leader: TMA bytes of both CTAs -> MMA
+    uint64_t* empty = bars + SC_MAX_STAGES;             // [8]  each CTA: MMA (multicast commit) -> its producer
+    uint64_t* tfull = bars + 2 * SC_MAX_STAGES;         // [2]  each CTA: MMA -> its epilogue
+    uint64_t* tempty = tfull + 2;                       // [2]  leader: epilogue warps of both CTAs -> MMA
+    uint64_t* qfull = tempty + 2;                       // leader: resident query tiles of both CTAs landed
+    uint64_t* qempty = qfull + 1;                       // each CTA: the item's last MMA retired, tile may be replaced
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qempty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_b);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < SC_MAX_STAGES; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], 1);
+            }
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(&tfull[a], 1);
+                mbar_init(&tempty[a], 2 * TC_EPI_WARPS);
+            }
+            mbar_init(qfull, 1);
+            mbar_init(qempty, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc_pair(tmem_slot, 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    const int n_items = p.n_items;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, qphase = 0;
+            const uint32_t qfull_leader = mapa_u32(smem_u32(qfull), 0);
+            for (int item = cluster_id; item < n_items; item += n_clusters) {
+                const ScItem it = sc_decode_item(p, item);
+                const int qrow0 = (it.pt * 2 + static_cast<int>(rank)) * TC_BM;
+                if (p.q_resident) {
+                    mbar_wait(qempty, qphase ^ 1);
+                    if (rank == 0) mbar_arrive_expect_tx(qfull, 2u * static_cast<uint32_t>(q_bytes));
+                    for (int kc = 0; kc < num_kc; ++kc)
+                        tma_load_2d_pair(q_region + kc * SC_CHUNK_BYTES, &tm_q, qfull_leader, kc * 64, qrow0);
+                    qphase ^= 1;
+                }
+                for (int t = it.t0; t < it.t1; ++t) {
+                    const int brow0 = t * TC_BN + static_cast<int>(rank) * (TC_BN / 2);
+                    for (int kc = 0; kc < num_kc; ++kc) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* st = ring + stage * stage_bytes;
+                        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2u * static_cast<uint32_t>(stage_bytes));
+                        const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
+                        tma_load_2d_pair(st, &tm_b, full_leader, kc * 64, brow0);
+                        if (!p.q_resident) tma_load_2d_pair(st + SC_CHUNK_BYTES, &tm_q, full_leader, kc * 64, qrow0);
+                        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA, one lane)
+        if (rank == 0 && lane == 0) {
+            // D fp32, A/B fp16 K-major, N = 256, M = 256 across the pair
+            constexpr uint32_t idesc = (1u << 4) | ((TC_BN >> 3) << 17) | (((2 * TC_BM) >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0, qphase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            long long w_full = 0, w_tempty = 0, t_begin = p.dbg ? clock64() : 0;
+            for (int item = cluster_id; item < n_items; item += n_clusters) {
+                const ScItem it = sc_decode_item(p, item);
+                if (p.q_resident) {
+                    mbar_wait(qfull, qphase);
+                    qphase ^= 1;
+                    tc_fence_after();
+                }
+                for (int t = it.t0; t < it.t1; ++t) {
+                    long long c0 = p.dbg ? clock64() : 0;
+                    mbar_wait(&tempty[acc], acc_phase ^ 1);
+                    if (p.dbg) w_tempty += clock64() - c0;
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + acc * TC_BN;
+                    for (int kc = 0; kc < num_kc; ++kc) {
+                        long long c1 = p.dbg ? clock64() : 0;
+                        mbar_wait(&full[stage], phase);
+                        if (p.dbg) w_full += clock64() - c1;
+                        tc_fence_after();
+                        const uint32_t sb = smem_u32(ring + stage * stage_bytes);
+                        const uint32_t sa = p.q_resident ? smem_u32(q_region + kc * SC_CHUNK_BYTES) : sb + SC_CHUNK_BYTES;
+                        const uint64_t a_desc = make_kmajor_desc(sa);
+                        const uint64_t b_desc = make_kmajor_desc(sb);
+                        if (kc + 1 < num_kc) {
+#pragma unroll
+                            for (int ks = 0; ks < TC_KCHUNK_BYTES / 32; ++ks) {
+                                const uint64_t off = static_cast<uint64_t>(ks * 2);   // one K step = 16 fp16 = 32 B
+                                umma_f16_pair(tmem_d, a_desc + off, b_desc + off, idesc, (kc | ks) != 0 ? 1u : 0u);
+                            }
+                        } else {
+                            umma_f16_pair(tmem_d, a_desc, b_desc, idesc, 1u);         // aux chunk: only its first 16 columns are used
+                        }
+                        tc_commit_pair(&empty[stage], 0x3);
+                        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit_pair(&tfull[acc], 0x3);
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                }
+                if (p.q_resident) tc_commit_pair(qempty, 0x3);
+            }
+            if (p.dbg) {
+                p.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
+                p.dbg[blockIdx.x * 8 + 1] = w_full;
+                p.dbg[blockIdx.x * 8 + 2] = w_tempty;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: certified screen (both CTAs)
+        const int g = warp & 3;                     // TMEM lane group this warp may read
+        const int half = (warp - 2) >> 2;           // which 128 of the tile's 256 database rows this warp scans
+        const float inf = sc_inf();
+        const float ymax2 = __uint_as_float(__ldg(p.dbstats + 0));
+        const float dymax = __uint_as_float(__ldg(p.dbstats + 1));
+        const float sy = __uint_as_float(__ldg(p.dbstats + 2));
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        long long w_tfull = 0, t_compact = 0, n_compact = 0, e_begin = p.dbg ? clock64() : 0;
+        uint32_t tempty_leader[2];
+        tempty_leader[0] = mapa_u32(smem_u32(&tempty[0]), 0);
+        tempty_leader[1] = mapa_u32(smem_u32(&tempty[1]), 0);
+        for (int item = cluster_id; item < n_items; item += n_clusters) {
+            const ScItem it = sc_decode_item(p, item);
+            const int qt = it.pt * 2 + static_cast<int>(rank);
+            const int q = qt * TC_BM + g * 32 + lane;
+            const float band2 = q < p.nq ? 2.f * screen_band(__ldg(p.qn + q), __ldg(p.dq + q), ymax2, dymax, sy, p.d_pad) : inf;
+            // queries with an unbounded band (unrepresentable rows) are answered by the exact fallback: skip them here
+            const bool valid = q < p.nq && band2 < inf;
+            const float qn = valid ? __ldg(p.qn + q) : 0.f;
+            const float Wq = valid ? -2.f * __ldg(p.sq + q) * sy : -1.f;      // dis~ = qn + Wq * acc'   (a negative power of two)
+            const float invW = 1.f / Wq;
+            // a row is a candidate iff dis~ < lim = (best known bound of the k-th smallest dis~) + 2 band
+            float lim = valid ? inf : -inf;
+            uint32_t* my_gthr = valid ? p.gthr + q : nullptr;
+            int* my_ovf = valid ? p.ovf + q : nullptr;
+            const size_t slot = sc_list_base(p, q < p.nq ? q : 0) + it.split * 2 + half;
+            uint64_t* wbuf = p.partial + (sc_list_base(p, (qt * TC_BM + g * 32) >> 5, 8) + it.split * 2 + half) * (32 * CAP);
+            int cnt = 0;
+            // Compactions stall the pair's whole pipeline (the accumulator cannot be handed back), so they run on a
+            // FIXED geometric schedule of tile indices: all 16 epilogue warps of the pair compact during the same tile
+            // and the stalls overlap instead of adding up; between two of them a list grows by only ~k ln(mul) entries.
+            // Later rounds are staggered by cluster so that the 74 pairs do not all hit L2 with their lists at once.
+            int next_sched = 1, round = 0;
+            for (int t = it.t0; t < it.t1; ++t) {
+                if (my_gthr) lim = fminf(lim, __uint_as_float(__ldcg(my_gthr)) + band2);
+                float thr = (lim - qn) * invW;              // acc' > thr  <=>  dis~ < lim
+                long long c2 = p.dbg ? clock64() : 0;
+                mbar_wait(&tfull[acc], acc_phase);
+                if (p.dbg) w_tfull += clock64() - c2;
+                tc_fence_after();
+                const uint32_t tcol = tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * TC_BN + half * (TC_BN / 2);
+                const int colbase = t * TC_BN + half * (TC_BN / 2);
+                uint32_t ra[32], rb[32];
+                // one 32-column chunk: 3-input max tree, then (rarely, per lane) the scan of the 8-column groups that hold a hit
+                auto scan = [&](const uint32_t (&r)[32], int col0) {
+                    // max tree whose inner nodes are kept: a hit is located by descending 32 -> 8 -> 3 columns
+                    float n3[4][3], n8[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        n3[j][0] = fmaxf(fmaxf(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])), __uint_as_float(r[8 * j + 2]));
+                        n3[j][1] = fmaxf(fmaxf(__uint_as_float(r[8 * j + 3]), __uint_as_float(r[8 * j + 4])), __uint_as_float(r[8 * j + 5]));
+                        n3[j][2] = fmaxf(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+                        n8[j] = fmaxf(fmaxf(n3[j][0], n3[j][1]), n3[j][2]);
+                    }
+                    const float m = fmaxf(fmaxf(fmaxf(n8[0], n8[1]), n8[2]), n8[3]);
+                    if (m > thr) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (n8[j] > thr) {
+#pragma unroll
+                                for (int s3 = 0; s3 < 3; ++s3) {
+                                    if (n3[j][s3] > thr) {
+#pragma unroll
+                                        for (int c = 3 * s3; c < (s3 == 2 ? 8 : 3 * s3 + 3); ++c) {
+                                            const float v = __uint_as_float(r[8 * j + c]);
+                                            if (v > thr) {
+                                                __stcg(wbuf + cnt * 32 + lane,
+                                                       pack_key(fmaxf(fmaf(v, Wq, qn), 0.f), static_cast<uint32_t>(col0 + 8 * j + c)));
+                                                ++cnt;
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (__any_sync(kFull, cnt > CAP - 32)) {
+                        long long c3 = p.dbg ? clock64() : 0;
+                        int cnt2 = cnt;                 // copies: references into a noinline call would pin cnt/lim in local memory
+                        float lim2 = lim;
+                        sc_compact_lanes<E>(wbuf, cnt2, lim2, band2, lane, p.k, my_gthr, my_ovf);
+                        cnt = cnt2;
+                        lim = lim2;
+                        thr = (lim - qn) * invW;
+                        if (p.dbg) { t_compact += clock64() - c3; n_compact += 1; }
+                    }
+                };
+                // software pipeline over the 4 chunks: the next tcgen05.ld is in flight while this chunk is scanned
+                tmem_ld32(tcol, ra);
+                tmem_ld_wait();
+                tmem_ld32(tcol + 32, rb);
+                scan(ra, colbase);
+                tmem_ld_wait();
+                tmem_ld32(tcol + 64, ra);
+                scan(rb, colbase + 32);
+                tmem_ld_wait();
+                tmem_ld32(tcol + 96, rb);
+                scan(ra, colbase + 64);
+                tmem_ld_wait();
+                // all TMEM reads of this accumulator have landed in registers: hand it back before the last scan
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
+                scan(rb, colbase + 96);
+                if (t - it.t0 + 1 == next_sched) {
+                    ++round;
+                    int base = 1;
+                    for (int r = 0; r < round; ++r) base *= p.sched_mul;
+                    next_sched = base + (round >= 3 ? ((cluster_id & 7) * base * (p.sched_mul - 1)) >> 4 : 0);
+                    if (__any_sync(kFull, cnt > p.k + 8)) {
+                        long long c3 = p.dbg ? clock64() : 0;
+                        int cnt2 = cnt;
+                        float lim2 = lim;
+                        sc_compact_lanes<E>(wbuf, cnt2, lim2, band2, lane, p.k, my_gthr, my_ovf);
+                        cnt = cnt2;
+                        lim = lim2;
+                        if (p.dbg) { t_compact += clock64() - c3; n_compact += 1; }
+                    }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+            if (q < p.nq) p.pcount[slot] = cnt;
+        }
+        if (p.dbg && warp == 2 && lane == 0) {
+            p.dbg[blockIdx.x * 8 + 3] = clock64() - e_begin;
+            p.dbg[blockIdx.x * 8 + 4] = w_tfull;
+            p.dbg[blockIdx.x * 8 + 5] = t_compact;
+            p.dbg[blockIdx.x * 8 + 6] = n_compact;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // no CTA may exit while its peer can still signal its barriers or read its tile
+    if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+}
+
+template <int E>
+cudaError_t launch_knn_screen(const CUtensorMap& tq, const CUtensorMap& tb, const ScreenParams& p, int grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(knn_screen_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    knn_screen_kernel<E><<<grid, TC_THREADS, smem, st>>>(tq, tb, p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Finish of the screen.  One warp per query:
+//   1. concatenate the query's candidate lists (all splits, both column halves) through a 32*E-entry
+//      staging buffer, sorting whenever it fills and keeping the certified band below k-th + 2 band;
+//   2. recompute the nb survivors exactly: fp32 difference form over the raw rows (4 rows in flight per lane);
+//   3. sort by (exact distance, id) and emit the best k, padded (FLT_MAX, -1) like faiss.
+// Queries whose band overflowed (here or in the sweep) are appended to ovf_list for the exact fallback.
+template <int E>
+__global__ void __launch_bounds__(128) screen_finalize_kernel(const uint64_t* __restrict__ partial, const int* __restrict__ pcount,
+                                                              int slot_stride, int64_t nq, int n_full_items, int rem_splits, int k,
+                                                              const float* __restrict__ xq, const float* __restrict__ xb, int d,
+                                                              int d_pad, const float* __restrict__ qn, const float* __restrict__ dq,
+                                                              const uint32_t* __restrict__ dbstats, const int* __restrict__ ovf_in,
+                                                              int* __restrict__ ovf_count, int* __restrict__ ovf_list, int64_t id_base,
+                                                              float* __restrict__ D, int64_t* __restrict__ I) {
+    constexpr int CAP = 32 * E;
+    extern __shared__ uint64_t sstage[];   // [warps][CAP] keys | [warps][CAP] float exact distances | [warps][257] prefix
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int64_t q = static_cast<int64_t>(blockIdx.x) * warps + warp;
+    if (q >= nq) return;
+    uint64_t* buf = sstage + warp * CAP;
+    float* sd = reinterpret_cast<float*>(sstage + warps * CAP) + warp * CAP;
+    int* prefix = reinterpret_cast<int*>(reinterpret_cast<float*>(sstage + warps * CAP) + warps * CAP) + warp * (kMaxRaggedLists + 1);
+    const float inf = sc_inf();
+    const float band2 = 2.f * screen_band(qn[q], dq[q], __uint_as_float(dbstats[0]), __uint_as_float(dbstats[1]), __uint_as_float(dbstats[2]), d_pad);
+    bool over = ovf_in[q] != 0 || !(band2 < inf);      // unbounded band: the sweep skipped this query
+    const bool split_q = q >= static_cast<int64_t>(n_full_items) * 2 * TC_BM;
+    const int n_lists = split_q ? 2 * rem_splits : 2;
+    const int* pc = pcount + sc_list_base(n_full_items, rem_splits, q, 2 * TC_BM);
+
+    int running = 0;
+    for (int base = 0; base < n_lists; base += 32) {
+        const int l = base + lane;
+        const int c = (l < n_lists) ? pc[l] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (l < n_lists) prefix[l] = running + incl - c;
+        running += __shfl_sync(kFull, incl, 31);
+    }
+    if (lane == 0) prefix[n_lists] = running;
+    __syncwarp();
+    const int total = running;
+    const uint64_t* src = partial + sc_list_base(n_full_items, rem_splits, q >> 5, 8) * (32 * static_cast<size_t>(slot_stride)) + (q & 31);
+
+    uint64_t key[E];
+    int fill = 0, done = 0;
+    // sort the staged keys, keep the band below k-th + 2 band; `last` = nothing more will be staged
+    auto sort_keep = [&](bool last) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < E; ++j) key[j] = (j * 32 + lane < fill) ? buf[j * 32 + lane] : kEmptyKey;
+        warp_bitonic_sort<E>(key, lane);
+        const float kth = (fill >= k) ? key_dist(warp_get<E>(key, k - 1)) : inf;
+        const float flim = kth + band2;
+        int mine = 0;
+#pragma unroll
+        for (int j = 0; j < E; ++j) mine += (key[j] != kEmptyKey && key_dist(key[j]) < flim) ? 1 : 0;
+        int nkeep = __reduce_add_sync(kFull, mine);
+        if (!last && nkeep > CAP - 32) {          // no room to stage the rest next to the band
+            over = true;
+            nkeep = k;
+        }
+#pragma unroll
+        for (int j = 0; j < E; ++j)
+            if (j * 32 + lane < nkeep) buf[j * 32 + lane] = key[j];
+        fill = nkeep;
+        __syncwarp();
+    };
+    while (done < total) {
+        const int take = min(CAP - fill, total - done);
+        for (int i = lane; i < take; i += 32) {
+            const int e = done + i;
+            int lo = 0, hi = n_lists;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (prefix[mid] <= e) lo = mid; else hi = mid;
+            }
+            buf[fill + i] = __ldcg(src + static_cast<int64_t>(lo) * (32 * slot_stride) + (e - prefix[lo]) * 32);
+        }
+        fill += take;
+        done += take;
+        sort_keep(done >= total);
+    }
+    const int nb = fill;      // certified band: every row that can be in the true top-k is among buf[0..nb)
+
+    // exact distances of the band
+    const float* qrow = xq + q * d;
+    const bool vec = ((d & 3) == 0) && (((reinterpret_cast<uintptr_t>(xq) | reinterpret_cast<uintptr_t>(xb)) & 15) == 0);
+    for (int r0 = 0; r0 < nb; r0 += 4) {
+        const float* row[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) row[u] = xb + static_cast<int64_t>(key_idx(buf[min(r0 + u, nb - 1)])) * d;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec) {
+            for (int c = lane; c < (d >> 2); c += 32) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(qrow) + c);
+                float4 b[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) b[u] = __ldg(reinterpret_cast<const float4*>(row[u]) + c);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float t;
+                    t = a.x - b[u].x; acc[u] = fmaf(t, t, acc[u]);
+                    t = a.y - b[u].y; acc[u] = fmaf(t, t, acc[u]);
+                    t = a.z - b[u].z; acc[u] = fmaf(t, t, acc[u]);
+                    t = a.w - b[u].w; acc[u] = fmaf(t, t, acc[u]);
+                }
+            }
+        } else {
+            for (int c = lane; c < d; c += 32) {
+                const float a = __ldg(qrow + c);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float t = a - __ldg(row[u] + c);
+                    acc[u] = fmaf(t, t, acc[u]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(kFull, acc[u], o);
+        }
+        if (lane < 4 && r0 + lane < nb) sd[r0 + lane] = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+        const int i = j * 32 + lane;
+        key[j] = (i < nb) ? pack_key(sd[i], key_idx(buf[i])) : kEmptyKey;
+    }
+    warp_bitonic_sort<E>(key, lane);
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+        const int i = j * 32 + lane;
+        if (i < k) {
+            const bool empty = key[j] == kEmptyKey;
+            D[q * k + i] = empty ? kFltMax : key_dist(key[j]);
+            I[q * k + i] = empty ? -1 : id_base + static_cast<int64_t>(key_idx(key[j]));
+        }
+    }
+    if (over && lane == 0) ovf_list[atomicAdd(ovf_count, 1)] = static_cast<int>(q);
+}
+
+template <int E>
+cudaError_t launch_screen_finalize(const uint64_t* partial, const int* pcount, int slot_stride, int64_t nq, int n_full_items, int rem_splits, int k,
+                                   const float* xq, const float* xb, int d, int d_pad, const float* qn, const float* dq,
+                                   const uint32_t* dbstats, const int* ovf_in, int* ovf_count, int* ovf_list, int64_t id_base, float* D,
+                                   int64_t* I, cudaStream_t st) {
+    constexpr int warps = 4;
+    if (2 * rem_splits > kMaxRaggedLists) return cudaErrorInvalidValue;
+    const size_t smem = warps * 32 * E * (sizeof(uint64_t) + sizeof(float)) + warps * (kMaxRaggedLists + 1) * sizeof(int);
+    screen_finalize_kernel<E><<<static_cast<unsigned>((nq + warps - 1) / warps), warps * 32, smem, st>>>(
+        partial, pcount, slot_stride, nq, n_full_items, rem_splits, k, xq, xb, d, d_pad, qn, dq, dbstats, ovf_in, ovf_count, ovf_list, id_base, D, I);
+    return cudaGetLastError();
+}
+
+}  // namespace agp

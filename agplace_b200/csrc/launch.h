@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math.h>
 
 namespace agp {
 
@@ -38,6 +39,44 @@ struct TcParams {
     uint32_t* gthr;         // [nq] shared pruning bound (fp32 bits, +inf initially); nullptr disables sharing
 };
 
+// Single-pass certified screen (knn_screen.cuh): one fp16 plane per operand, CTA pairs (cta_group::2).
+struct ScreenParams {
+    int nq;
+    int d_pad;
+    int k;
+    int n_ptiles;           // 256-query pair tiles (each CTA of the pair owns 128 of them)
+    int n_full_items;       // pair tiles swept unsplit (multiple of the number of clusters)
+    int rem_splits;         // database ranges each remaining pair tile is split into
+    int list_splits;        // candidate lists are indexed [q][list_splits][2]
+    int n_items;
+    int n_dbtiles;
+    int q_resident;         // 1: the CTA's query tile stays in shared memory for a whole item (d_pad <= 512)
+    int n_stages;           // depth of the operand ring
+    int sched_mul;          // scheduled compactions after tiles 1, mul, mul^2, ... of an item
+    const float* qn;        // [nq] |q|^2
+    const float* sq;        // [nq] query row scale 2^eq
+    const float* dq;        // [nq] |q - fp16 plane| (rounded up)
+    const uint32_t* dbstats;// fp32 bits: [0] max |y|^2, [1] max |y - fp16 plane|, [2] database scale sy = 2^eg
+    uint64_t* partial;      // candidate slots, bundles of 32 queries x 32*E entries per list (knn_screen.cuh:sc_list_base)
+    int* pcount;            // entries per list
+    uint32_t* gthr;         // [nq] smallest known upper bound of the k-th best screened distance
+    int* ovf;               // [nq] set when a query's certified band did not fit its slots
+    long long* dbg;
+};
+
+// |screened distance - true distance| <= screen_band(): fp16 rounding of both operands (Cauchy-Schwarz on the
+// measured residual norms), round-toward-zero fp32 accumulation in the tensor core, fp32 epilogue arithmetic.
+//   2 (|dq| |y| + |q| |dy|)        fp16 rounding of the two operand planes (Cauchy-Schwarz on the residual norms)
+//   2 c_acc (|q||y| + |y|^2)       tensor-core accumulation over K = d_pad + 16 (products exact, sums truncated)
+//   2^-20 (|q|^2 + |y|^2)          fp32 norms and the epilogue's fma
+//   2^-24 sy + 2^-32 |y|^2         three-piece fp16 representation of -|y|^2 / (2 sy) in the aux chunk
+__host__ __device__ inline float screen_band(float qn2, float dq, float ymax2, float dymax, float sy, int d_pad) {
+    const float nq = sqrtf(qn2) * 1.0001f, ymax = sqrtf(ymax2) * 1.0001f;
+    const float c_acc = static_cast<float>(d_pad / 16 + 17) * 2.3841858e-7f;     // 2^-22 per K = 16 step
+    return 2.002f * (dq * ymax + nq * dymax) + 2.f * c_acc * (nq * ymax + ymax2) + 9.5367432e-7f * (qn2 + ymax2) +
+           5.9604645e-8f * sy + 2.3283064e-10f * ymax2;
+}
+
 // smallest power-of-two register count E with 32*E >= 2*k (>= 64 keys)
 inline int sel_regs_for_k(int k) {
     int e = 2;
@@ -49,6 +88,14 @@ inline int sel_regs_for_k(int k) {
 template <int E>
 cudaError_t launch_knn_tc(const CUtensorMap& qhi, const CUtensorMap& qlo, const CUtensorMap& bhi, const CUtensorMap& blo,
                           const TcParams& p, int grid, cudaStream_t st);
+template <int E>
+cudaError_t launch_knn_screen(const CUtensorMap& tq, const CUtensorMap& tb, const ScreenParams& p, int grid, size_t smem, cudaStream_t st);
+// exact selection among the screened candidates + fp32 difference-form re-rank of the certified band
+template <int E>
+cudaError_t launch_screen_finalize(const uint64_t* partial, const int* pcount, int slot_stride, int64_t nq, int n_full_items, int rem_splits, int k,
+                                   const float* xq, const float* xb, int d, int d_pad, const float* qn, const float* dq,
+                                   const uint32_t* dbstats, const int* ovf_in, int* ovf_count, int* ovf_list, int64_t id_base, float* D,
+                                   int64_t* I, cudaStream_t st);
 template <int E>
 cudaError_t launch_select_rows(const float* dist, int64_t ld, int64_t n, int k, int nq, int n_chunks, uint64_t* partial,
                                cudaStream_t st);
@@ -71,7 +118,15 @@ cudaError_t launch_prep_rows(bool split, const float* x, int64_t n, int d, int d
                              cudaStream_t st);
 // fp16 planes of the power-of-two scaled rows; scale[r] = factor * 2^ex (factor = 1 for queries, -2 for database rows)
 cudaError_t launch_prep_rows_f16(const float* x, int64_t n, int d, int d_pad, float* norm, void* hi, void* lo, float* scale, float factor,
-                                 int max_blocks, cudaStream_t st);
+                                 float* dres, uint32_t* stats, int max_blocks, cudaStream_t st);
+// single-pass screen planes: [rows, d_pad + 64] fp16 = scaled row + aux chunk (k_misc.cu:prep_rows_screen_kernel)
+cudaError_t launch_prep_rows_screen(const float* x, int64_t n, int d, int d_pad, void* plane, float* norm, float* scale_out, float* dres,
+                                    uint32_t* stats, int is_db, int max_blocks, cudaStream_t st);
+cudaError_t launch_fix_db_scale(const float* x, int64_t count, uint32_t* stats, int max_blocks, cudaStream_t st);
+cudaError_t launch_init_aux(void* plane, int d_pad, int64_t row0, int64_t row1, cudaStream_t st);
+// rows out[i] = x[list[i]] and results D/I[list[i]] = Dt/It[i] (exact fallback of overflowed queries)
+cudaError_t launch_gather_rows(const float* x, const int* list, int n, int d, float* out, cudaStream_t st);
+cudaError_t launch_scatter_results(const float* Dt, const int64_t* It, const int* list, int n, int k, float* D, int64_t* I, cudaStream_t st);
 cudaError_t launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st);
 cudaError_t launch_diff_small(const float* xq, int nq, const float* xb, int64_t n, int d, float* dist, int64_t ld, int num_sms,
                               cudaStream_t st);

@@ -175,6 +175,13 @@ class IndexFlatL2:
         return ms.value, n.value
 
 
+    def get_stats(self):
+        """(queries answered by the single-pass screen, queries re-run through the 3xFP16 fallback)."""
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self._lib.agp_index_get_stats(self._h, ctypes.byref(a), ctypes.byref(b)), "agp_index_get_stats")
+        return a.value, b.value
+
+
 def positives_to_csr(positives_per_query):
     """Reference format (object array / list of unsorted int arrays, test.py:73) -> CSR int64."""
     lens = np.fromiter((len(p) for p in positives_per_query), dtype=np.int64, count=len(positives_per_query))

@@ -35,11 +35,13 @@ typedef struct agp_index agp_index;
 enum agp_mem_kind { AGP_MEM_HOST = 0, AGP_MEM_DEVICE = 1 };
 
 enum agp_precision {
-    AGP_PRECISION_AUTO = 0,       /* faiss's own switch: nq < 20 exact difference form, else tensor cores (3xFP16) */
+    AGP_PRECISION_AUTO = 0,       /* faiss's own switch: nq < 20 exact difference form, else tensor cores (certified screen) */
     AGP_PRECISION_FP32_SIMT = 1,  /* fp32 FMA on CUDA cores, expansion form (reference/cross-check mode)       */
     AGP_PRECISION_3XTF32 = 2,     /* always the tcgen05 3xTF32 fused kernel                                    */
     AGP_PRECISION_EXACT_DIFF = 3, /* always the difference form (nq processed in groups of < 20)               */
-    AGP_PRECISION_3XFP16 = 4      /* always the tcgen05 kernel on fp16 hi/lo planes of power-of-two scaled rows */
+    AGP_PRECISION_3XFP16 = 4,     /* always the tcgen05 kernel on fp16 hi/lo planes of power-of-two scaled rows */
+    AGP_PRECISION_FP16_SCREEN = 5 /* always the single-pass certified fp16 screen (CTA pairs) + exact fp32 finish;
+                                     queries whose certified band overflows fall back to 3xFP16               */
 };
 
 enum agp_error {
@@ -94,6 +96,10 @@ AGP_API int agp_index_set_id_base(agp_index* idx, int64_t id_base);
  * synchronise per search while enabled).  get returns accumulated milliseconds and launches. */
 AGP_API int agp_index_set_profiling(agp_index* idx, int enable);
 AGP_API int agp_index_get_profile(agp_index* idx, double* kernel_ms, int64_t* kernel_launches, int reset);
+
+/* Counters of the single-pass screen: queries it answered, and how many of those had to be re-run
+ * through the 3xFP16 kernel because their certified candidate band did not fit (diagnostics). */
+AGP_API int agp_index_get_stats(const agp_index* idx, int64_t* screened_queries, int64_t* fallback_queries);
 
 /* K4 across shards: merge n_lists per-shard results (device memory, e.g. the output of one NCCL
  * all-gather) into one canonical list per query.  List g holds D at D_lists + g * d_list_stride
