@@ -16,7 +16,7 @@ from oracle import flatl2_oracle as orc
 from tests.helpers import make_mining_problem, reference_recall_loop
 
 GOLDEN = sorted((Path(__file__).parent / "golden").glob("*.npz"))
-MODES = ["auto", "3xtf32", "3xfp16", "fp32_simt", "exact_diff"]
+MODES = ["auto", "fp16_screen", "3xtf32", "3xfp16", "fp32_simt", "exact_diff"]
 FLT_MAX = np.float32(3.4028234663852886e38)
 
 
@@ -53,7 +53,7 @@ SHAPES = [  # nq, n, d, k
 ]
 
 
-@pytest.mark.parametrize("precision", ["auto", "3xtf32", "3xfp16", "fp32_simt"])
+@pytest.mark.parametrize("precision", ["auto", "fp16_screen", "3xtf32", "3xfp16", "fp32_simt"])
 @pytest.mark.parametrize("nq,n,d,k", SHAPES)
 def test_random_shapes_match_oracle(nq, n, d, k, precision):
     rng = np.random.default_rng(nq * 7 + n * 3 + d + k)
@@ -126,10 +126,49 @@ def test_huge_norms_zeros_and_exact_ties_across_tiles():
     base = rng.integers(-3, 4, size=(1, 32)).astype(np.float32)
     xb2 = np.repeat(base, 5000, axis=0)
     xq2 = rng.integers(-3, 4, size=(40, 32)).astype(np.float32)
-    for precision in ("3xtf32", "fp32_simt"):
+    for precision in ("auto", "3xtf32", "fp32_simt"):
         D2, I2 = search(xb2, xq2, 64, precision)
         np.testing.assert_array_equal(I2, np.tile(np.arange(64), (40, 1)))
         assert (D2 == D2[:, :1]).all()
+
+
+def test_screen_certified_band_and_fallback():
+    """The single-pass fp16 screen must return the fp64-true neighbour set whatever the data looks like: a
+    band that does not fit (mass duplicates) or rows the fp16 plane cannot hold (mixed magnitudes, tiny or
+    huge scales) are answered by the exact fallback, visible in get_stats()."""
+    rng = np.random.default_rng(21)
+    # (a) well-behaved descriptors: no fallback at all
+    xb = rng.standard_normal((6000, 128)).astype(np.float32); xb /= np.linalg.norm(xb, axis=1, keepdims=True)
+    xq = rng.standard_normal((300, 128)).astype(np.float32); xq /= np.linalg.norm(xq, axis=1, keepdims=True)
+    ix = agp().IndexFlatL2(128, precision="fp16_screen"); ix.add(xb)
+    D, I = ix.search(xq, 25)
+    assert ix.get_stats() == (300, 0)
+    D64, I64 = orc.knn_fp64(xq, xb, 25)
+    ok, msg = orc.compare_knn(D, I, D64.astype(np.float32), I64)
+    assert ok, msg
+    # (b) 3 distinct rows repeated 2000 times: every band overflows -> all queries re-run exactly, ids ascending
+    xb2 = xb[rng.integers(0, 3, 6000)]
+    ix2 = agp().IndexFlatL2(128, precision="fp16_screen"); ix2.add(xb2)
+    D2, I2 = ix2.search(xq, 25)
+    assert ix2.get_stats()[1] == 300
+    Dr, Ir = orc.knn_fp32(xq, xb2, 25)
+    ok, msg = orc.compare_knn(D2, I2, Dr, Ir, xq=xq, xb=xb2, abs_floor_eps=8 * 2.0 ** -24)
+    assert ok, msg
+    # (c) magnitudes spread over 12 decades inside one database, and queries likewise
+    scale_b = (10.0 ** rng.uniform(-6, 6, size=(4000, 1))).astype(np.float32)
+    xb3 = (rng.standard_normal((4000, 64)).astype(np.float32)) * scale_b
+    xq3 = xb3[rng.integers(0, 4000, 120)] * (1 + 1e-3 * rng.standard_normal((120, 64)).astype(np.float32))
+    ix3 = agp().IndexFlatL2(64, precision="fp16_screen"); ix3.add(xb3[:1000]); ix3.add(xb3[1000:])
+    D3, I3 = ix3.search(xq3, 5)
+    D64, I64 = orc.knn_fp64(xq3, xb3, 5)
+    ok, msg = orc.compare_knn(D3, I3, D64.astype(np.float32), I64, xq=xq3, xb=xb3, abs_floor_eps=8 * 2.0 ** -24)
+    assert ok, msg
+    # (d) reset picks a new database scale
+    ix3.reset(); ix3.add(xb[:, :64] * 1e-3)
+    D4, I4 = ix3.search(xq[:, :64] * 1e-3, 10)
+    D64, I64 = orc.knn_fp64(xq[:, :64] * 1e-3, xb[:, :64] * 1e-3, 10)
+    ok, msg = orc.compare_knn(D4, I4, D64.astype(np.float32), I64)
+    assert ok, msg
 
 
 def test_add_in_chunks_reset_and_reuse():
