@@ -26,7 +26,7 @@ CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = (
     [("agpknn.cu", None, "agpknn.o"), ("k_misc.cu", None, "k_misc.o")]
     + [("k_tc.cu", e, f"k_tc_{e}.o") for e in (2, 4, 8, 16)]
-    + [("k_screen.cu", e, f"k_screen_{e}.o") for e in (2, 4, 8, 16)]
+    + [("k_screen.cu", e, f"k_screen_{e}.o") for e in (8, 16)]
     + [("k_select.cu", e, f"k_select_{e}.o") for e in (2, 4, 8, 16, 32)]
 )
 

@@ -74,7 +74,7 @@ struct agp_index {
     int kind = KIND_TF32, elem_bytes = 4;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     Buf q_raw, q_hi, q_lo, qn, sq, cand, partial, panel, d_out, i_out, gthr, cand_d, cand_i, dbg;
-    Buf dq, ovf, ovf_list, ovf_x, ovf_d, ovf_i;     // single-pass screen: residual norms, overflow flags / list / fallback scratch
+    Buf dq, ovf, ovf_list, ovf_x, ovf_d, ovf_i, hthr;     // single-pass screen: residual norms, overflow flags / list / fallback scratch
     uint32_t* dbstats = nullptr;                     // [4] max |y|^2, max |y - fp16(y)| over the database (fp32 bits)
     int* h_count = nullptr;                          // pinned host word for the overflow count
     int64_t stat_screened = 0, stat_fallback = 0;
@@ -457,18 +457,15 @@ static int screen_regs_for_k(int k) {
     const int kc_est = k + std::max(16, k / 4);
     if (env_e) {
         const int e = atoi(env_e);
-        if ((e == 2 || e == 4 || e == 8 || e == 16) && 32 * e - 64 >= kc_est + 16) return e;
+        if ((e == 8 || e == 16) && 32 * e - 128 >= kc_est + 16) return e;
     }
-    int e = 2;
-    while ((32 * e < kc_est + kc_est / 2 + 32 || 32 * e - 64 < kc_est + 16) && e < 16) e <<= 1;
-    return e;
+    // a list must hold k + band next to one whole tile (128 columns) of new admissions
+    return (32 * 8 - 128 >= kc_est + 32) ? 8 : 16;
 }
 
 #define DISPATCH_EV(e, fn, ...)                                                                  \
     [&]() -> int {                                                                               \
         switch (e) {                                                                             \
-            case 2: LAUNCH(fn<2>(__VA_ARGS__)); return 0;                                        \
-            case 4: LAUNCH(fn<4>(__VA_ARGS__)); return 0;                                        \
             case 8: LAUNCH(fn<8>(__VA_ARGS__)); return 0;                                        \
             case 16: LAUNCH(fn<16>(__VA_ARGS__)); return 0;                                      \
             default: return set_err(AGP_EINVAL, "unsupported register budget %d", e);            \
@@ -527,6 +524,7 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         p.q_resident = resident;
         p.n_stages = n_stages;
         p.sched_mul = 2;
+        { const char* e = getenv("AGP_SCREEN_SKIP_EPI"); p.debug_skip_epilogue = (e && atoi(e) != 0) ? 1 : 0; }
         { const char* e = getenv("AGP_SCREEN_SCHED"); if (e && atoi(e) >= 2) p.sched_mul = atoi(e); }
         const int grid = 2 * std::min(p.n_items, clusters);
         const size_t n_lists_total = static_cast<size_t>(p.n_full_items) * 2 * TC_BM * 2 + static_cast<size_t>(rem_tiles) * 2 * TC_BM * 2 * p.rem_splits;
@@ -539,6 +537,9 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         CK(cudaMemsetAsync(ix->ovf.p, 0, static_cast<size_t>(nqc) * sizeof(int), ix->stream));
         CK(cudaMemsetAsync(ix->ovf_list.p, 0, sizeof(int), ix->stream));
         LAUNCH(launch_fill_f32(static_cast<float*>(ix->gthr.p), nqc, HUGE_VALF, ix->stream));
+        CKR(ensure(ix->hthr, n_lists_total * sizeof(uint32_t)));
+        LAUNCH(launch_fill_f32(static_cast<float*>(ix->hthr.p), static_cast<int64_t>(n_lists_total), HUGE_VALF, ix->stream));
+        p.hthr = static_cast<uint32_t*>(ix->hthr.p);
         p.qn = static_cast<const float*>(ix->qn.p);
         p.sq = static_cast<const float*>(ix->sq.p);
         p.dq = static_cast<const float*>(ix->dq.p);
@@ -668,7 +669,7 @@ void agp_index_free(agp_index* ix) {
     if (ix->wx) cudaFree(ix->wx);
     if (ix->xs) cudaFree(ix->xs);
     free_buf(ix->sq);
-    free_buf(ix->dq); free_buf(ix->ovf); free_buf(ix->ovf_list); free_buf(ix->ovf_x); free_buf(ix->ovf_d); free_buf(ix->ovf_i);
+    free_buf(ix->dq); free_buf(ix->hthr); free_buf(ix->ovf); free_buf(ix->ovf_list); free_buf(ix->ovf_x); free_buf(ix->ovf_d); free_buf(ix->ovf_i);
     if (ix->dbstats) cudaFree(ix->dbstats);
     if (ix->h_count) cudaFreeHost(ix->h_count);
     free_buf(ix->q_raw); free_buf(ix->q_hi); free_buf(ix->q_lo); free_buf(ix->qn); free_buf(ix->cand);

@@ -99,7 +99,7 @@ __device__ __noinline__ void sc_compact_sort(int L, uint64_t* wbuf, int& cnt, fl
     for (int j = 0; j < E; ++j) mine += (key[j] != kEmptyKey && key_dist(key[j]) < flim) ? 1 : 0;
     int nkeep = __reduce_add_sync(kFull, mine);
     bool over = false;
-    if (nkeep > CAP - 64) {          // the certified band itself is wider than the slots
+    if (nkeep > CAP - TC_BN / 2) {   // the certified band itself is wider than the slots can hold next to one tile of admissions
         over = true;
         nkeep = k;
         flim = kth;
@@ -126,8 +126,8 @@ __device__ __noinline__ void sc_compact_sort(int L, uint64_t* wbuf, int& cnt, fl
 //   4. a second pass keeps, in place, the entries below min(lim, pd + 2 band).
 // Lanes that still cannot free enough slots (pathological ties) get the exact warp sort.
 template <int E>
-__device__ __noinline__ void sc_compact_lanes(uint64_t* wbuf, int& cnt, float& lim, float band2, int lane, int k, uint32_t* my_gthr,
-                                              int* my_ovf) {
+__device__ __forceinline__ void sc_compact_lanes(uint64_t* wbuf, int& cnt, float& lim, float band2, int lane, int k, uint32_t* my_gthr,
+                                                 uint32_t* my_hthr, int* my_ovf) {
     constexpr int CAP = 32 * E;
     const float inf = sc_inf();
     constexpr int BITS = E > 4 && E <= 8 ? 8 : (E <= 4 ? 8 : 16);     // counter width: lists hold < 2^BITS entries
@@ -170,19 +170,22 @@ __device__ __noinline__ void sc_compact_lanes(uint64_t* wbuf, int& cnt, float& l
         }
     }
     // smallest bucket edge with at least k entries at or below it
-    float pd = inf;
+    // ... and, for the pair-wide bound, with at least ceil(k/2): if BOTH column halves of a query have that many entries
+    // at or below x, the query has k rows at or below x (see the caller).
+    float pd = inf, pdh = inf;
     int cum = 0;
-    bool found = false;
+    bool found = false, foundh = false;
+    const int kh = (k + 1) >> 1;
 #pragma unroll
     for (int b = 0; b < 15; ++b) {              // the last bucket is open-ended: its edge bounds nothing
         const unsigned long long hr = (b / PER == 0) ? h0 : (b / PER == 1) ? h1 : (b / PER == 2) ? h2 : h3;
         cum += static_cast<int>((hr >> ((b % PER) * BITS)) & ((1ull << BITS) - 1));
-        if (!found && cum >= k) {
-            found = true;
-            // upper edge of bucket b, nudged up so that rounding in the bucket index can never put an entry above it
-            pd = (lo + static_cast<float>(b + 1) / scale) * 1.000001f + 1e-30f;
-        }
+        // upper edge of bucket b, nudged up so that rounding in the bucket index can never put an entry above it
+        const float edge = (lo + static_cast<float>(b + 1) / scale) * 1.000001f + 1e-30f;
+        if (!foundh && cum >= kh) { foundh = true; pdh = edge; }
+        if (!found && cum >= k) { found = true; pd = edge; }
     }
+    if (act && pdh < inf && my_hthr) atomicMin(my_hthr, __float_as_uint(pdh));
     const float flim = fminf(lim, pd + band2);
     int w = 0;
     for (int i0 = 0; i0 < nmax; i0 += 16) {
@@ -203,11 +206,15 @@ __device__ __noinline__ void sc_compact_lanes(uint64_t* wbuf, int& cnt, float& l
         lim = flim;
         if (pd < inf && my_gthr) atomicMin(my_gthr, __float_as_uint(pd));
     }
-    unsigned need = __ballot_sync(kFull, cnt > CAP - 32);
+    unsigned need = __ballot_sync(kFull, cnt > CAP - TC_BN / 2);
     while (need) {
         const int L = __ffs(need) - 1;
         need &= need - 1;
-        sc_compact_sort<E>(L, wbuf, cnt, lim, band2, lane, k, my_gthr, my_ovf);
+        int cnt2 = cnt;                 // copies: references into a noinline call would pin cnt / lim in local memory
+        float lim2 = lim;
+        sc_compact_sort<E>(L, wbuf, cnt2, lim2, band2, lane, k, my_gthr, my_ovf);
+        cnt = cnt2;
+        lim = lim2;
     }
 }
 
@@ -378,6 +385,10 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             // a row is a candidate iff dis~ < lim = (best known bound of the k-th smallest dis~) + 2 band
             float lim = valid ? inf : -inf;
             uint32_t* my_gthr = valid ? p.gthr + q : nullptr;
+            // pair-wide bound: hthr[list] = bound of the ceil(k/2)-th best of one column half; max over the two halves of
+            // this (query, split) bounds the query's k-th best over everything both halves have swept
+            uint32_t* my_hthr = valid ? p.hthr + (sc_list_base(p, q) + it.split * 2 + half) : nullptr;
+            const uint32_t* peer_hthr = valid ? p.hthr + (sc_list_base(p, q) + it.split * 2 + (half ^ 1)) : nullptr;
             int* my_ovf = valid ? p.ovf + q : nullptr;
             const size_t slot = sc_list_base(p, q < p.nq ? q : 0) + it.split * 2 + half;
             uint64_t* wbuf = p.partial + (sc_list_base(p, (qt * TC_BM + g * 32) >> 5, 8) + it.split * 2 + half) * (32 * CAP);
@@ -388,12 +399,23 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             // Later rounds are staggered by cluster so that the 74 pairs do not all hit L2 with their lists at once.
             int next_sched = 1, round = 0;
             for (int t = it.t0; t < it.t1; ++t) {
-                if (my_gthr) lim = fminf(lim, __uint_as_float(__ldcg(my_gthr)) + band2);
+                if (my_gthr) {
+                    const float pair_bound = fmaxf(__uint_as_float(__ldcg(my_hthr)), __uint_as_float(__ldcg(peer_hthr)));
+                    lim = fminf(lim, fminf(__uint_as_float(__ldcg(my_gthr)), pair_bound) + band2);
+                }
                 float thr = (lim - qn) * invW;              // acc' > thr  <=>  dis~ < lim
                 long long c2 = p.dbg ? clock64() : 0;
                 mbar_wait(&tfull[acc], acc_phase);
                 if (p.dbg) w_tfull += clock64() - c2;
                 tc_fence_after();
+                if (p.debug_skip_epilogue) {      // ceiling probe: TMA + MMA pipeline only (results are not produced)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                    continue;
+                }
                 const uint32_t tcol = tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * TC_BN + half * (TC_BN / 2);
                 const int colbase = t * TC_BN + half * (TC_BN / 2);
                 uint32_t ra[32], rb[32];
@@ -430,16 +452,6 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                             }
                         }
                     }
-                    if (__any_sync(kFull, cnt > CAP - 32)) {
-                        long long c3 = p.dbg ? clock64() : 0;
-                        int cnt2 = cnt;                 // copies: references into a noinline call would pin cnt/lim in local memory
-                        float lim2 = lim;
-                        sc_compact_lanes<E>(wbuf, cnt2, lim2, band2, lane, p.k, my_gthr, my_ovf);
-                        cnt = cnt2;
-                        lim = lim2;
-                        thr = (lim - qn) * invW;
-                        if (p.dbg) { t_compact += clock64() - c3; n_compact += 1; }
-                    }
                 };
                 // software pipeline over the 4 chunks: the next tcgen05.ld is in flight while this chunk is scanned
                 tmem_ld32(tcol, ra);
@@ -458,20 +470,20 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
                 scan(rb, colbase + 96);
+                // Compaction happens only here, between tiles, where nothing but the list state is live.  A tile appends
+                // at most 128 entries to a list, so "room for 128" at every tile start rules out overflow inside a tile.
+                bool do_compact = __any_sync(kFull, cnt > CAP - TC_BN / 2);
                 if (t - it.t0 + 1 == next_sched) {
                     ++round;
                     int base = 1;
                     for (int r = 0; r < round; ++r) base *= p.sched_mul;
                     next_sched = base + (round >= 3 ? ((cluster_id & 7) * base * (p.sched_mul - 1)) >> 4 : 0);
-                    if (__any_sync(kFull, cnt > p.k + 8)) {
-                        long long c3 = p.dbg ? clock64() : 0;
-                        int cnt2 = cnt;
-                        float lim2 = lim;
-                        sc_compact_lanes<E>(wbuf, cnt2, lim2, band2, lane, p.k, my_gthr, my_ovf);
-                        cnt = cnt2;
-                        lim = lim2;
-                        if (p.dbg) { t_compact += clock64() - c3; n_compact += 1; }
-                    }
+                    do_compact = do_compact || __any_sync(kFull, cnt > p.k + 8);
+                }
+                if (do_compact) {
+                    long long c3 = p.dbg ? clock64() : 0;
+                    sc_compact_lanes<E>(wbuf, cnt, lim, band2, lane, p.k, my_gthr, my_hthr, my_ovf);
+                    if (p.dbg) { t_compact += clock64() - c3; n_compact += 1; }
                 }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;

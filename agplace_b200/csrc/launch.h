@@ -52,6 +52,7 @@ struct ScreenParams {
     int n_dbtiles;
     int q_resident;         // 1: the CTA's query tile stays in shared memory for a whole item (d_pad <= 512)
     int n_stages;           // depth of the operand ring
+    int debug_skip_epilogue;// development probe: epilogue hands every accumulator straight back
     int sched_mul;          // scheduled compactions after tiles 1, mul, mul^2, ... of an item
     const float* qn;        // [nq] |q|^2
     const float* sq;        // [nq] query row scale 2^eq
@@ -60,6 +61,7 @@ struct ScreenParams {
     uint64_t* partial;      // candidate slots, bundles of 32 queries x 32*E entries per list (knn_screen.cuh:sc_list_base)
     int* pcount;            // entries per list
     uint32_t* gthr;         // [nq] smallest known upper bound of the k-th best screened distance
+    uint32_t* hthr;         // per list: upper bound of the ceil(k/2)-th best of that list (fp32 bits, +inf initially)
     int* ovf;               // [nq] set when a query's certified band did not fit its slots
     long long* dbg;
 };
