@@ -161,7 +161,10 @@ static int grow(agp_index* ix, int64_t need) {
     }
     uint8_t* nxs = nullptr;
     const size_t screen_row = static_cast<size_t>(ix->d_pad + 64) * 2;
-    if (ix->screen) CK(cudaMalloc(&nxs, static_cast<size_t>(ncap) * screen_row));
+    if (ix->screen) {
+        CK(cudaMalloc(&nxs, static_cast<size_t>(ncap) * screen_row));
+        CK(cudaMemsetAsync(nxs, 0, static_cast<size_t>(ncap) * screen_row, ix->stream));     // rows without a vector: finite zeros + aux -inf
+    }
     LAUNCH(launch_fill_f32(nyn, ncap, HUGE_VALF, ix->stream));
     if (ix->screen) {
         if (ix->ntotal > 0)
@@ -518,7 +521,20 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         p.n_dbtiles = n_dbtiles;
         p.n_full_items = (p.n_ptiles / clusters) * clusters;
         const int rem_tiles = p.n_ptiles - p.n_full_items;
-        p.rem_splits = rem_tiles > 0 ? std::max(1, std::min({clusters / rem_tiles, n_dbtiles, 64})) : 1;
+        // remainder: database ranges per pair tile chosen to minimise waves x (range length + per-item overhead of
+        // ~3 tiles: query tile load, pipeline fill/drain, first compaction rounds)
+        p.rem_splits = 1;
+        if (rem_tiles > 0) {
+            double best_cost = 1e300;
+            const int max_s = std::min(n_dbtiles, 64);      // 2 lists per range, finalize handles up to 256 lists
+            for (int sp = 1; sp <= max_s; ++sp) {
+                const int64_t items = static_cast<int64_t>(rem_tiles) * sp;
+                const int64_t waves = (items + clusters - 1) / clusters;
+                const double cost = static_cast<double>(waves) * ((n_dbtiles + sp - 1) / sp + 3.0);
+                if (cost < best_cost * 0.999) { best_cost = cost; p.rem_splits = sp; }
+            }
+        }
+        p.rem_tiles = rem_tiles;
         p.list_splits = p.rem_splits;
         p.n_items = p.n_full_items + rem_tiles * p.rem_splits;
         p.q_resident = resident;

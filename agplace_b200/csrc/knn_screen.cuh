@@ -53,9 +53,12 @@ __device__ __forceinline__ ScItem sc_decode_item(const ScreenParams& p, int item
         it.pt = item;
         it.split = 0;
     } else {
+        // range-major: the ranges of one pair tile are spread over successive waves, so every later range starts from
+        // the bound gthr[] the earlier ones have published instead of rediscovering it (concurrent items also stream
+        // the same database range, which keeps it in L2)
         const int r = item - p.n_full_items;
-        it.pt = p.n_full_items + r / p.rem_splits;
-        it.split = r - (r / p.rem_splits) * p.rem_splits;
+        it.split = r / p.rem_tiles;
+        it.pt = p.n_full_items + (r - it.split * p.rem_tiles);
         nsp = p.rem_splits;
     }
     it.t0 = static_cast<int>(static_cast<int64_t>(it.split) * p.n_dbtiles / nsp);

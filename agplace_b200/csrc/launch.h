@@ -47,6 +47,7 @@ struct ScreenParams {
     int n_ptiles;           // 256-query pair tiles (each CTA of the pair owns 128 of them)
     int n_full_items;       // pair tiles swept unsplit (multiple of the number of clusters)
     int rem_splits;         // database ranges each remaining pair tile is split into
+    int rem_tiles;          // pair tiles in the split remainder
     int list_splits;        // candidate lists are indexed [q][list_splits][2]
     int n_items;
     int n_dbtiles;
