@@ -41,7 +41,7 @@ enum agp_precision {
     AGP_PRECISION_EXACT_DIFF = 3, /* always the difference form (nq processed in groups of < 20)               */
     AGP_PRECISION_3XFP16 = 4,     /* always the tcgen05 kernel on fp16 hi/lo planes of power-of-two scaled rows */
     AGP_PRECISION_FP16_SCREEN = 5 /* always the single-pass certified fp16 screen (CTA pairs) + exact fp32 finish;
-                                     queries whose certified band overflows fall back to 3xFP16               */
+                                     queries whose certified band overflows are re-run with fp32 FMA tiles    */
 };
 
 enum agp_error {
@@ -98,7 +98,8 @@ AGP_API int agp_index_set_profiling(agp_index* idx, int enable);
 AGP_API int agp_index_get_profile(agp_index* idx, double* kernel_ms, int64_t* kernel_launches, int reset);
 
 /* Counters of the single-pass screen: queries it answered, and how many of those had to be re-run
- * through the 3xFP16 kernel because their certified candidate band did not fit (diagnostics). */
+ * through the fp32 FMA path because their certified candidate band did not fit or a row was not
+ * representable in the fp16 plane (diagnostics). */
 AGP_API int agp_index_get_stats(const agp_index* idx, int64_t* screened_queries, int64_t* fallback_queries);
 
 /* K4 across shards: merge n_lists per-shard results (device memory, e.g. the output of one NCCL
