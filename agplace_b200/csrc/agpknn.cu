@@ -595,8 +595,19 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
             for (size_t i = 0; i < pc.size(); ++i) { tot += pc[i]; mx = std::max(mx, pc[i]); }
             fprintf(stderr, "[agp screen dbg] E=%d stages=%d grid=%d items=%d (full %d + %d x %d) | candidates/query mean=%.1f, max list=%d\n", E,
                     n_stages, grid, p.n_items, p.n_full_items, rem_tiles, p.rem_splits, tot / nqc, mx);
+            {
+                const int nl = std::min<int>(16, rem_tiles > 0 && p.n_full_items == 0 ? 2 * p.rem_splits : 2);
+                float hv[16], gv = 0.f;
+                CK(cudaMemcpy(hv, ix->hthr.p, nl * sizeof(float), cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(&gv, ix->gthr.p, sizeof(float), cudaMemcpyDeviceToHost));
+                fprintf(stderr, "[agp screen dbg] query 0: gthr=%.5f hthr:", gv);
+                for (int i = 0; i < nl; ++i) fprintf(stderr, " %.5f", hv[i]);
+                fprintf(stderr, " | pcount:");
+                for (int i = 0; i < nl; ++i) fprintf(stderr, " %d", pc[i]);
+                fprintf(stderr, "\n");
+            }
             fprintf(stderr, "[agp screen dbg] mma(leader): total=%.0f wait_full=%.0f wait_tempty=%.0f | epi(w2, all CTAs): total=%.0f wait_tfull=%.0f "
-                            "compact=%.0f n_compact=%.0f (cycles, mean)\n", sl[0], sl[1], sl[2], sa[3], sa[4], sa[5], sa[6]);
+                            "compact=%.0f n_compact=%.0f hits(lane0,w2)=%.0f (cycles, mean)\n", sl[0], sl[1], sl[2], sa[3], sa[4], sa[5], sa[6], sa[7]);
         }
         CK(cudaStreamSynchronize(ix->stream));
         const int n_ovf = *ix->h_count;

@@ -129,8 +129,8 @@ __device__ __noinline__ void sc_compact_sort(int L, uint64_t* wbuf, int& cnt, fl
 //   4. a second pass keeps, in place, the entries below min(lim, pd + 2 band).
 // Lanes that still cannot free enough slots (pathological ties) get the exact warp sort.
 template <int E>
-__device__ __forceinline__ void sc_compact_lanes(uint64_t* wbuf, int& cnt, float& lim, float band2, int lane, int k, uint32_t* my_gthr,
-                                                 uint32_t* my_hthr, int* my_ovf) {
+__device__ __forceinline__ void sc_compact_lanes(uint64_t* wbuf, int& cnt, float& lim, float band2, int lane, int k, int kh,
+                                                 uint32_t* my_gthr, uint32_t* my_hthr, int* my_ovf) {
     constexpr int CAP = 32 * E;
     const float inf = sc_inf();
     constexpr int BITS = E > 4 && E <= 8 ? 8 : (E <= 4 ? 8 : 16);     // counter width: lists hold < 2^BITS entries
@@ -173,12 +173,11 @@ __device__ __forceinline__ void sc_compact_lanes(uint64_t* wbuf, int& cnt, float
         }
     }
     // smallest bucket edge with at least k entries at or below it
-    // ... and, for the pair-wide bound, with at least ceil(k/2): if BOTH column halves of a query have that many entries
+    // ... and, for the group-wide bound, with at least kh = ceil(k / L): if ALL L lists of a group have that many entries
     // at or below x, the query has k rows at or below x (see the caller).
     float pd = inf, pdh = inf;
     int cum = 0;
     bool found = false, foundh = false;
-    const int kh = (k + 1) >> 1;
 #pragma unroll
     for (int b = 0; b < 15; ++b) {              // the last bucket is open-ended: its edge bounds nothing
         const unsigned long long hr = (b / PER == 0) ? h0 : (b / PER == 1) ? h1 : (b / PER == 2) ? h2 : h3;
@@ -372,6 +371,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         int acc = 0;
         uint32_t acc_phase = 0;
         long long w_tfull = 0, t_compact = 0, n_compact = 0, e_begin = p.dbg ? clock64() : 0;
+        long long n_hits = 0;
         uint32_t tempty_leader[2];
         tempty_leader[0] = mapa_u32(smem_u32(&tempty[0]), 0);
         tempty_leader[1] = mapa_u32(smem_u32(&tempty[1]), 0);
@@ -388,10 +388,15 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             // a row is a candidate iff dis~ < lim = (best known bound of the k-th smallest dis~) + 2 band
             float lim = valid ? inf : -inf;
             uint32_t* my_gthr = valid ? p.gthr + q : nullptr;
-            // pair-wide bound: hthr[list] = bound of the ceil(k/2)-th best of one column half; max over the two halves of
-            // this (query, split) bounds the query's k-th best over everything both halves have swept
+            // Group-wide bound: hthr[list] = bound of the ceil(k/L)-th best of one list; the max over the L lists of a group
+            // bounds the query's k-th best over everything the whole group has swept -- far tighter than any single list's
+            // own k-th.  Group = the two column halves of this (query, range); for a split remainder with few ranges, ALL
+            // 2 x ranges lists of the query (they run concurrently on different clusters).
+            const bool wide = it.pt >= p.n_full_items && 2 * p.rem_splits <= 16;
+            const int L = wide ? 2 * p.rem_splits : 2;
+            const int kh = (p.k + L - 1) / L;
             uint32_t* my_hthr = valid ? p.hthr + (sc_list_base(p, q) + it.split * 2 + half) : nullptr;
-            const uint32_t* peer_hthr = valid ? p.hthr + (sc_list_base(p, q) + it.split * 2 + (half ^ 1)) : nullptr;
+            const uint32_t* grp_hthr = valid ? p.hthr + (sc_list_base(p, q) + (wide ? 0 : it.split * 2)) : nullptr;
             int* my_ovf = valid ? p.ovf + q : nullptr;
             const size_t slot = sc_list_base(p, q < p.nq ? q : 0) + it.split * 2 + half;
             uint64_t* wbuf = p.partial + (sc_list_base(p, (qt * TC_BM + g * 32) >> 5, 8) + it.split * 2 + half) * (32 * CAP);
@@ -403,8 +408,11 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             int next_sched = 1, round = 0;
             for (int t = it.t0; t < it.t1; ++t) {
                 if (my_gthr) {
-                    const float pair_bound = fmaxf(__uint_as_float(__ldcg(my_hthr)), __uint_as_float(__ldcg(peer_hthr)));
-                    lim = fminf(lim, fminf(__uint_as_float(__ldcg(my_gthr)), pair_bound) + band2);
+                    float grp_bound = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < L) grp_bound = fmaxf(grp_bound, __uint_as_float(__ldcg(grp_hthr + j)));
+                    lim = fminf(lim, fminf(__uint_as_float(__ldcg(my_gthr)), grp_bound) + band2);
                 }
                 float thr = (lim - qn) * invW;              // acc' > thr  <=>  dis~ < lim
                 long long c2 = p.dbg ? clock64() : 0;
@@ -448,6 +456,9 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                                                 __stcg(wbuf + cnt * 32 + lane,
                                                        pack_key(fmaxf(fmaf(v, Wq, qn), 0.f), static_cast<uint32_t>(col0 + 8 * j + c)));
                                                 ++cnt;
+#ifdef AGP_SCREEN_COUNT_HITS
+                                                ++n_hits;
+#endif
                                             }
                                         }
                                     }
@@ -485,7 +496,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                 }
                 if (do_compact) {
                     long long c3 = p.dbg ? clock64() : 0;
-                    sc_compact_lanes<E>(wbuf, cnt, lim, band2, lane, p.k, my_gthr, my_hthr, my_ovf);
+                    sc_compact_lanes<E>(wbuf, cnt, lim, band2, lane, p.k, kh, my_gthr, my_hthr, my_ovf);
                     if (p.dbg) { t_compact += clock64() - c3; n_compact += 1; }
                 }
                 acc ^= 1;
@@ -498,6 +509,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             p.dbg[blockIdx.x * 8 + 4] = w_tfull;
             p.dbg[blockIdx.x * 8 + 5] = t_compact;
             p.dbg[blockIdx.x * 8 + 6] = n_compact;
+            p.dbg[blockIdx.x * 8 + 7] = n_hits;      // lane 0 of warp 2 only (AGP_SCREEN_COUNT_HITS builds)
         }
     }
     tc_fence_before();

@@ -128,7 +128,10 @@ class ShardedIndexFlatL2:
         which = torch.searchsorted(starts, I_local.clamp(min=0), right=True) - 1
         return torch.where(I_local < 0, I_local, I_local + gbase[which.clamp(min=0)])
 
-    def search(self, x, k, *, params=None, D=None, I=None):
+    def search(self, x, k, *, params=None, D=None, I=None, gather=True):
+        """``gather=False`` (query-split only): return just this rank's slice of the results -- rows
+        ``shard_bounds(nq, world)[rank]`` of ``(D, I)`` -- and skip the all-gather; the results then stay
+        partitioned by query like the work was (no collective on the data path)."""
         import torch
         import torch.distributed as dist
         nq, d = x.shape
@@ -160,6 +163,10 @@ class ShardedIndexFlatL2:
             I_loc = torch.from_numpy(np.ascontiguousarray(I_loc)).to(dev)
         dev = D_loc.device
 
+        if self.shard == "query" and not gather:
+            if as_numpy:
+                return D_loc.cpu().numpy(), I_loc.cpu().numpy()
+            return D_loc, I_loc
         if self.shard == "query":
             # pad every slice to `per` rows, all-gather, drop the padding
             rows = per

@@ -192,6 +192,7 @@ def run_ours(args):
     c = workload(args.workload)
     n, nq, d, k = c["n"], c["nq"], c["d"], c["k"]
     peaks = load_peaks()
+    nq_rank = nq                          # queries of the named config
 
     # ---- sharding policy (north_star): row-shard the database only when it "exceeds one GPU"; a database that
     # fits is replicated and the QUERIES are split across ranks (no redundant work, results concatenated by
@@ -201,11 +202,17 @@ def run_ours(args):
     shard_mode = args.shard if args.shard != "auto" else ("query" if fits else "db")
     if world == 1:
         shard_mode = "single"
+    # Scaling mode.  weak (default; queries are independent units, so the path partitions with no data-path
+    # collective): every rank answers its own batch of the config's nq queries against the replicated database,
+    # i.e. the job is world x nq queries and per-GPU work is fixed.  strong: the config's nq queries in total.
+    weak = world > 1 and args.scaling == "weak" and shard_mode == "query"
+    if weak:
+        nq = nq_rank * world
     # ---- database: resident in HBM before anything is timed.  db-sharded: rank r owns rows shard_bounds(n)[r].
     lo, hi = shard_bounds(n, world)[rank] if shard_mode == "db" else (0, n)
     t_add0 = time.perf_counter()
     if n * d * 4 <= 2e9:
-        xb, xq = make_host_data(c)
+        xb, xq = make_host_data(dict(c, nq=nq))
         xb_local = xb[lo:hi]
         gen = "host numpy default_rng (seeded), unit-norm rows"
     else:   # large configs: generate each shard on its own GPU (seeded per shard), never materialise on the host
@@ -247,17 +254,23 @@ def run_ours(args):
     D_host = torch.empty((nq, k), dtype=torch.float32).pin_memory()
     I_host = torch.empty((nq, k), dtype=torch.int64).pin_memory()
 
+    no_gather = shard_mode == "query"      # query-split: results stay partitioned by query, like the inputs
+
     def step_device():
+        if no_gather:
+            return index.search(xq_dev, k, gather=False)
         return index.search(xq_dev, k)
 
     def step_e2e():
         if world == 1:
             xd = xq_pinned.to(dev, non_blocking=True)
             D, I = index.search(xd, k)
-        else:       # the sharded index copies what this rank needs (query-sharded: only its slice of the queries)
+        elif no_gather:   # the sharded index copies only this rank's slice of the queries and returns only its slice of (D, I)
+            D, I = index.search(xq_pinned, k, gather=False)
+        else:
             D, I = index.search(xq_pinned, k)
-        D_host.copy_(D, non_blocking=True)
-        I_host.copy_(I, non_blocking=True)
+        D_host[: D.shape[0]].copy_(D, non_blocking=True)
+        I_host[: I.shape[0]].copy_(I, non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the caller needs the results on the host
 
     def barrier():
@@ -328,16 +341,18 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"{c['name']}: {c['desc']}", "n": n, "nq": nq, "d": d, "k": k, "precision": "auto: certified single-pass fp16 tcgen05 screen (fp32 accumulate) + exact fp32 difference-form re-rank",
                    "sharding": ("single GPU" if world == 1 else
                                 f"database row-sharded over {world} ranks, queries replicated, one NCCL all-gather + merge" if shard_mode == "db" else
-                                f"database fits one GPU: replicated on {world} ranks, queries split across ranks, one NCCL all-gather of the results"),
+                                f"database fits one GPU: replicated on {world} ranks, queries split across ranks, results stay partitioned by query (no data-path collective); "
+                                + (f"weak scaling: {world} x {nq_rank} queries per step" if weak else f"strong scaling: {nq} queries per step in total")),
                    "l2": "inputs larger than L2 (fp32 rows %.0f MB + fp16 plane %.0f MB + queries %.0f MB per rank vs 126 MB L2)" % (n_local * d * 4 / 1e6, n_local * (d + 64) * 2 / 1e6, nq * d * 4 / 1e6),
                    "generator": gen, "add_seconds": add_s},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(nq * d * 4 * (world if shard_mode == "db" else 1)), "d2h_bytes_per_step": int(nq * k * 12 * world)},
+                "h2d_bytes_per_step": int(nq * d * 4 * (world if shard_mode == "db" else 1)),
+                "d2h_bytes_per_step": int(nq * k * 12 * (world if shard_mode == "db" else 1))},
         "gpu_launches": int(launches * world),
         "roofline": roofline,
         "clocks": clocks,
@@ -367,6 +382,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--shard", default="auto", choices=["auto", "db", "query"], help="multi-GPU partitioning (auto: query-split if the database fits one GPU)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every rank answers its own batch of the config's queries (job = N x nq); strong = nq in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     args = ap.parse_args()

@@ -34,7 +34,11 @@ def _worker(rank, world, port, shard, out_dir):
         ix.add(xb[:20000]); ix.add(xb[20000:])
         D, I = ix.search(xq, 40)                                   # numpy in -> numpy out
         Dt, It = ix.search(torch.from_numpy(xq).cuda(), 100)       # CUDA in -> CUDA out
-        np.savez(Path(out_dir) / f"r{rank}.npz", D=D, I=I, D2=Dt.cpu().numpy(), I2=It.cpu().numpy())
+        extra = {}
+        if shard == "query":                                       # results left partitioned by query: this rank's slice only
+            Dl, Il = ix.search(xq, 40, gather=False)
+            extra = dict(Dl=Dl, Il=Il)
+        np.savez(Path(out_dir) / f"r{rank}.npz", D=D, I=I, D2=Dt.cpu().numpy(), I2=It.cpu().numpy(), **extra)
     finally:
         dist.destroy_process_group()
 
@@ -61,3 +65,8 @@ def test_nccl_sharded_equals_single(tmp_path, shard):
         np.testing.assert_array_equal(got["D"], Ds)
         np.testing.assert_array_equal(got["I2"], Is2)
         np.testing.assert_array_equal(got["D2"], Ds2)
+        if shard == "query":
+            from agplace_b200.sharded import shard_bounds
+            a, b = shard_bounds(len(xq), world)[r]
+            np.testing.assert_array_equal(got["Il"], Is[a:b])
+            np.testing.assert_array_equal(got["Dl"], Ds[a:b])
