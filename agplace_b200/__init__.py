@@ -4,7 +4,7 @@
 (test.py:27-32 and the mining helpers in datasets/datasets_ws_*.py): ``faiss.IndexFlatL2`` here is
 a hand-written sm_100a CUDA engine behind the C ABI in ``include/agpknn.h``.
 """
-from .index import FLT_MAX, METRIC_L2, IndexFlatL2, default_device, positives_to_csr, recall_hits
+from .index import FLT_MAX, METRIC_L2, IndexFlatL2, best_of_lists, default_device, positives_to_csr, recall_hits
 
-__all__ = ["IndexFlatL2", "METRIC_L2", "FLT_MAX", "default_device", "positives_to_csr", "recall_hits"]
+__all__ = ["IndexFlatL2", "METRIC_L2", "FLT_MAX", "best_of_lists", "default_device", "positives_to_csr", "recall_hits"]
 __version__ = "0.1.0"

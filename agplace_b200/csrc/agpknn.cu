@@ -74,7 +74,8 @@ struct agp_index {
     int kind = KIND_TF32, elem_bytes = 4;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     Buf q_raw, q_hi, q_lo, qn, sq, cand, partial, panel, d_out, i_out, gthr, cand_d, cand_i, dbg;
-    Buf dq, ovf, ovf_list, ovf_x, ovf_d, ovf_i, hthr;     // single-pass screen: residual norms, overflow flags / list / fallback scratch
+    Buf dq, ovf, ovf_list, ovf_x, ovf_d, ovf_i, hthr;
+    Buf mk_d, mk_i, mk_off, mk_ids;                  // masked search: k' result lists and the exclusion lists (CSR)     // single-pass screen: residual norms, overflow flags / list / fallback scratch
     uint32_t* dbstats = nullptr;                     // [4] max |y|^2, max |y - fp16(y)| over the database (fp32 bits)
     int* h_count = nullptr;                          // pinned host word for the overflow count
     int64_t stat_screened = 0, stat_fallback = 0;
@@ -696,7 +697,7 @@ void agp_index_free(agp_index* ix) {
     if (ix->wx) cudaFree(ix->wx);
     if (ix->xs) cudaFree(ix->xs);
     free_buf(ix->sq);
-    free_buf(ix->dq); free_buf(ix->hthr); free_buf(ix->ovf); free_buf(ix->ovf_list); free_buf(ix->ovf_x); free_buf(ix->ovf_d); free_buf(ix->ovf_i);
+    free_buf(ix->dq); free_buf(ix->hthr); free_buf(ix->mk_d); free_buf(ix->mk_i); free_buf(ix->mk_off); free_buf(ix->mk_ids); free_buf(ix->ovf); free_buf(ix->ovf_list); free_buf(ix->ovf_x); free_buf(ix->ovf_d); free_buf(ix->ovf_i);
     if (ix->dbstats) cudaFree(ix->dbstats);
     if (ix->h_count) cudaFreeHost(ix->h_count);
     free_buf(ix->q_raw); free_buf(ix->q_hi); free_buf(ix->q_lo); free_buf(ix->qn); free_buf(ix->cand);
@@ -859,6 +860,94 @@ int agp_index_search(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, 
     } else if (x_mem_kind != AGP_MEM_DEVICE) {
         CK(cudaStreamSynchronize(ix->stream));
     }
+    return 0;
+}
+
+int agp_index_search_masked(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, int k, const int64_t* excl_offsets,
+                            const int64_t* excl_ids, float* D, int64_t* I, int out_mem_kind) {
+    if (!ix) return set_err(AGP_EINVAL, "index is null");
+    if (nq < 0) return set_err(AGP_EINVAL, "nq must be >= 0");
+    if (k <= 0) return set_err(AGP_EINVAL, "k must be positive, got %d", k);
+    if (nq == 0) return 0;
+    if (!x || !D || !I || !excl_offsets) return set_err(AGP_EINVAL, "x, D, I and excl_offsets must be non-null");
+    int64_t max_ex = 0;
+    for (int64_t q = 0; q < nq; ++q) {
+        const int64_t c = excl_offsets[q + 1] - excl_offsets[q];
+        if (c < 0) return set_err(AGP_EINVAL, "excl_offsets must be non-decreasing");
+        max_ex = std::max(max_ex, c);
+    }
+    const int64_t n_ex = excl_offsets[nq];
+    if (n_ex > 0 && !excl_ids) return set_err(AGP_EINVAL, "excl_ids is null");
+    // every excluded id can displace at most one result: k + max|excl| candidates always contain the k survivors
+    const int64_t kp64 = std::min<int64_t>(k + max_ex, std::max<int64_t>(ix->ntotal, k));
+    if (kp64 > AGP_MAX_K) return set_err(AGP_EINVAL, "k + longest exclusion list = %lld exceeds AGP_MAX_K=%d", static_cast<long long>(k + max_ex), AGP_MAX_K);
+    const int kp = static_cast<int>(kp64);
+    CK(cudaSetDevice(ix->device));
+    CKR(ensure(ix->mk_d, static_cast<size_t>(nq) * kp * sizeof(float)));
+    CKR(ensure(ix->mk_i, static_cast<size_t>(nq) * kp * sizeof(int64_t)));
+    CKR(ensure(ix->mk_off, static_cast<size_t>(nq + 1) * sizeof(int64_t)));
+    CKR(ensure(ix->mk_ids, static_cast<size_t>(std::max<int64_t>(n_ex, 1)) * sizeof(int64_t)));
+    CK(cudaMemcpyAsync(ix->mk_off.p, excl_offsets, static_cast<size_t>(nq + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ix->stream));
+    if (n_ex > 0) CK(cudaMemcpyAsync(ix->mk_ids.p, excl_ids, static_cast<size_t>(n_ex) * sizeof(int64_t), cudaMemcpyHostToDevice, ix->stream));
+    CKR(agp_index_search(ix, nq, x, x_mem_kind, kp, static_cast<float*>(ix->mk_d.p), static_cast<int64_t*>(ix->mk_i.p), AGP_MEM_DEVICE));
+    float* D_dev = D;
+    int64_t* I_dev = I;
+    if (out_mem_kind != AGP_MEM_DEVICE) {
+        CKR(ensure(ix->d_out, static_cast<size_t>(nq) * k * sizeof(float)));
+        CKR(ensure(ix->i_out, static_cast<size_t>(nq) * k * sizeof(int64_t)));
+        D_dev = static_cast<float*>(ix->d_out.p);
+        I_dev = static_cast<int64_t*>(ix->i_out.p);
+    }
+    LAUNCH(launch_mask_select(static_cast<const float*>(ix->mk_d.p), static_cast<const int64_t*>(ix->mk_i.p), kp,
+                              static_cast<const int64_t*>(ix->mk_off.p), static_cast<const int64_t*>(ix->mk_ids.p), nq, k, D_dev, I_dev, ix->stream));
+    if (out_mem_kind != AGP_MEM_DEVICE) {
+        CK(cudaMemcpyAsync(D, D_dev, static_cast<size_t>(nq) * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+        CK(cudaMemcpyAsync(I, I_dev, static_cast<size_t>(nq) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
+    }
+    CK(cudaStreamSynchronize(ix->stream));      // the exclusion lists are host memory the caller may reuse
+    return 0;
+}
+
+int agp_best_of_lists(int device, int64_t nq, int d, const float* xq, const float* rows, const int64_t* offsets, float* best_d,
+                      int64_t* best_pos) {
+    if (nq < 0 || d <= 0) return set_err(AGP_EINVAL, "bad nq or d");
+    if (nq == 0) return 0;
+    if (!xq || !offsets || !best_d || !best_pos) return set_err(AGP_EINVAL, "null pointer");
+    const int64_t total = offsets[nq];
+    if (total > 0 && !rows) return set_err(AGP_EINVAL, "rows is null");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_err(AGP_ENODEV, "no CUDA device visible: agpknn has no CPU fallback");
+    }
+    CK(cudaSetDevice(device));
+    float *d_q = nullptr, *d_rows = nullptr, *d_bd = nullptr;
+    int64_t *d_off = nullptr, *d_bp = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() { cudaFree(d_q); cudaFree(d_rows); cudaFree(d_bd); cudaFree(d_off); cudaFree(d_bp); };
+#define CKB(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            rc = set_err(AGP_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            cleanup();                                                                              \
+            return rc;                                                                              \
+        }                                                                                           \
+    } while (0)
+    CKB(cudaMalloc(&d_q, static_cast<size_t>(nq) * d * sizeof(float)));
+    CKB(cudaMalloc(&d_rows, static_cast<size_t>(std::max<int64_t>(total, 1)) * d * sizeof(float)));
+    CKB(cudaMalloc(&d_off, static_cast<size_t>(nq + 1) * sizeof(int64_t)));
+    CKB(cudaMalloc(&d_bd, static_cast<size_t>(nq) * sizeof(float)));
+    CKB(cudaMalloc(&d_bp, static_cast<size_t>(nq) * sizeof(int64_t)));
+    CKB(cudaMemcpy(d_q, xq, static_cast<size_t>(nq) * d * sizeof(float), cudaMemcpyHostToDevice));
+    if (total > 0) CKB(cudaMemcpy(d_rows, rows, static_cast<size_t>(total) * d * sizeof(float), cudaMemcpyHostToDevice));
+    CKB(cudaMemcpy(d_off, offsets, static_cast<size_t>(nq + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    g_launches.fetch_add(1);
+    CKB(launch_best_of_lists(d_q, d_rows, d, d_off, nq, d_bd, d_bp, nullptr));
+    CKB(cudaMemcpy(best_d, d_bd, static_cast<size_t>(nq) * sizeof(float), cudaMemcpyDeviceToHost));
+    CKB(cudaMemcpy(best_pos, d_bp, static_cast<size_t>(nq) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    cleanup();
+#undef CKB
     return 0;
 }
 

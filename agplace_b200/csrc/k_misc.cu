@@ -398,7 +398,95 @@ __global__ void scatter_results_kernel(const float* __restrict__ Dt, const int64
     }
 }
 
+// N2 (batched mining): drop, per query, the ids on its exclusion list from an ascending result list of kp entries
+// and keep the first k survivors -- the reference's `setdiff1d(sampled_database_indexes, soft_positives)` followed by
+// `search(..., k)` (datasets/datasets_ws_kitti360.py:1088-1091,985-993), done for all queries at once.  One warp per query;
+// exclusion lists are short (the soft positives that fall inside the sampled set).
+__global__ void __launch_bounds__(128) mask_select_kernel(const float* __restrict__ Dp, const int64_t* __restrict__ Ip, int kp,
+                                                          const int64_t* __restrict__ ex_off, const int64_t* __restrict__ ex_ids,
+                                                          int64_t nq, int k, float* __restrict__ D, int64_t* __restrict__ I) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const int64_t e0 = ex_off[q], e1 = ex_off[q + 1];
+    int out = 0;
+    for (int base = 0; base < kp && out < k; base += 32) {
+        const int r = base + lane;
+        const int64_t id = r < kp ? Ip[q * kp + r] : -1;
+        bool keep = id >= 0;
+        for (int64_t e = e0; keep && e < e1; ++e) keep = ex_ids[e] != id;
+        const unsigned m = __ballot_sync(kFull, keep);
+        const int pos = out + __popc(m & ((1u << lane) - 1u));
+        if (keep && pos < k) {
+            D[q * k + pos] = Dp[q * kp + r];
+            I[q * k + pos] = id;
+        }
+        out += __popc(m);
+    }
+    for (int r = min(out, k) + lane; r < k; r += 32) {       // fewer than k survivors: faiss-style padding
+        D[q * k + r] = 3.4028234663852886e38f;
+        I[q * k + r] = -1;
+    }
+}
+
+// N2: nearest row of each query's OWN candidate list (the reference's get_best_positive_index, kitti360:976-983, for all
+// queries at once).  rows = the gathered candidate features, list q = rows [off[q], off[q+1]).  Exact fp32 difference
+// form with the same per-lane summation order as diff_small_kernel / the re-rank, so the winner and its distance are
+// bit-identical to a one-query IndexFlatL2 search; ties resolve to the earlier position (faiss Top1 keeps the first).
+__global__ void __launch_bounds__(128) best_of_lists_kernel(const float* __restrict__ xq, const float* __restrict__ rows, int d,
+                                                            const int64_t* __restrict__ off, int64_t nq, float* __restrict__ best_d,
+                                                            int64_t* __restrict__ best_pos) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const float* qrow = xq + q * d;
+    const bool vec = ((d & 3) == 0) && (((reinterpret_cast<uintptr_t>(xq) | reinterpret_cast<uintptr_t>(rows)) & 15) == 0);
+    float bd = 3.4028234663852886e38f;
+    int64_t bp = -1;
+    for (int64_t r = off[q]; r < off[q + 1]; ++r) {
+        const float* row = rows + r * d;
+        float acc = 0.f;
+        if (vec) {
+            for (int c = lane; c < (d >> 2); c += 32) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(qrow) + c);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(row) + c);
+                float t;
+                t = a.x - b.x; acc = fmaf(t, t, acc);
+                t = a.y - b.y; acc = fmaf(t, t, acc);
+                t = a.z - b.z; acc = fmaf(t, t, acc);
+                t = a.w - b.w; acc = fmaf(t, t, acc);
+            }
+        } else {
+            for (int c = lane; c < d; c += 32) {
+                const float t = __ldg(qrow + c) - __ldg(row + c);
+                acc = fmaf(t, t, acc);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+        if (bp < 0 || acc < bd) { bd = acc; bp = r - off[q]; }
+    }
+    if (lane == 0) {
+        best_d[q] = bd;
+        best_pos[q] = bp;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ launchers
+cudaError_t launch_mask_select(const float* Dp, const int64_t* Ip, int kp, const int64_t* ex_off, const int64_t* ex_ids, int64_t nq, int k,
+                               float* D, int64_t* I, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    mask_select_kernel<<<static_cast<unsigned>((nq + 3) / 4), 128, 0, st>>>(Dp, Ip, kp, ex_off, ex_ids, nq, k, D, I);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_best_of_lists(const float* xq, const float* rows, int d, const int64_t* off, int64_t nq, float* best_d,
+                                 int64_t* best_pos, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    best_of_lists_kernel<<<static_cast<unsigned>((nq + 3) / 4), 128, 0, st>>>(xq, rows, d, off, nq, best_d, best_pos);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gather_rows(const float* x, const int* list, int n, int d, float* out, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     gather_rows_kernel<<<n, 128, 0, st>>>(x, list, n, d, out);

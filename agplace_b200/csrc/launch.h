@@ -127,6 +127,11 @@ cudaError_t launch_prep_rows_screen(const float* x, int64_t n, int d, int d_pad,
                                     uint32_t* stats, int is_db, int max_blocks, cudaStream_t st);
 cudaError_t launch_fix_db_scale(const float* x, int64_t count, uint32_t* stats, int max_blocks, cudaStream_t st);
 cudaError_t launch_init_aux(void* plane, int d_pad, int64_t row0, int64_t row1, cudaStream_t st);
+// N2 batched mining helpers (k_misc.cu)
+cudaError_t launch_mask_select(const float* Dp, const int64_t* Ip, int kp, const int64_t* ex_off, const int64_t* ex_ids, int64_t nq, int k,
+                               float* D, int64_t* I, cudaStream_t st);
+cudaError_t launch_best_of_lists(const float* xq, const float* rows, int d, const int64_t* off, int64_t nq, float* best_d,
+                                 int64_t* best_pos, cudaStream_t st);
 // rows out[i] = x[list[i]] and results D/I[list[i]] = Dt/It[i] (exact fallback of overflowed queries)
 cudaError_t launch_gather_rows(const float* x, const int* list, int n, int d, float* out, cudaStream_t st);
 cudaError_t launch_scatter_results(const float* Dt, const int64_t* It, const int* list, int n, int k, float* D, int64_t* I, cudaStream_t st);

@@ -165,6 +165,28 @@ class IndexFlatL2:
         x.record_stream(torch.cuda.current_stream(x.device))
         return D, I
 
+    def search_masked(self, x, k, exclude):
+        """Batched masked search.  ``exclude[q]`` = row ids of this index that query q must not
+        return -- the reference's ``np.setdiff1d(sampled_database_indexes, soft_positives)`` followed by a
+        fresh ``IndexFlatL2`` per query (datasets/datasets_ws_kitti360.py:1088-1091, 985-993), for all queries
+        in one call.  Returns numpy ``(D fp32 [nq,k], I int64 [nq,k])`` with ids referring to THIS index."""
+        n, d = x.shape
+        assert d == self.d
+        assert k > 0
+        assert len(exclude) == n
+        if _is_torch(x):
+            x = x.detach().cpu().numpy()
+        x = np.ascontiguousarray(x, dtype="float32")
+        offsets, ids = positives_to_csr(exclude)
+        D = np.empty((n, int(k)), dtype=np.float32)
+        I = np.empty((n, int(k)), dtype=np.int64)
+        self._use_own_stream()
+        _lib.check(self._lib.agp_index_search_masked(self._h, n, ctypes.c_void_p(x.ctypes.data), _lib.MEM_HOST, int(k),
+                                                     ctypes.c_void_p(offsets.ctypes.data), ctypes.c_void_p(ids.ctypes.data),
+                                                     ctypes.c_void_p(D.ctypes.data), ctypes.c_void_p(I.ctypes.data), _lib.MEM_HOST),
+                   "agp_index_search_masked")
+        return D, I
+
     # ------------------------------------------------------------------ instrumentation (bench.py)
     def set_profiling(self, enable: bool):
         _lib.check(self._lib.agp_index_set_profiling(self._h, int(bool(enable))), "agp_index_set_profiling")
@@ -190,6 +212,26 @@ def positives_to_csr(positives_per_query):
     ids = (np.concatenate([np.asarray(p, dtype=np.int64).reshape(-1) for p in positives_per_query])
            if len(lens) and offsets[-1] > 0 else np.empty(0, dtype=np.int64))
     return offsets, np.ascontiguousarray(ids)
+
+
+def best_of_lists(xq, rows, offsets, device=None):
+    """Nearest row of each query's own candidate list on the GPU (N2; the reference's
+    ``get_best_positive_index``, datasets/datasets_ws_kitti360.py:976-983, batched).  ``rows`` are the gathered
+    candidate features, list q = ``rows[offsets[q]:offsets[q+1]]``.  Returns ``(best_distance fp32 [nq],
+    best_position int64 [nq])`` -- position inside the query's own list, first on ties, -1 if empty."""
+    lib = _lib.load()
+    device = default_device() if device is None else int(device)
+    xq = np.ascontiguousarray(xq, dtype=np.float32)
+    rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, xq.shape[1])
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    nq, d = xq.shape
+    assert len(offsets) == nq + 1 and offsets[-1] == len(rows)
+    bd = np.empty(nq, dtype=np.float32)
+    bp = np.empty(nq, dtype=np.int64)
+    _lib.check(lib.agp_best_of_lists(device, nq, d, ctypes.c_void_p(xq.ctypes.data), ctypes.c_void_p(rows.ctypes.data),
+                                     ctypes.c_void_p(offsets.ctypes.data), ctypes.c_void_p(bd.ctypes.data),
+                                     ctypes.c_void_p(bp.ctypes.data)), "agp_best_of_lists")
+    return bd, bp
 
 
 def recall_hits(predictions, positives_per_query, recall_values, device=None):

@@ -10,6 +10,12 @@ and ``datasets_ws.py:689-706``):
   ``compute_triplets_full`` (kitti360:1022-1049), including the order of ``np.random`` draws, so
   that the mined ``triplets_global_indexes`` are identical for identical descriptors.
 
+``compute_triplets_partial_batched`` / ``compute_triplets_full_batched`` produce the SAME
+``triplets_global_indexes`` -- same RNG draws, same arithmetic (exact fp32 difference form), same tie order -- with
+two GPU calls per refresh instead of two index constructions + two searches per query: one
+``best_of_lists`` over every query's own hard positives and one ``IndexFlatL2.search_masked`` over the sampled
+database rows with the per-query soft positives masked out.
+
 Feature extraction (``compute_cache*``) is the caller's business: ``cache`` is any object whose
 ``cache[i]`` / ``cache[index_array]`` returns fp32 rows, e.g. :class:`RAMEfficient2DMatrix`
 (kitti360:1147-1167) or a plain ndarray.
@@ -18,7 +24,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .index import IndexFlatL2
+from .index import IndexFlatL2, best_of_lists
 
 
 class RAMEfficient2DMatrix:
@@ -118,4 +124,39 @@ class TripletMiner:
             self.neg_cache[query_index] = neg_indexes
             triplets.append((query_index, best_positive_index, *neg_indexes))
         self.triplets_global_indexes = np.asarray(triplets, dtype=np.int64)
+        return self.triplets_global_indexes
+
+    # ------------------------------------------------------------------ batched (N2)
+    def _best_positives_batched(self, sampled_queries_indexes, cache, query_features):
+        """get_best_positive_index for every sampled query in one kernel launch."""
+        lens = np.array([len(self.hard_positives_per_query[q]) for q in sampled_queries_indexes], dtype=np.int64)
+        offsets = np.zeros(len(lens) + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        all_pos = np.concatenate([np.asarray(self.hard_positives_per_query[q]).reshape(-1) for q in sampled_queries_indexes])
+        rows = np.asarray(cache[all_pos], dtype=np.float32)
+        _, best = best_of_lists(query_features, rows, offsets)
+        return np.array([self.hard_positives_per_query[q][b] for q, b in zip(sampled_queries_indexes, best)], dtype=np.int64)
+
+    def compute_triplets_partial_batched(self, cache, cache_refresh_rate):
+        """Same result as :meth:`compute_triplets_partial` (kitti360:1056-1137): the sampled database rows are
+        indexed ONCE, in the order of the random draw -- ``np.setdiff1d(..., assume_unique=True)`` does not sort, so
+        that is the order (and the tie-break order) of every per-query subset in the reference -- each query's soft
+        positives inside the sample become its exclusion list, and positions map back through the sample."""
+        sampled_queries_indexes = np.random.choice(self.queries_num, cache_refresh_rate, replace=False)
+        sampled_database_indexes = np.random.choice(self.database_num, self.neg_samples_num, replace=False)
+        query_features = np.stack([self.get_query_features(q, cache) for q in sampled_queries_indexes]).astype(np.float32)
+        best_pos = self._best_positives_batched(sampled_queries_indexes, cache, query_features)
+        sample = np.asarray(sampled_database_indexes)
+        index = self.index_cls(self.features_dim)
+        index.add(np.asarray(cache[sample], dtype=np.float32))
+        exclude = []
+        for q in sampled_queries_indexes:
+            soft = np.asarray(self.soft_positives_per_query[q]).reshape(-1)
+            exclude.append(np.flatnonzero(np.isin(sample, soft)).astype(np.int64))
+        _, I = index.search_masked(query_features, self.negs_num_per_query, exclude)
+        # (I == -1, fewer than negs_num_per_query candidates, wraps to the last element exactly like the reference's
+        # numpy indexing of neg_samples[neg_nums])
+        negs = sample[I].astype(np.int32)
+        self.triplets_global_indexes = np.concatenate(
+            [sampled_queries_indexes.reshape(-1, 1).astype(np.int64), best_pos.reshape(-1, 1), negs.astype(np.int64)], axis=1)
         return self.triplets_global_indexes

@@ -102,6 +102,24 @@ AGP_API int agp_index_get_profile(agp_index* idx, double* kernel_ms, int64_t* ke
  * representable in the fp16 plane (diagnostics). */
 AGP_API int agp_index_get_stats(const agp_index* idx, int64_t* screened_queries, int64_t* fallback_queries);
 
+/* Batched, masked search: one call for what the reference's mining loop does per query,
+ *   neg = np.setdiff1d(sampled_database_indexes, soft_positives[q]); IndexFlatL2(d).add(cache[neg]).search(q, k)
+ * (datasets/datasets_ws_kitti360.py:1088-1091 + 985-993; copies in datasets_ws_nuscenes.py, datasets_ws.py).
+ * The index holds the sampled rows once; query q's excluded row ids (positions in the index) are
+ * excl_ids[excl_offsets[q] .. excl_offsets[q+1]) (HOST arrays).  Returns the k nearest non-excluded rows,
+ * ascending, ties by id, padded (3.4028235e38, -1) -- exactly what a fresh index over the surviving rows
+ * returns, with positions referring to the full index.  k + longest exclusion list <= AGP_MAX_K. */
+AGP_API int agp_index_search_masked(agp_index* idx, int64_t nq, const float* x, int x_mem_kind, int k,
+                                    const int64_t* excl_offsets, const int64_t* excl_ids, float* D, int64_t* I,
+                                    int out_mem_kind);
+
+/* Nearest row of each query's own candidate list (N2; the reference's get_best_positive_index,
+ * datasets/datasets_ws_kitti360.py:976-983, for all queries at once).  xq: nq x d; rows: the gathered
+ * candidate features, list q = rows [offsets[q], offsets[q+1]); all HOST arrays.  best_pos[q] = position
+ * inside list q of the nearest row (exact fp32 difference form, first on ties, -1 for an empty list). */
+AGP_API int agp_best_of_lists(int device, int64_t nq, int d, const float* xq, const float* rows, const int64_t* offsets,
+                              float* best_d, int64_t* best_pos);
+
 /* K4 across shards: merge n_lists per-shard results (device memory, e.g. the output of one NCCL
  * all-gather) into one canonical list per query.  List g holds D at D_lists + g * d_list_stride
  * (floats) and I at I_lists + g * i_list_stride (int64), each [nq][k].  If every id is below

@@ -267,6 +267,53 @@ def test_mined_triplets_identical_to_oracle(mode):
     np.testing.assert_array_equal(out[0], out[1])
 
 
+def test_batched_mining_identical_to_the_per_query_loop():
+    """one best_of_lists + one search_masked per refresh must mine exactly the triplets the
+    reference's per-query loop (two fresh indexes per query) mines -- same RNG draws, same arithmetic, same ties."""
+    from agplace_b200 import mining
+    p = make_mining_problem(33, database_num=3000, queries_num=400, d=256)
+    # duplicate some database rows so that exact distance ties occur among the negatives
+    p.cache[100:140] = p.cache[200:240]
+    out = []
+    for batched in (False, True):
+        miner = mining.TripletMiner(p.d, p.database_num, p.queries_num, p.hard, p.soft, negs_num_per_query=10,
+                                    neg_samples_num=1000)
+        np.random.seed(3)
+        f = miner.compute_triplets_partial_batched if batched else miner.compute_triplets_partial
+        out.append(f(p.cache, 300))
+    np.testing.assert_array_equal(out[0], out[1])
+    assert out[0].shape == (300, 12) and out[0].dtype == np.int64
+
+
+def test_search_masked_equals_search_on_the_surviving_rows():
+    import agplace_b200
+    rng = np.random.default_rng(17)
+    xb = rng.standard_normal((700, 64)).astype(np.float32)
+    xq = rng.standard_normal((90, 64)).astype(np.float32)
+    exclude = [np.sort(rng.choice(700, size=rng.integers(0, 40), replace=False)).astype(np.int64) for _ in range(90)]
+    def check(xb_, xq_, exclude_, k):
+        ix = agplace_b200.IndexFlatL2(64); ix.add(xb_)
+        D, I = ix.search_masked(xq_, k, exclude_)
+        for q in range(len(xq_)):
+            keep = np.setdiff1d(np.arange(len(xb_)), exclude_[q])
+            Dr, Ir = orc.knn_fp32(xq_[q:q + 1], xb_[keep], k)      # nq = 1: faiss's exact difference form
+            Ir = np.where(Ir >= 0, keep[np.clip(Ir, 0, len(keep) - 1)], -1)
+            ok, msg = orc.compare_knn(D[q:q + 1], I[q:q + 1], Dr, Ir)
+            assert ok, f"query {q}: {msg}"
+    check(xb, xq, exclude, 10)
+    # fewer survivors than k: padded (FLT_MAX, -1) like faiss; nq < 20 goes through the difference-form path
+    few = [np.arange(25, dtype=np.int64), np.array([], dtype=np.int64), np.arange(5, 30, dtype=np.int64)]
+    check(xb[:30], xq[:3], few, 10)
+    with pytest.raises(RuntimeError):                          # k + longest exclusion list is bounded by AGP_MAX_K
+        big = agplace_b200.IndexFlatL2(64); big.add(xb)
+        big.search_masked(xq[:1], 10, [np.arange(600, dtype=np.int64)])
+    bd, bp = agplace_b200.best_of_lists(xq[:3], xb[[4, 9, 9, 2, 7]], np.array([0, 2, 2, 5]))
+    d0 = ((xb[[4, 9]].astype(np.float64) - xq[0]) ** 2).sum(1)
+    d2 = ((xb[[9, 2, 7]].astype(np.float64) - xq[2]) ** 2).sum(1)
+    assert bp.tolist() == [int(np.argmin(d0)), -1, int(np.argmin(d2))]
+    np.testing.assert_allclose(bd[[0, 2]], [d0.min(), d2.min()], rtol=2e-6)
+
+
 def test_virtual_shards_merge_equals_single_index():
     """8 virtual shards on one GPU exercise id bases + the cross-shard merge kernel (multi-GPU row)."""
     import ctypes
