@@ -18,7 +18,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <mutex>
 #include <new>
+#include <unordered_map>
 #include <vector>
 
 #include "launch.h"
@@ -58,6 +60,87 @@ static int set_err(int code, const char* fmt, ...) {
         CK(expr);                 \
     } while (0)
 
+// ------------------------------------------------------------------------------------------ device memory / stream pools
+// The reference constructs a fresh IndexFlatL2 for every mined query (two per query, 8000 per cache refresh:
+// datasets/datasets_ws_kitti360.py:978,987), so index construction, add() and destruction must not each pay
+// cudaMalloc / cudaFree / cudaStreamCreate.  Blocks up to 256 MB are recycled through size-class free lists (power of
+// two below 1 MB, whole MB above); a block is only returned here after its owner has synchronised the stream that used
+// it, so the next owner may use it on any stream.  At most 4 GB per device stay cached.
+namespace {
+struct DevPools {
+    std::mutex mu;
+    std::unordered_map<size_t, std::vector<void*>> blocks[16];
+    size_t cached[16] = {0};
+    std::vector<cudaStream_t> streams[16];
+};
+DevPools g_pools;
+constexpr size_t kPoolMaxBlock = size_t(256) << 20, kPoolMaxCached = size_t(4) << 30;
+
+size_t pool_class(size_t bytes) {
+    if (bytes <= 256) return 256;
+    if (bytes < (size_t(1) << 20)) {
+        size_t c = 256;
+        while (c < bytes) c <<= 1;
+        return c;
+    }
+    return (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+}
+
+cudaError_t pool_alloc(int dev, void** p, size_t bytes) {
+    const size_t c = pool_class(bytes);
+    if (dev >= 0 && dev < 16 && c <= kPoolMaxBlock) {
+        std::lock_guard<std::mutex> lk(g_pools.mu);
+        auto it = g_pools.blocks[dev].find(c);
+        if (it != g_pools.blocks[dev].end() && !it->second.empty()) {
+            *p = it->second.back();
+            it->second.pop_back();
+            g_pools.cached[dev] -= c;
+            return cudaSuccess;
+        }
+    }
+    return cudaMalloc(p, c);
+}
+
+// precondition: every stream that touched the block has been synchronised
+void pool_free(int dev, void* p, size_t bytes) {
+    if (!p) return;
+    const size_t c = pool_class(bytes);
+    if (dev >= 0 && dev < 16 && c <= kPoolMaxBlock) {
+        std::lock_guard<std::mutex> lk(g_pools.mu);
+        if (g_pools.cached[dev] + c <= kPoolMaxCached) {
+            g_pools.blocks[dev][c].push_back(p);
+            g_pools.cached[dev] += c;
+            return;
+        }
+    }
+    cudaFree(p);
+}
+
+cudaError_t pool_stream(int dev, cudaStream_t* s) {
+    if (dev >= 0 && dev < 16) {
+        std::lock_guard<std::mutex> lk(g_pools.mu);
+        if (!g_pools.streams[dev].empty()) {
+            *s = g_pools.streams[dev].back();
+            g_pools.streams[dev].pop_back();
+            return cudaSuccess;
+        }
+    }
+    return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+}
+
+void pool_stream_release(int dev, cudaStream_t s) {       // precondition: synchronised
+    if (!s) return;
+    if (dev >= 0 && dev < 16) {
+        std::lock_guard<std::mutex> lk(g_pools.mu);
+        if (g_pools.streams[dev].size() < 64) {
+            g_pools.streams[dev].push_back(s);
+            return;
+        }
+    }
+    cudaStreamDestroy(s);
+}
+}  // namespace
+
 // ------------------------------------------------------------------------------------------ index
 struct Buf {
     void* p = nullptr;
@@ -69,7 +152,8 @@ struct agp_index {
     int64_t ntotal = 0, cap = 0, id_base = 0;
     float *xb = nullptr, *yn = nullptr, *wx = nullptr;
     uint8_t *xb_hi = nullptr, *xb_lo = nullptr;
-    uint8_t* xs = nullptr;        // single-pass screen plane [cap, d_pad + 64] fp16 (scaled rows + aux chunk)
+    uint8_t* xs = nullptr;        // single-pass screen plane [xs_cap, d_pad + 64] fp16 (scaled rows + aux chunk), built lazily
+    int64_t xs_cap = 0, xs_rows = 0;   // plane capacity and rows converted so far (the first screened search converts the rest)
     bool planes = false, screen = false, scale_set = false;
     int kind = KIND_TF32, elem_bytes = 4;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -87,19 +171,26 @@ struct agp_index {
     int64_t prof_launches = 0;
 };
 
+// scratch buffers belong to the index that is currently executing a call on this thread
+static thread_local int t_dev = 0;
+static thread_local cudaStream_t t_stream = nullptr;
+
 static int ensure(Buf& b, size_t bytes) {
     if (b.bytes >= bytes && b.p) return 0;
-    if (b.p) CK(cudaFree(b.p));
+    if (b.p) {
+        CK(cudaStreamSynchronize(t_stream));      // queued work may still use the old block
+        pool_free(t_dev, b.p, b.bytes);
+    }
     b.p = nullptr;
     b.bytes = 0;
-    size_t want = bytes + bytes / 4 + 256;
-    CK(cudaMalloc(&b.p, want));
+    const size_t want = pool_class(bytes + bytes / 4 + 256);
+    CK(pool_alloc(t_dev, &b.p, want));
     b.bytes = want;
     return 0;
 }
 
-static int free_buf(Buf& b) {
-    if (b.p) cudaFree(b.p);
+static int free_buf(Buf& b) {       // caller has synchronised the index's stream
+    if (b.p) pool_free(t_dev, b.p, b.bytes);
     b.p = nullptr;
     b.bytes = 0;
     return 0;
@@ -143,6 +234,8 @@ static int make_plane_map(CUtensorMap* m, const void* base, int64_t rows, int d_
 }
 
 // ------------------------------------------------------------------------------------------ storage
+static size_t screen_row_bytes(const agp_index* ix) { return static_cast<size_t>(ix->d_pad + 64) * 2; }
+
 static int grow(agp_index* ix, int64_t need) {
     if (need <= ix->cap) return 0;
     int64_t ncap = std::max<int64_t>(need, ix->cap + ix->cap / 2);
@@ -150,28 +243,18 @@ static int grow(agp_index* ix, int64_t need) {
     float *nxb = nullptr, *nyn = nullptr, *nwx = nullptr;
     uint8_t *nhi = nullptr, *nlo = nullptr;
     const size_t plane_row = static_cast<size_t>(ix->d_pad) * ix->elem_bytes;
-    CK(cudaMalloc(&nxb, static_cast<size_t>(ncap) * ix->d * sizeof(float)));
-    CK(cudaMalloc(&nyn, static_cast<size_t>(ncap) * sizeof(float)));
+    const int dev = ix->device;
+    CK(pool_alloc(dev, reinterpret_cast<void**>(&nxb), static_cast<size_t>(ncap) * ix->d * sizeof(float)));
+    CK(pool_alloc(dev, reinterpret_cast<void**>(&nyn), static_cast<size_t>(ncap) * sizeof(float)));
     if (ix->planes) {
-        CK(cudaMalloc(&nhi, static_cast<size_t>(ncap) * plane_row));
-        CK(cudaMalloc(&nlo, static_cast<size_t>(ncap) * plane_row));
+        CK(pool_alloc(dev, reinterpret_cast<void**>(&nhi), static_cast<size_t>(ncap) * plane_row));
+        CK(pool_alloc(dev, reinterpret_cast<void**>(&nlo), static_cast<size_t>(ncap) * plane_row));
         if (ix->kind == KIND_F16) {
-            CK(cudaMalloc(&nwx, static_cast<size_t>(ncap) * sizeof(float)));
+            CK(pool_alloc(dev, reinterpret_cast<void**>(&nwx), static_cast<size_t>(ncap) * sizeof(float)));
             LAUNCH(launch_fill_f32(nwx, ncap, 0.f, ix->stream));
         }
     }
-    uint8_t* nxs = nullptr;
-    const size_t screen_row = static_cast<size_t>(ix->d_pad + 64) * 2;
-    if (ix->screen) {
-        CK(cudaMalloc(&nxs, static_cast<size_t>(ncap) * screen_row));
-        CK(cudaMemsetAsync(nxs, 0, static_cast<size_t>(ncap) * screen_row, ix->stream));     // rows without a vector: finite zeros + aux -inf
-    }
     LAUNCH(launch_fill_f32(nyn, ncap, HUGE_VALF, ix->stream));
-    if (ix->screen) {
-        if (ix->ntotal > 0)
-            CK(cudaMemcpyAsync(nxs, ix->xs, static_cast<size_t>(ix->ntotal) * screen_row, cudaMemcpyDeviceToDevice, ix->stream));
-        LAUNCH(launch_init_aux(nxs, ix->d_pad, ix->ntotal, ncap, ix->stream));      // rows without a vector: aux = -inf
-    }
     if (ix->ntotal > 0) {
         CK(cudaMemcpyAsync(nxb, ix->xb, static_cast<size_t>(ix->ntotal) * ix->d * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
         CK(cudaMemcpyAsync(nyn, ix->yn, static_cast<size_t>(ix->ntotal) * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
@@ -181,16 +264,48 @@ static int grow(agp_index* ix, int64_t need) {
             if (nwx) CK(cudaMemcpyAsync(nwx, ix->wx, static_cast<size_t>(ix->ntotal) * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
         }
     }
-    CK(cudaStreamSynchronize(ix->stream));
-    if (ix->xb) cudaFree(ix->xb);
-    if (ix->yn) cudaFree(ix->yn);
-    if (ix->xb_hi) cudaFree(ix->xb_hi);
-    if (ix->xb_lo) cudaFree(ix->xb_lo);
-    if (ix->wx) cudaFree(ix->wx);
-    if (ix->xs) cudaFree(ix->xs);
-    ix->xs = nxs;
+    if (ix->cap > 0) {
+        CK(cudaStreamSynchronize(ix->stream));      // the old blocks go back to the pool only once nothing queued reads them
+        pool_free(dev, ix->xb, static_cast<size_t>(ix->cap) * ix->d * sizeof(float));
+        pool_free(dev, ix->yn, static_cast<size_t>(ix->cap) * sizeof(float));
+        pool_free(dev, ix->xb_hi, static_cast<size_t>(ix->cap) * plane_row);
+        pool_free(dev, ix->xb_lo, static_cast<size_t>(ix->cap) * plane_row);
+        pool_free(dev, ix->wx, static_cast<size_t>(ix->cap) * sizeof(float));
+    }
     ix->xb = nxb; ix->yn = nyn; ix->xb_hi = nhi; ix->xb_lo = nlo; ix->wx = nwx;
     ix->cap = ncap;
+    return 0;
+}
+
+// The fp16 screen plane is built on demand: an index that only ever answers small batches (the reference's mining
+// calls: 1 query against <= 1000 rows) never pays for it.  Converts rows [xs_rows, ntotal) from the resident fp32 rows.
+static int ensure_screen_plane(agp_index* ix) {
+    const size_t row = screen_row_bytes(ix);
+    if (ix->xs_cap < ix->cap) {
+        uint8_t* nxs = nullptr;
+        CK(pool_alloc(ix->device, reinterpret_cast<void**>(&nxs), static_cast<size_t>(ix->cap) * row));
+        CK(cudaMemsetAsync(nxs, 0, static_cast<size_t>(ix->cap) * row, ix->stream));     // rows without a vector: finite zeros ...
+        if (ix->xs_rows > 0)
+            CK(cudaMemcpyAsync(nxs, ix->xs, static_cast<size_t>(ix->xs_rows) * row, cudaMemcpyDeviceToDevice, ix->stream));
+        LAUNCH(launch_init_aux(nxs, ix->d_pad, ix->xs_rows, ix->cap, ix->stream));         // ... and aux = -inf
+        if (ix->xs) {
+            CK(cudaStreamSynchronize(ix->stream));
+            pool_free(ix->device, ix->xs, static_cast<size_t>(ix->xs_cap) * row);
+        }
+        ix->xs = nxs;
+        ix->xs_cap = ix->cap;
+    }
+    if (ix->xs_rows < ix->ntotal) {
+        const int64_t n = ix->ntotal - ix->xs_rows;
+        const float* src = ix->xb + ix->xs_rows * ix->d;
+        if (!ix->scale_set) {      // database-wide fp16 scale: fixed by the rows present at the first conversion after create / reset
+            LAUNCH(launch_fix_db_scale(src, n * ix->d, ix->dbstats, ix->num_sms * 8, ix->stream));
+            ix->scale_set = true;
+        }
+        LAUNCH(launch_prep_rows_screen(src, n, ix->d, ix->d_pad, ix->xs + static_cast<size_t>(ix->xs_rows) * row, nullptr, nullptr, nullptr,
+                                       ix->dbstats, 1, ix->num_sms * 32, ix->stream));
+        ix->xs_rows = ix->ntotal;
+    }
     return 0;
 }
 
@@ -480,6 +595,7 @@ static int screen_regs_for_k(int k) {
 static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, float* D, int64_t* I) {
     const int64_t n = ix->ntotal;
     if (k > 256 || !ix->screen || (ix->num_sms & 1)) return search_simt(ix, xq_dev, nq, k, D, I);
+    CKR(ensure_screen_plane(ix));
     const int E = screen_regs_for_k(k);
     const int slots = 32 * E;
     const int n_dbtiles = static_cast<int>((n + TC_BN - 1) / TC_BN);
@@ -629,6 +745,14 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
     return 0;
 }
 
+// every entry point that touches an index starts here: device current, scratch pool bound to the index's stream
+#define ENTER(ix)                          \
+    do {                                   \
+        CK(cudaSetDevice((ix)->device));   \
+        t_dev = (ix)->device;              \
+        t_stream = (ix)->stream;           \
+    } while (0)
+
 // ------------------------------------------------------------------------------------------ C ABI
 extern "C" {
 
@@ -656,9 +780,18 @@ int agp_index_create(int d, int device, int precision_mode, agp_index** out) {
         return set_err(AGP_ENODEV, "no CUDA device visible: agpknn has no CPU fallback");
     }
     if (device < 0 || device >= ndev) return set_err(AGP_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) return set_err(AGP_ENODEV, "device %d is sm_%d%d; agpknn is built for sm_100a only", device, prop.major, prop.minor);
+    // device attributes are cached: the mining loop constructs thousands of indexes (cudaGetDeviceProperties is slow)
+    static int s_major[16] = {0}, s_minor[16] = {0}, s_sms[16] = {0};
+    int major = 0, minor = 0, sms = 0;
+    if (device < 16 && s_sms[device] > 0) {
+        major = s_major[device]; minor = s_minor[device]; sms = s_sms[device];
+    } else {
+        CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+        CK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        if (device < 16) { s_major[device] = major; s_minor[device] = minor; s_sms[device] = sms; }
+    }
+    if (major != 10) return set_err(AGP_ENODEV, "device %d is sm_%d%d; agpknn is built for sm_100a only", device, major, minor);
     CK(cudaSetDevice(device));
     agp_index* ix = new (std::nothrow) agp_index();
     if (!ix) return set_err(AGP_ENOMEM, "host allocation failed");
@@ -666,19 +799,20 @@ int agp_index_create(int d, int device, int precision_mode, agp_index** out) {
     ix->d_pad = static_cast<int>(round_up(d, TC_KPAD));
     ix->device = device;
     ix->mode = precision_mode;
-    ix->num_sms = prop.multiProcessorCount;
+    ix->num_sms = sms;
     ix->planes = (precision_mode == AGP_PRECISION_3XTF32 || precision_mode == AGP_PRECISION_3XFP16);
     ix->screen = (precision_mode == AGP_PRECISION_AUTO || precision_mode == AGP_PRECISION_FP16_SCREEN);
     ix->kind = (precision_mode == AGP_PRECISION_3XTF32) ? KIND_TF32 : KIND_F16;
     ix->elem_bytes = ix->kind == KIND_TF32 ? 4 : 2;
-    cudaError_t e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
+    cudaError_t e = pool_stream(device, &ix->own_stream);
     if (e != cudaSuccess) {
         delete ix;
         return set_err(AGP_ECUDA, "stream creation failed: %s", cudaGetErrorString(e));
     }
     ix->stream = ix->own_stream;
-    if (cudaMalloc(&ix->dbstats, 4 * sizeof(uint32_t)) != cudaSuccess || cudaMemset(ix->dbstats, 0, 4 * sizeof(uint32_t)) != cudaSuccess) {
-        cudaStreamDestroy(ix->own_stream);
+    if (pool_alloc(device, reinterpret_cast<void**>(&ix->dbstats), 4 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemsetAsync(ix->dbstats, 0, 4 * sizeof(uint32_t), ix->stream) != cudaSuccess) {
+        pool_stream_release(device, ix->own_stream);
         delete ix;
         return set_err(AGP_ENOMEM, "device allocation failed");
     }
@@ -689,22 +823,28 @@ int agp_index_create(int d, int device, int precision_mode, agp_index** out) {
 void agp_index_free(agp_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
+    t_dev = ix->device;
+    t_stream = ix->stream;
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    if (ix->xb) cudaFree(ix->xb);
-    if (ix->xb_hi) cudaFree(ix->xb_hi);
-    if (ix->xb_lo) cudaFree(ix->xb_lo);
-    if (ix->yn) cudaFree(ix->yn);
-    if (ix->wx) cudaFree(ix->wx);
-    if (ix->xs) cudaFree(ix->xs);
+    if (ix->own_stream && ix->own_stream != ix->stream) cudaStreamSynchronize(ix->own_stream);
+    const size_t plane_row = static_cast<size_t>(ix->d_pad) * ix->elem_bytes;
+    pool_free(ix->device, ix->xb, static_cast<size_t>(ix->cap) * ix->d * sizeof(float));
+    pool_free(ix->device, ix->yn, static_cast<size_t>(ix->cap) * sizeof(float));
+    pool_free(ix->device, ix->xb_hi, static_cast<size_t>(ix->cap) * plane_row);
+    pool_free(ix->device, ix->xb_lo, static_cast<size_t>(ix->cap) * plane_row);
+    pool_free(ix->device, ix->wx, static_cast<size_t>(ix->cap) * sizeof(float));
+    pool_free(ix->device, ix->xs, static_cast<size_t>(ix->xs_cap) * screen_row_bytes(ix));
+    pool_free(ix->device, ix->dbstats, 4 * sizeof(uint32_t));
     free_buf(ix->sq);
-    free_buf(ix->dq); free_buf(ix->hthr); free_buf(ix->mk_d); free_buf(ix->mk_i); free_buf(ix->mk_off); free_buf(ix->mk_ids); free_buf(ix->ovf); free_buf(ix->ovf_list); free_buf(ix->ovf_x); free_buf(ix->ovf_d); free_buf(ix->ovf_i);
-    if (ix->dbstats) cudaFree(ix->dbstats);
-    if (ix->h_count) cudaFreeHost(ix->h_count);
+    free_buf(ix->dq); free_buf(ix->hthr); free_buf(ix->mk_d); free_buf(ix->mk_i); free_buf(ix->mk_off); free_buf(ix->mk_ids);
+    free_buf(ix->ovf); free_buf(ix->ovf_list); free_buf(ix->ovf_x); free_buf(ix->ovf_d); free_buf(ix->ovf_i);
     free_buf(ix->q_raw); free_buf(ix->q_hi); free_buf(ix->q_lo); free_buf(ix->qn); free_buf(ix->cand);
-    free_buf(ix->gthr); free_buf(ix->dbg); free_buf(ix->cand_d); free_buf(ix->cand_i); free_buf(ix->partial); free_buf(ix->panel); free_buf(ix->d_out); free_buf(ix->i_out);
+    free_buf(ix->gthr); free_buf(ix->dbg); free_buf(ix->cand_d); free_buf(ix->cand_i); free_buf(ix->partial); free_buf(ix->panel);
+    free_buf(ix->d_out); free_buf(ix->i_out);
+    if (ix->h_count) cudaFreeHost(ix->h_count);
     for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
     if (ix->ev_order) cudaEventDestroy(ix->ev_order);
-    if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
+    pool_stream_release(ix->device, ix->own_stream);
     delete ix;
 }
 
@@ -718,7 +858,7 @@ int agp_index_set_stream(agp_index* ix, void* s, int use_own_stream) {
     if (ns != ix->stream) {
         // order everything already queued on the old stream (adds, searches that still own the
         // scratch buffers) before anything the new stream will run
-        CK(cudaSetDevice(ix->device));
+        ENTER(ix);
         if (!ix->ev_order) CK(cudaEventCreateWithFlags(&ix->ev_order, cudaEventDisableTiming));
         CK(cudaEventRecord(ix->ev_order, ix->stream));
         CK(cudaStreamWaitEvent(ns, ix->ev_order, 0));
@@ -742,7 +882,7 @@ int agp_index_set_profiling(agp_index* ix, int on) {
 
 int agp_index_get_profile(agp_index* ix, double* ms, int64_t* launches, int reset) {
     if (!ix) return set_err(AGP_EINVAL, "index is null");
-    CK(cudaSetDevice(ix->device));
+    ENTER(ix);
     prof_collect(ix);
     if (ms) *ms = ix->prof_ms;
     if (launches) *launches = ix->prof_launches;
@@ -755,18 +895,19 @@ int agp_index_get_profile(agp_index* ix, double* ms, int64_t* launches, int rese
 
 int agp_index_reserve(agp_index* ix, int64_t n) {
     if (!ix) return set_err(AGP_EINVAL, "index is null");
-    CK(cudaSetDevice(ix->device));
+    ENTER(ix);
     return grow(ix, n);
 }
 
 int agp_index_reset(agp_index* ix) {
     if (!ix) return set_err(AGP_EINVAL, "index is null");
-    CK(cudaSetDevice(ix->device));
+    ENTER(ix);
     if (ix->cap > 0) {
         LAUNCH(launch_fill_f32(ix->yn, ix->cap, HUGE_VALF, ix->stream));
     }
     CK(cudaMemsetAsync(ix->dbstats, 0, 4 * sizeof(uint32_t), ix->stream));
-    if (ix->screen && ix->cap > 0) LAUNCH(launch_init_aux(ix->xs, ix->d_pad, 0, ix->cap, ix->stream));
+    if (ix->xs) LAUNCH(launch_init_aux(ix->xs, ix->d_pad, 0, ix->xs_cap, ix->stream));
+    ix->xs_rows = 0;
     ix->scale_set = false;
     ix->ntotal = 0;
     return 0;
@@ -785,20 +926,13 @@ int agp_index_add(agp_index* ix, int64_t n, const float* x, int mem_kind) {
     if (n == 0) return 0;
     if (!x) return set_err(AGP_EINVAL, "x is null");
     if (ix->ntotal + n > 0x7fffffffLL) return set_err(AGP_EINVAL, "a single shard holds at most 2^31-1 rows");
-    CK(cudaSetDevice(ix->device));
+    ENTER(ix);
     CKR(grow(ix, ix->ntotal + n));
     float* dst = ix->xb + ix->ntotal * ix->d;
     CK(cudaMemcpyAsync(dst, x, static_cast<size_t>(n) * ix->d * sizeof(float),
                        mem_kind == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ix->stream));
     const size_t plane_off = static_cast<size_t>(ix->ntotal) * ix->d_pad * ix->elem_bytes;
-    if (ix->screen) {
-        if (!ix->scale_set) {      // database-wide fp16 scale: fixed by the first batch after create / reset
-            LAUNCH(launch_fix_db_scale(dst, n * ix->d, ix->dbstats, ix->num_sms * 8, ix->stream));
-            ix->scale_set = true;
-        }
-        LAUNCH(launch_prep_rows_screen(dst, n, ix->d, ix->d_pad, ix->xs + static_cast<size_t>(ix->ntotal) * (ix->d_pad + 64) * 2,
-                                       ix->yn + ix->ntotal, nullptr, nullptr, ix->dbstats, 1, ix->num_sms * 32, ix->stream));
-    } else if (ix->planes && ix->kind == KIND_F16) {
+    if (ix->planes && ix->kind == KIND_F16) {
         LAUNCH(launch_prep_rows_f16(dst, n, ix->d, ix->d_pad, ix->yn + ix->ntotal, ix->xb_hi + plane_off, ix->xb_lo + plane_off,
                                     ix->wx + ix->ntotal, -2.f, nullptr, ix->dbstats, ix->num_sms * 32, ix->stream));
     } else if (ix->planes) {
@@ -820,7 +954,7 @@ int agp_index_search(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, 
     if (nq == 0) return 0;
     if (!x || !D || !I) return set_err(AGP_EINVAL, "x, D and I must be non-null");
     if (nq > 0x7fffffffLL) return set_err(AGP_EINVAL, "nq too large");
-    CK(cudaSetDevice(ix->device));
+    ENTER(ix);
 
     const float* xq_dev = x;
     if (x_mem_kind != AGP_MEM_DEVICE) {
@@ -882,7 +1016,7 @@ int agp_index_search_masked(agp_index* ix, int64_t nq, const float* x, int x_mem
     const int64_t kp64 = std::min<int64_t>(k + max_ex, std::max<int64_t>(ix->ntotal, k));
     if (kp64 > AGP_MAX_K) return set_err(AGP_EINVAL, "k + longest exclusion list = %lld exceeds AGP_MAX_K=%d", static_cast<long long>(k + max_ex), AGP_MAX_K);
     const int kp = static_cast<int>(kp64);
-    CK(cudaSetDevice(ix->device));
+    ENTER(ix);
     CKR(ensure(ix->mk_d, static_cast<size_t>(nq) * kp * sizeof(float)));
     CKR(ensure(ix->mk_i, static_cast<size_t>(nq) * kp * sizeof(int64_t)));
     CKR(ensure(ix->mk_off, static_cast<size_t>(nq + 1) * sizeof(int64_t)));

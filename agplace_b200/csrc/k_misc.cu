@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256) prep_rows_screen_kernel(const float* __re
         if (lane == 1) aux = __floats2half2_rn(a2, 0.f);
         prow[(d_pad >> 1) + lane] = aux;
         if (lane == 0) {
-            norm[r] = acc;
+            if (norm) norm[r] = acc;
             if (scale_out) scale_out[r] = s;
             float dr = sqrtf(res) * s * 1.001f;        // residual norm in the row's own units, rounded up
             if (bad || !(dr < inf)) dr = inf;
