@@ -139,7 +139,7 @@ def run_reference(args):
     orc.build()
     c = workload(args.workload)
     if c["n"] * c["d"] * 4 > 24e9:
-        print(json.dumps({"impl": "reference", "unavailable": f"{c['name']} database does not fit this host's RAM budget for the CPU port"}))
+        emit(json.dumps({"impl": "reference", "unavailable": f"{c['name']} database does not fit this host's RAM budget for the CPU port"}))
         return 0
     xb, xq = make_host_data(c)
     cores = os.cpu_count() or 1
@@ -158,7 +158,7 @@ def run_reference(args):
     sample_desc = f"{sample_q} of {c['nq']} queries x full {c['n']}x{c['d']} database per step, k={c['k']}"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{c['name']}: {c['desc']}", "n": c["n"], "nq": c["nq"], "d": c["d"], "k": c["k"],
                    "note": "faiss-IndexFlatL2-equivalent CPU restatement (faiss not installable in this image); bounded query sample per step"},
@@ -166,7 +166,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     return 0
 
 
@@ -368,13 +368,34 @@ def run_ours(args):
                                 "sample": f"{sample_q} of {nq} queries x full {n}x{d} database, k={k}, one pass ({dt:.1f} s); "
                                           "faiss-IndexFlatL2-equivalent CPU restatement (numpy/OpenBLAS sgemm + C heaps)"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Only the JSON line may reach stdout: libraries that print there at C level (NCCL's version banner) are sent
+    to stderr by re-pointing fd 1; emit() writes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(text):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (text + "\n").encode())
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
