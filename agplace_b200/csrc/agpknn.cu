@@ -525,15 +525,15 @@ static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, floa
         const char* env_dbg = getenv("AGP_TC_DEBUG");
         const bool dbg = env_dbg && atoi(env_dbg) != 0;
         if (dbg) {
-            CKR(ensure(ix->dbg, static_cast<size_t>(grid) * 8 * sizeof(long long)));
-            CK(cudaMemsetAsync(ix->dbg.p, 0, static_cast<size_t>(grid) * 8 * sizeof(long long), ix->stream));
+            CKR(ensure(ix->dbg, static_cast<size_t>(grid) * 16 * sizeof(long long)));
+            CK(cudaMemsetAsync(ix->dbg.p, 0, static_cast<size_t>(grid) * 16 * sizeof(long long), ix->stream));
             p.dbg = static_cast<long long*>(ix->dbg.p);
         }
         ProfScope prof(ix);
         CKR(DISPATCH_E(kc, launch_knn_tc, m_qhi, m_qlo, m_bhi, m_blo, p, grid, ix->stream));
         prof.stop();
         if (dbg) {
-            std::vector<long long> h(static_cast<size_t>(grid) * 8);
+            std::vector<long long> h(static_cast<size_t>(grid) * 16);
             CK(cudaMemcpyAsync(h.data(), ix->dbg.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
             CK(cudaStreamSynchronize(ix->stream));
             double s[8] = {0};
@@ -606,9 +606,9 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
     const int q_bytes = resident ? num_kc * chunk_bytes : 0;
     const int stage_bytes = resident ? chunk_bytes : 2 * chunk_bytes;
     const int smem_max = 227 * 1024;
-    int n_stages = std::min(8, (smem_max - 1024 - 512 - q_bytes) / stage_bytes);
+    int n_stages = std::min(8, (smem_max - 1024 - SC_BAR_BYTES - SC_XCHG_BYTES - q_bytes) / stage_bytes);
     { const char* e = getenv("AGP_SCREEN_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= n_stages) n_stages = atoi(e); }
-    const size_t smem = 1024 + static_cast<size_t>(q_bytes) + static_cast<size_t>(n_stages) * stage_bytes + 512;
+    const size_t smem = 1024 + static_cast<size_t>(q_bytes) + static_cast<size_t>(n_stages) * stage_bytes + SC_BAR_BYTES + SC_XCHG_BYTES;
     CUtensorMap m_b;
     // whole 256-row tiles: rows between ntotal and the tile end are storage padding masked by yn = +inf
     CKR(make_plane_map(&m_b, ix->xs, static_cast<int64_t>(n_dbtiles) * TC_BN, ix->d_pad, TC_BM, 2, ld));
@@ -656,9 +656,11 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         p.n_items = p.n_full_items + rem_tiles * p.rem_splits;
         p.q_resident = resident;
         p.n_stages = n_stages;
-        p.sched_mul = 2;
+        p.sched_mul = 8;
+        p.flags = 0;
         { const char* e = getenv("AGP_SCREEN_SKIP_EPI"); p.debug_skip_epilogue = (e && atoi(e) != 0) ? 1 : 0; }
-        { const char* e = getenv("AGP_SCREEN_SCHED"); if (e && atoi(e) >= 2) p.sched_mul = atoi(e); }
+        { const char* e = getenv("AGP_SCREEN_SCHED"); if (e && atoi(e) >= 5) p.sched_mul = atoi(e); }     // quarters: 8 = x2, 6 = x1.5
+        { const char* e = getenv("AGP_SCREEN_FLAGS"); if (e) p.flags = atoi(e); }
         const int grid = 2 * std::min(p.n_items, clusters);
         const size_t n_lists_total = static_cast<size_t>(p.n_full_items) * 2 * TC_BM * 2 + static_cast<size_t>(rem_tiles) * 2 * TC_BM * 2 * p.rem_splits;
         CKR(ensure(ix->cand, n_lists_total * sizeof(int)));
@@ -685,8 +687,8 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         const char* env_dbg = getenv("AGP_TC_DEBUG");
         const bool dbg = env_dbg && atoi(env_dbg) != 0;
         if (dbg) {
-            CKR(ensure(ix->dbg, static_cast<size_t>(grid) * 8 * sizeof(long long)));
-            CK(cudaMemsetAsync(ix->dbg.p, 0, static_cast<size_t>(grid) * 8 * sizeof(long long), ix->stream));
+            CKR(ensure(ix->dbg, static_cast<size_t>(grid) * 16 * sizeof(long long)));
+            CK(cudaMemsetAsync(ix->dbg.p, 0, static_cast<size_t>(grid) * 16 * sizeof(long long), ix->stream));
             p.dbg = static_cast<long long*>(ix->dbg.p);
         }
         int* ovf_count = static_cast<int*>(ix->ovf_list.p);
@@ -700,12 +702,12 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
                         static_cast<const int*>(ix->ovf.p), ovf_count, ovf_list, ix->id_base, D + q0 * k, I + q0 * k, ix->stream));
         CK(cudaMemcpyAsync(ix->h_count, ovf_count, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
         if (dbg) {
-            std::vector<long long> h(static_cast<size_t>(grid) * 8);
+            std::vector<long long> h(static_cast<size_t>(grid) * 16);
             CK(cudaMemcpyAsync(h.data(), ix->dbg.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
             CK(cudaStreamSynchronize(ix->stream));
-            double sl[8] = {0}, sa[8] = {0};
+            double sl[16] = {0}, sa[16] = {0};
             for (int b = 0; b < grid; ++b)
-                for (int j = 0; j < 8; ++j) { sa[j] += static_cast<double>(h[b * 8 + j]) / grid; if ((b & 1) == 0) sl[j] += static_cast<double>(h[b * 8 + j]) / (grid / 2); }
+                for (int j = 0; j < 16; ++j) { sa[j] += static_cast<double>(h[b * 16 + j]) / grid; if ((b & 1) == 0) sl[j] += static_cast<double>(h[b * 16 + j]) / (grid / 2); }
             std::vector<int> pc(n_lists_total);
             CK(cudaMemcpy(pc.data(), ix->cand.p, pc.size() * sizeof(int), cudaMemcpyDeviceToHost));
             double tot = 0; int mx = 0;
@@ -724,7 +726,7 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
                 fprintf(stderr, "\n");
             }
             fprintf(stderr, "[agp screen dbg] mma(leader): total=%.0f wait_full=%.0f wait_tempty=%.0f | epi(w2, all CTAs): total=%.0f wait_tfull=%.0f "
-                            "compact=%.0f n_compact=%.0f hits(lane0,w2)=%.0f (cycles, mean)\n", sl[0], sl[1], sl[2], sa[3], sa[4], sa[5], sa[6], sa[7]);
+                            "compact=%.0f n_compact=%.0f hits(lane0,w2)=%.0f scan=%.0f tiles=%.0f compact_first=%.0f flags=%d sched=%d (cycles, mean)\n", sl[0], sl[1], sl[2], sa[3], sa[4], sa[5], sa[6], sa[7], sa[8], sa[9], sa[10], p.flags, p.sched_mul);
         }
         CK(cudaStreamSynchronize(ix->stream));
         const int n_ovf = *ix->h_count;
@@ -1039,6 +1041,63 @@ int agp_index_search_masked(agp_index* ix, int64_t nq, const float* x, int x_mem
         CK(cudaMemcpyAsync(I, I_dev, static_cast<size_t>(nq) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
     }
     CK(cudaStreamSynchronize(ix->stream));      // the exclusion lists are host memory the caller may reuse
+    return 0;
+}
+
+int agp_index_search_subset(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, int k, const int64_t* cand_offsets,
+                            const int64_t* cand_ids, float* D, int64_t* I, int out_mem_kind) {
+    if (!ix) return set_err(AGP_EINVAL, "index is null");
+    if (nq < 0) return set_err(AGP_EINVAL, "nq must be >= 0");
+    if (k <= 0) return set_err(AGP_EINVAL, "k must be positive, got %d", k);
+    if (k > AGP_MAX_K) return set_err(AGP_EINVAL, "k=%d exceeds AGP_MAX_K=%d", k, AGP_MAX_K);
+    if (nq == 0) return 0;
+    if (!x || !D || !I || !cand_offsets) return set_err(AGP_EINVAL, "x, D, I and cand_offsets must be non-null");
+    if (nq > 0x7fffffffLL) return set_err(AGP_EINVAL, "nq too large");
+    if (cand_offsets[0] != 0) return set_err(AGP_EINVAL, "cand_offsets[0] must be 0");
+    if (static_cast<size_t>(ix->d) * sizeof(float) > 48 * 1024) return set_err(AGP_EINVAL, "search_subset supports d <= 12288");
+    for (int64_t q = 0; q < nq; ++q) {
+        const int64_t c = cand_offsets[q + 1] - cand_offsets[q];
+        if (c < 0) return set_err(AGP_EINVAL, "cand_offsets must be non-decreasing");
+        if (c > 0xffffffffLL) return set_err(AGP_EINVAL, "candidate list too long");
+    }
+    const int64_t total = cand_offsets[nq];
+    if (total > 0 && !cand_ids) return set_err(AGP_EINVAL, "cand_ids is null");
+    for (int64_t e = 0; e < total; ++e)
+        if (cand_ids[e] < 0 || cand_ids[e] >= ix->ntotal)
+            return set_err(AGP_EINVAL, "cand_ids[%lld] = %lld is not a row of this index (ntotal = %lld)", static_cast<long long>(e),
+                           static_cast<long long>(cand_ids[e]), static_cast<long long>(ix->ntotal));
+    ENTER(ix);
+    const float* xq_dev = x;
+    if (x_mem_kind != AGP_MEM_DEVICE) {
+        CKR(ensure(ix->q_raw, static_cast<size_t>(nq) * ix->d * sizeof(float)));
+        CK(cudaMemcpyAsync(ix->q_raw.p, x, static_cast<size_t>(nq) * ix->d * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+        xq_dev = static_cast<const float*>(ix->q_raw.p);
+    }
+    float* D_dev = D;
+    int64_t* I_dev = I;
+    if (out_mem_kind != AGP_MEM_DEVICE) {
+        CKR(ensure(ix->d_out, static_cast<size_t>(nq) * k * sizeof(float)));
+        CKR(ensure(ix->i_out, static_cast<size_t>(nq) * k * sizeof(int64_t)));
+        D_dev = static_cast<float*>(ix->d_out.p);
+        I_dev = static_cast<int64_t*>(ix->i_out.p);
+    }
+    CKR(ensure(ix->mk_off, static_cast<size_t>(nq + 1) * sizeof(int64_t)));
+    CKR(ensure(ix->mk_ids, static_cast<size_t>(std::max<int64_t>(total, 1)) * sizeof(int64_t)));
+    CKR(ensure(ix->partial, static_cast<size_t>(std::max<int64_t>(total, 1)) * sizeof(uint64_t)));
+    CK(cudaMemcpyAsync(ix->mk_off.p, cand_offsets, static_cast<size_t>(nq + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ix->stream));
+    if (total > 0) CK(cudaMemcpyAsync(ix->mk_ids.p, cand_ids, static_cast<size_t>(total) * sizeof(int64_t), cudaMemcpyHostToDevice, ix->stream));
+    {
+        ProfScope prof(ix);
+        CKR(DISPATCH_E32(k, launch_subset_topk, xq_dev, static_cast<const float*>(ix->xb), ix->d, static_cast<const int64_t*>(ix->mk_off.p),
+                         static_cast<const int64_t*>(ix->mk_ids.p), ix->ntotal, nq, k, static_cast<uint64_t*>(ix->partial.p), D_dev, I_dev,
+                         ix->stream));
+        prof.stop();
+    }
+    if (out_mem_kind != AGP_MEM_DEVICE) {
+        CK(cudaMemcpyAsync(D, D_dev, static_cast<size_t>(nq) * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+        CK(cudaMemcpyAsync(I, I_dev, static_cast<size_t>(nq) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
+    }
+    CK(cudaStreamSynchronize(ix->stream));      // the candidate lists are host memory the caller may reuse
     return 0;
 }
 

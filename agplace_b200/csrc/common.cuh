@@ -124,6 +124,12 @@ __device__ __forceinline__ void batch_fence(float (&d)[8]) {
     asm volatile("" ::: "memory");
     asm volatile("" : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]), "+f"(d[4]), "+f"(d[5]), "+f"(d[6]), "+f"(d[7]));
 }
+__device__ __forceinline__ void batch_fence(uint64_t (&d)[32]) {
+    asm volatile("" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i += 8)
+        asm volatile("" : "+l"(d[i]), "+l"(d[i + 1]), "+l"(d[i + 2]), "+l"(d[i + 3]), "+l"(d[i + 4]), "+l"(d[i + 5]), "+l"(d[i + 6]), "+l"(d[i + 7]));
+}
 __device__ __forceinline__ void batch_fence(uint64_t (&d)[16]) {
     asm volatile("" ::: "memory");
 #pragma unroll

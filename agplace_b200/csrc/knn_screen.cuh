@@ -41,7 +41,6 @@ namespace agp {
 
 constexpr int SC_CHUNK_BYTES = TC_BM * TC_KCHUNK_BYTES;      // 128 rows x 128 B = 16 KB (query chunk, or half a database chunk)
 constexpr int SC_MAX_STAGES = 8;
-constexpr int SC_BAR_BYTES = 512;
 
 struct ScItem {
     int pt, split, t0, t1;
@@ -128,14 +127,20 @@ __device__ __noinline__ void sc_compact_sort(int L, uint64_t* wbuf, int& cnt, fl
 //      (entries below lo count in bucket 0, entries above hi in bucket 15, so the cumulative counts are exact);
 //   4. a second pass keeps, in place, the entries below min(lim, pd + 2 band).
 // Lanes that still cannot free enough slots (pathological ties) get the exact warp sort.
+// Pair exchange (xchg != nullptr: scheduled rounds of an unsplit sweep, entered by BOTH warps of a lane group): the two
+// column halves of a query swap the bound of their ceil(k/2)-th best through shared memory between counting and
+// filtering, so the round already filters against the query-wide bound max(own, partner) instead of the list's own
+// k-th -- the lists leave a round with ~k/2 entries instead of ~k, which is what the next round has to move.
 template <int E>
 __device__ __forceinline__ void sc_compact_lanes(uint64_t* wbuf, int& cnt, float& lim, float band2, int lane, int k, int kh,
-                                                 uint32_t* my_gthr, uint32_t* my_hthr, int* my_ovf) {
+                                                 uint32_t* my_gthr, uint32_t* my_hthr, int* my_ovf, float* xchg, float* xchg_partner,
+                                                 int bar_id) {
     constexpr int CAP = 32 * E;
     const float inf = sc_inf();
-    constexpr int BITS = E > 4 && E <= 8 ? 8 : (E <= 4 ? 8 : 16);     // counter width: lists hold < 2^BITS entries
+    constexpr int BITS = E <= 8 ? 8 : 16;                             // counter width: lists hold < 2^BITS entries
     constexpr int PER = 64 / BITS, NREG = 16 / PER;
-    const bool act = cnt > k + 8;
+    constexpr int FB = 32;                                             // keys in flight per round trip of the filter pass
+    const bool act = cnt > (xchg ? kh : k) + 8;
     const int n = act ? cnt : 0;
     const int nmax = __reduce_max_sync(kFull, n);
     const uint64_t* mine = wbuf + lane;
@@ -154,22 +159,26 @@ __device__ __forceinline__ void sc_compact_lanes(uint64_t* wbuf, int& cnt, float
     if (lim < inf) hi = lim;
     const float scale = 16.f / fmaxf(hi - lo, 1e-30f);
     unsigned long long h0 = 0, h1 = 0, h2 = 0, h3 = 0;      // 16 packed bucket counters (h2, h3 only when BITS == 16)
-    for (int i0 = 0; i0 < nmax; i0 += 32) {     // 32 independent loads in flight per round trip
-        float d[32];
+    auto count = [&](float dv, bool valid) {
+        const int b = min(max(__float2int_rd((dv - lo) * scale), 0), 15);
+        const unsigned long long one = valid ? (1ull << ((b % PER) * BITS)) : 0ull;
+        const int r = b / PER;
+        h0 += (r == 0) ? one : 0ull;
+        h1 += (r == 1) ? one : 0ull;
+        if (NREG > 2) {
+            h2 += (r == 2) ? one : 0ull;
+            h3 += (r == 3) ? one : 0ull;
+        }
+    };
+    int w = 0;
+    {
+        for (int i0 = 0; i0 < nmax; i0 += 32) {     // 32 independent loads in flight per round trip
+            float d[32];
 #pragma unroll
-        for (int u = 0; u < 32; ++u) d[u] = (i0 + u < n) ? slot_dist(mine + (i0 + u) * 32) : -1.f;
-        batch_fence(d);
+            for (int u = 0; u < 32; ++u) d[u] = (i0 + u < n) ? slot_dist(mine + (i0 + u) * 32) : -1.f;
+            batch_fence(d);
 #pragma unroll
-        for (int u = 0; u < 32; ++u) {
-            const int b = min(max(__float2int_rd((d[u] - lo) * scale), 0), 15);
-            const unsigned long long one = (d[u] >= 0.f) ? (1ull << ((b % PER) * BITS)) : 0ull;
-            const int r = b / PER;
-            h0 += (r == 0) ? one : 0ull;
-            h1 += (r == 1) ? one : 0ull;
-            if (NREG > 2) {
-                h2 += (r == 2) ? one : 0ull;
-                h3 += (r == 3) ? one : 0ull;
-            }
+            for (int u = 0; u < 32; ++u) count(d[u], d[u] >= 0.f);
         }
     }
     // smallest bucket edge with at least k entries at or below it
@@ -188,15 +197,23 @@ __device__ __forceinline__ void sc_compact_lanes(uint64_t* wbuf, int& cnt, float
         if (!found && cum >= k) { found = true; pd = edge; }
     }
     if (act && pdh < inf && my_hthr) atomicMin(my_hthr, __float_as_uint(pdh));
-    const float flim = fminf(lim, pd + band2);
-    int w = 0;
-    for (int i0 = 0; i0 < nmax; i0 += 16) {
-        uint64_t key[16];
+    float flim = fminf(lim, pd + band2);
+    if (xchg) {
+        // a lane that did not count this round still knows the bound it published earlier (or none)
+        const float mine_h = act ? pdh : (my_hthr ? __uint_as_float(__ldcg(my_hthr)) : inf);
+        xchg[lane] = mine_h;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        const float both = fmaxf(mine_h, xchg_partner[lane]);
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        flim = fminf(flim, both + band2);
+    }
+    for (int i0 = 0; i0 < nmax; i0 += FB) {
+        uint64_t key[FB];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) key[u] = (i0 + u < n) ? __ldcg(mine + (i0 + u) * 32) : kEmptyKey;
+        for (int u = 0; u < FB; ++u) key[u] = (i0 + u < n) ? __ldcg(mine + (i0 + u) * 32) : kEmptyKey;
         batch_fence(key);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
+        for (int u = 0; u < FB; ++u) {
             if (i0 + u < n && key_dist(key[u]) < flim) {
                 __stcg(wbuf + w * 32 + lane, key[u]);
                 ++w;
@@ -208,6 +225,8 @@ __device__ __forceinline__ void sc_compact_lanes(uint64_t* wbuf, int& cnt, float
         lim = flim;
         if (pd < inf && my_gthr) atomicMin(my_gthr, __float_as_uint(pd));
     }
+    // a list that is still short of room for one tile of admissions: one exact warp-wide sort (also the only place
+    // that can declare a band overflow)
     unsigned need = __ballot_sync(kFull, cnt > CAP - TC_BN / 2);
     while (need) {
         const int L = __ffs(need) - 1;
@@ -241,6 +260,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     uint64_t* qfull = tempty + 2;                       // leader: resident query tiles of both CTAs landed
     uint64_t* qempty = qfull + 1;                       // each CTA: the item's last MMA retired, tile may be replaced
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qempty + 1);
+    float* xchg_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + SC_BAR_BYTES);      // [TC_EPI_WARPS][32]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -355,9 +375,9 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                 if (p.q_resident) tc_commit_pair(qempty, 0x3);
             }
             if (p.dbg) {
-                p.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
-                p.dbg[blockIdx.x * 8 + 1] = w_full;
-                p.dbg[blockIdx.x * 8 + 2] = w_tempty;
+                p.dbg[blockIdx.x * 16 + 0] = clock64() - t_begin;
+                p.dbg[blockIdx.x * 16 + 1] = w_full;
+                p.dbg[blockIdx.x * 16 + 2] = w_tempty;
             }
         }
     } else {
@@ -371,7 +391,9 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         int acc = 0;
         uint32_t acc_phase = 0;
         long long w_tfull = 0, t_compact = 0, n_compact = 0, e_begin = p.dbg ? clock64() : 0;
-        long long n_hits = 0;
+        long long n_hits = 0, t_scan = 0, n_tiles = 0, t_compact1 = 0;
+        const bool f_pred_on = (p.flags & 1) == 0;      // AGP_SCREEN_FLAGS bit 0 selects the branchy scan (A/B switch)
+        const bool f_xchg = (p.flags & 4) == 0;         // bit 2 turns the pair exchange of the rounds off (A/B switch)
         uint32_t tempty_leader[2];
         tempty_leader[0] = mapa_u32(smem_u32(&tempty[0]), 0);
         tempty_leader[1] = mapa_u32(smem_u32(&tempty[1]), 0);
@@ -401,11 +423,13 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             const size_t slot = sc_list_base(p, q < p.nq ? q : 0) + it.split * 2 + half;
             uint64_t* wbuf = p.partial + (sc_list_base(p, (qt * TC_BM + g * 32) >> 5, 8) + it.split * 2 + half) * (32 * CAP);
             int cnt = 0;
+            const bool f_pred = f_pred_on && ((reinterpret_cast<unsigned long long>(wbuf) >> 32) ==
+                                              ((reinterpret_cast<unsigned long long>(wbuf + 32 * CAP) - 1) >> 32));
             // Compactions stall the pair's whole pipeline (the accumulator cannot be handed back), so they run on a
             // FIXED geometric schedule of tile indices: all 16 epilogue warps of the pair compact during the same tile
             // and the stalls overlap instead of adding up; between two of them a list grows by only ~k ln(mul) entries.
             // Later rounds are staggered by cluster so that the 74 pairs do not all hit L2 with their lists at once.
-            int next_sched = 1, round = 0;
+            int next_sched = 1, sched_base = 1, round = 0;
             for (int t = it.t0; t < it.t1; ++t) {
                 if (my_gthr) {
                     float grp_bound = 0.f;
@@ -419,14 +443,6 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                 mbar_wait(&tfull[acc], acc_phase);
                 if (p.dbg) w_tfull += clock64() - c2;
                 tc_fence_after();
-                if (p.debug_skip_epilogue) {      // ceiling probe: TMA + MMA pipeline only (results are not produced)
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1;
-                    continue;
-                }
                 const uint32_t tcol = tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * TC_BN + half * (TC_BN / 2);
                 const int colbase = t * TC_BN + half * (TC_BN / 2);
                 uint32_t ra[32], rb[32];
@@ -467,37 +483,93 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                         }
                     }
                 };
+                // Branch-light variant of the same scan: a hit is rare per LANE but common per WARP (several of the 32 x 32
+                // values of a chunk pass early in a sweep), so the nested descent above runs its divergent branch chain on
+                // nearly every chunk.  Here one branch per 8-column group guards eight PREDICATED appends (compare, store,
+                // pointer bump under one predicate): the cost of a group no longer depends on how many lanes hit in it.
+                // append pointer as (constant high word, running low word): one predicated 32-bit add per append.  A bundle
+                // that straddles a 4 GB line of the address space (the low word would wrap) takes the branchy scan instead.
+                const unsigned long long wbase = reinterpret_cast<unsigned long long>(wbuf + lane);
+                const uint32_t wp_hi = static_cast<uint32_t>(wbase >> 32);
+                uint32_t wp_lo = static_cast<uint32_t>(wbase) + static_cast<uint32_t>(cnt) * 256u;
+                auto scan_pred = [&](const uint32_t (&r)[32], int col0) {
+                    float n8[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float a = fmaxf(fmaxf(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])), __uint_as_float(r[8 * j + 2]));
+                        const float b = fmaxf(fmaxf(__uint_as_float(r[8 * j + 3]), __uint_as_float(r[8 * j + 4])), __uint_as_float(r[8 * j + 5]));
+                        const float c = fmaxf(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+                        n8[j] = fmaxf(fmaxf(a, b), c);
+                    }
+                    const float m = fmaxf(fmaxf(fmaxf(n8[0], n8[1]), n8[2]), n8[3]);
+                    if (m > thr) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (n8[j] > thr) {
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) {
+                                    const float v = __uint_as_float(r[8 * j + c]);
+                                    const uint32_t db = __float_as_uint(fmaxf(fmaf(v, Wq, qn), 0.f));
+                                    const uint32_t col = static_cast<uint32_t>(col0 + 8 * j + c);
+                                    asm volatile(
+                                        "{\n"
+                                        ".reg .pred p;\n"
+                                        ".reg .b64 a;\n"
+                                        "setp.gt.f32 p, %1, %2;\n"
+                                        "mov.b64 a, {%0, %5};\n"
+                                        "@p st.global.cg.v2.b32 [a], {%3, %4};\n"
+                                        "@p add.u32 %0, %0, 256;\n"
+                                        "}\n"
+                                        : "+r"(wp_lo)
+                                        : "f"(v), "f"(thr), "r"(col), "r"(db), "r"(wp_hi)
+                                        : "memory");
+                                }
+                            }
+                        }
+                    }
+                };
+                long long c4 = p.dbg ? clock64() : 0;
+                const int cnt_before = cnt;
                 // software pipeline over the 4 chunks: the next tcgen05.ld is in flight while this chunk is scanned
                 tmem_ld32(tcol, ra);
                 tmem_ld_wait();
                 tmem_ld32(tcol + 32, rb);
-                scan(ra, colbase);
+                if (f_pred) scan_pred(ra, colbase); else scan(ra, colbase);
                 tmem_ld_wait();
                 tmem_ld32(tcol + 64, ra);
-                scan(rb, colbase + 32);
+                if (f_pred) scan_pred(rb, colbase + 32); else scan(rb, colbase + 32);
                 tmem_ld_wait();
                 tmem_ld32(tcol + 96, rb);
-                scan(ra, colbase + 64);
+                if (f_pred) scan_pred(ra, colbase + 64); else scan(ra, colbase + 64);
                 tmem_ld_wait();
                 // all TMEM reads of this accumulator have landed in registers: hand it back before the last scan
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
-                scan(rb, colbase + 96);
+                if (f_pred) scan_pred(rb, colbase + 96); else scan(rb, colbase + 96);
+                if (f_pred) cnt = static_cast<int>((wp_lo - static_cast<uint32_t>(wbase)) >> 8);
+                if (p.dbg) { t_scan += clock64() - c4; n_tiles += 1; n_hits += cnt - cnt_before; }
                 // Compaction happens only here, between tiles, where nothing but the list state is live.  A tile appends
                 // at most 128 entries to a list, so "room for 128" at every tile start rules out overflow inside a tile.
                 bool do_compact = __any_sync(kFull, cnt > CAP - TC_BN / 2);
+                bool scheduled = false;
                 if (t - it.t0 + 1 == next_sched) {
+                    scheduled = true;
                     ++round;
-                    int base = 1;
-                    for (int r = 0; r < round; ++r) base *= p.sched_mul;
-                    next_sched = base + (round >= 3 ? ((cluster_id & 7) * base * (p.sched_mul - 1)) >> 4 : 0);
-                    do_compact = do_compact || __any_sync(kFull, cnt > p.k + 8);
+                    // rounds after tiles 1, m, m^2, ... with m = sched_mul / 4 (at least one tile apart)
+                    const int nb = max(sched_base + 1, (sched_base * p.sched_mul) >> 2);
+                    const int width = max((nb * p.sched_mul >> 2) - nb, 1);
+                    sched_base = nb;
+                    next_sched = nb + (round >= 3 ? ((cluster_id & 7) * width) >> 4 : 0);
+                    // with the pair exchange both warps of a lane group must enter the round (named barrier inside)
+                    do_compact = do_compact || (f_xchg && !wide) || __any_sync(kFull, cnt > p.k + 8);
                 }
                 if (do_compact) {
                     long long c3 = p.dbg ? clock64() : 0;
-                    sc_compact_lanes<E>(wbuf, cnt, lim, band2, lane, p.k, kh, my_gthr, my_hthr, my_ovf);
-                    if (p.dbg) { t_compact += clock64() - c3; n_compact += 1; }
+                    float* xc = (scheduled && f_xchg && !wide) ? xchg_all + (warp - 2) * 32 : nullptr;
+                    float* xp = xchg_all + ((warp - 2) ^ 4) * 32;
+                    sc_compact_lanes<E>(wbuf, cnt, lim, band2, lane, p.k, kh, my_gthr, my_hthr, my_ovf, xc, xp, 1 + g);
+                    if (p.dbg) { t_compact += clock64() - c3; n_compact += 1; if (t == it.t0) t_compact1 += clock64() - c3; }
                 }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
@@ -505,11 +577,14 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             if (q < p.nq) p.pcount[slot] = cnt;
         }
         if (p.dbg && warp == 2 && lane == 0) {
-            p.dbg[blockIdx.x * 8 + 3] = clock64() - e_begin;
-            p.dbg[blockIdx.x * 8 + 4] = w_tfull;
-            p.dbg[blockIdx.x * 8 + 5] = t_compact;
-            p.dbg[blockIdx.x * 8 + 6] = n_compact;
-            p.dbg[blockIdx.x * 8 + 7] = n_hits;      // lane 0 of warp 2 only (AGP_SCREEN_COUNT_HITS builds)
+            p.dbg[blockIdx.x * 16 + 3] = clock64() - e_begin;
+            p.dbg[blockIdx.x * 16 + 4] = w_tfull;
+            p.dbg[blockIdx.x * 16 + 5] = t_compact;
+            p.dbg[blockIdx.x * 16 + 6] = n_compact;
+            p.dbg[blockIdx.x * 16 + 7] = n_hits;      // lane 0 of warp 2 only (AGP_SCREEN_COUNT_HITS builds)
+            p.dbg[blockIdx.x * 16 + 8] = t_scan;      // tfull wait done -> scans done
+            p.dbg[blockIdx.x * 16 + 9] = n_tiles;
+            p.dbg[blockIdx.x * 16 + 10] = t_compact1; // compactions right after the first tile of an item
         }
     }
     tc_fence_before();

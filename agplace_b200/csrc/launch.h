@@ -15,6 +15,8 @@ constexpr int TC_KPAD = 64;           // descriptor dimension is zero-padded to 
 constexpr int KIND_TF32 = 0;          // operand planes hold TF32 values in fp32 containers ("3xTF32")
 constexpr int KIND_F16 = 1;           // operand planes hold fp16 of the power-of-two scaled row ("3xFP16")
 constexpr int kMaxSmallNq = 20;       // faiss distance_compute_blas_threshold
+constexpr int SC_BAR_BYTES = 512;     // screen kernel shared memory tail: mbarriers + TMEM slot ...
+constexpr int SC_XCHG_BYTES = 1024;   // ... then [8 epilogue warps][32 lanes] fp32: bound exchange between the two column halves
 
 struct TcParams {
     int kind;               // KIND_TF32 or KIND_F16
@@ -54,7 +56,8 @@ struct ScreenParams {
     int q_resident;         // 1: the CTA's query tile stays in shared memory for a whole item (d_pad <= 512)
     int n_stages;           // depth of the operand ring
     int debug_skip_epilogue;// development probe: epilogue hands every accumulator straight back
-    int sched_mul;          // scheduled compactions after tiles 1, mul, mul^2, ... of an item
+    int sched_mul;          // scheduled compactions after tiles 1, m, m^2, ... of an item, m = sched_mul / 4 (8 = doubling)
+    int flags;              // A/B switches (AGP_SCREEN_FLAGS): bit 0 = branchy scan instead of the predicated one, bit 2 = no pair exchange in the rounds
     const float* qn;        // [nq] |q|^2
     const float* sq;        // [nq] query row scale 2^eq
     const float* dq;        // [nq] |q - fp16 plane| (rounded up)
@@ -111,6 +114,11 @@ cudaError_t launch_merge_keys(const uint64_t* partial, int64_t nq, int n_lists, 
 template <int E>
 cudaError_t launch_merge_lists(const float* Din, int64_t d_stride, const int64_t* Iin, int64_t i_stride, bool by_id, int64_t nq,
                                int n_lists, int k, float* D, int64_t* I, cudaStream_t st);
+
+// top-k of each query's own candidate list (positions), exact fp32 difference form (merge.cuh:subset_topk_kernel)
+template <int E>
+cudaError_t launch_subset_topk(const float* xq, const float* xb, int d, const int64_t* off, const int64_t* cand_ids, int64_t ntotal,
+                               int64_t nq, int k, uint64_t* scratch, float* D, int64_t* I, cudaStream_t st);
 
 template <int E>
 cudaError_t launch_rerank(const float* xq, const float* xb, int d, const int64_t* Icand, int kc, int64_t nq, int k, int64_t id_base,

@@ -110,6 +110,77 @@ cudaError_t launch_merge_lists(const float* Din, int64_t d_stride, const int64_t
     return cudaGetLastError();
 }
 
+// N2 (compute_triplets_full, batched): top-k of each query's OWN candidate list.  The index holds the database rows
+// once; list q = cand_ids[off[q] .. off[q+1]) are row positions in the index -- the reference builds a fresh
+// IndexFlatL2 over cache[neg_indexes] per query (datasets/datasets_ws_kitti360.py:985-993, called from :1041).
+// One block per query: its warps evaluate the exact fp32 difference form (same per-lane summation order as
+// diff_small_kernel, so distances are bit-identical to a one-query search over the gathered rows) into a key scratch
+// (distance, position in the list); warp 0 then selects the k smallest by (distance, position) -- the order a
+// fresh index over the list returns -- and emits POSITIONS, padded (FLT_MAX, -1) like faiss.
+template <int E>
+__global__ void __launch_bounds__(256) subset_topk_kernel(const float* __restrict__ xq, const float* __restrict__ xb, int d,
+                                                          const int64_t* __restrict__ off, const int64_t* __restrict__ cand_ids,
+                                                          int64_t ntotal, int k, uint64_t* __restrict__ scratch,
+                                                          float* __restrict__ D, int64_t* __restrict__ I) {
+    extern __shared__ float sqrow[];   // [d]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int64_t q = blockIdx.x;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) sqrow[c] = xq[q * d + c];
+    __syncthreads();
+    const int64_t e0 = off[q], e1 = off[q + 1];
+    const bool vec = ((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15) == 0);
+    for (int64_t e = e0 + warp; e < e1; e += warps) {
+        const int64_t id = cand_ids[e];
+        uint64_t key = kEmptyKey;                      // ids outside the index are skipped, never dereferenced
+        if (id >= 0 && id < ntotal) {
+            const float* row = xb + id * d;
+            float acc = 0.f;
+            if (vec) {
+                for (int c = lane; c < (d >> 2); c += 32) {
+                    const float4 a = reinterpret_cast<const float4*>(sqrow)[c];
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(row) + c);
+                    float t;
+                    t = a.x - b.x; acc = fmaf(t, t, acc);
+                    t = a.y - b.y; acc = fmaf(t, t, acc);
+                    t = a.z - b.z; acc = fmaf(t, t, acc);
+                    t = a.w - b.w; acc = fmaf(t, t, acc);
+                }
+            } else {
+                for (int c = lane; c < d; c += 32) {
+                    const float t = sqrow[c] - __ldg(row + c);
+                    acc = fmaf(t, t, acc);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+            key = pack_key(acc, static_cast<uint32_t>(e - e0));
+        }
+        if (lane == 0) scratch[e] = key;
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    uint64_t key[E];
+    warp_select_stream<E>(key, lane, k, e1 - e0, [&](int64_t i) { return scratch[e0 + i]; });
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+        const int i = j * 32 + lane;
+        if (i < k) {
+            const bool empty = key[j] == kEmptyKey;
+            D[q * k + i] = empty ? kFltMax : key_dist(key[j]);
+            I[q * k + i] = empty ? -1 : static_cast<int64_t>(key_idx(key[j]));
+        }
+    }
+}
+
+template <int E>
+cudaError_t launch_subset_topk(const float* xq, const float* xb, int d, const int64_t* off, const int64_t* cand_ids, int64_t ntotal,
+                               int64_t nq, int k, uint64_t* scratch, float* D, int64_t* I, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    subset_topk_kernel<E><<<static_cast<unsigned>(nq), 256, static_cast<size_t>(d) * sizeof(float), st>>>(xq, xb, d, off, cand_ids, ntotal,
+                                                                                                       k, scratch, D, I);
+    return cudaGetLastError();
+}
+
 // Ragged variant for the fused kernel's output: list (q, l) holds pcount[q*L+l] unsorted keys.  Lists are
 // stored in bundles of 32 consecutive queries, interleaved: entry e of list l of query q sits at
 // ((q/32) * L + l) * 32 * slot_stride + e * 32 + (q % 32)   (slot_stride = slots per list).  One warp per query: the counts are scanned into a shared prefix array, then the

@@ -187,6 +187,29 @@ class IndexFlatL2:
                    "agp_index_search_masked")
         return D, I
 
+    def search_subset(self, x, k, candidates):
+        """Batched search over per-query candidate subsets (``compute_triplets_full``).
+        ``candidates[q]`` = row ids of THIS index that query q may return -- the reference builds a fresh
+        ``IndexFlatL2`` over ``cache[neg_indexes]`` per query (datasets/datasets_ws_kitti360.py:985-993 called from
+        :1041).  Returns numpy ``(D fp32 [nq,k], I int64 [nq,k])`` where ``I`` holds POSITIONS inside
+        ``candidates[q]`` (exactly what the fresh index returns), ties by position, padded ``(3.4028235e38, -1)``."""
+        n, d = x.shape
+        assert d == self.d
+        assert k > 0
+        assert len(candidates) == n
+        if _is_torch(x):
+            x = x.detach().cpu().numpy()
+        x = np.ascontiguousarray(x, dtype="float32")
+        offsets, ids = positives_to_csr(candidates)
+        D = np.empty((n, int(k)), dtype=np.float32)
+        I = np.empty((n, int(k)), dtype=np.int64)
+        self._use_own_stream()
+        _lib.check(self._lib.agp_index_search_subset(self._h, n, ctypes.c_void_p(x.ctypes.data), _lib.MEM_HOST, int(k),
+                                                     ctypes.c_void_p(offsets.ctypes.data), ctypes.c_void_p(ids.ctypes.data),
+                                                     ctypes.c_void_p(D.ctypes.data), ctypes.c_void_p(I.ctypes.data), _lib.MEM_HOST),
+                   "agp_index_search_subset")
+        return D, I
+
     # ------------------------------------------------------------------ instrumentation (bench.py)
     def set_profiling(self, enable: bool):
         _lib.check(self._lib.agp_index_set_profiling(self._h, int(bool(enable))), "agp_index_set_profiling")

@@ -154,9 +154,44 @@ class TripletMiner:
             soft = np.asarray(self.soft_positives_per_query[q]).reshape(-1)
             exclude.append(np.flatnonzero(np.isin(sample, soft)).astype(np.int64))
         _, I = index.search_masked(query_features, self.negs_num_per_query, exclude)
-        # (I == -1, fewer than negs_num_per_query candidates, wraps to the last element exactly like the reference's
-        # numpy indexing of neg_samples[neg_nums])
         negs = sample[I].astype(np.int32)
+        # I == -1 (fewer than negs_num_per_query candidates): the reference's numpy indexing neg_samples[neg_nums] wraps
+        # to the LAST element of that query's own subset, i.e. the last sampled row that is not excluded
+        short = np.flatnonzero((I < 0).any(axis=1))
+        for r in short:
+            keep = np.ones(len(sample), dtype=bool)
+            keep[exclude[r]] = False
+            subset = sample[keep]
+            if len(subset) == 0:
+                raise IndexError("index -1 is out of bounds for axis 0 with size 0")      # what the reference raises
+            negs[r, I[r] < 0] = subset[-1]
+        self.triplets_global_indexes = np.concatenate(
+            [sampled_queries_indexes.reshape(-1, 1).astype(np.int64), best_pos.reshape(-1, 1), negs.astype(np.int64)], axis=1)
+        return self.triplets_global_indexes
+
+    def compute_triplets_full_batched(self, cache, cache_refresh_rate):
+        """Same result as :meth:`compute_triplets_full` (kitti360:1022-1049), including the ``neg_cache`` it leaves
+        behind.  The global ``np.random`` stream is consumed in the reference's order (the query draw, then one
+        database draw per query inside the loop -- neither search consumes random numbers), the whole database is
+        indexed ONCE, and every query's own sorted-unique candidate set (``np.unique(concatenate([neg_cache[q],
+        setdiff1d(draw, soft_positives)]))``) goes through one ``IndexFlatL2.search_subset`` call: exact fp32
+        difference form, ties by position in the sorted set = by database id, like a fresh index over the set."""
+        sampled_queries_indexes = np.random.choice(self.queries_num, cache_refresh_rate, replace=False)
+        candidates = []
+        for query_index in sampled_queries_indexes:
+            neg_indexes = np.random.choice(self.database_num, self.neg_samples_num, replace=False)
+            soft_positives = self.soft_positives_per_query[query_index]
+            neg_indexes = np.setdiff1d(neg_indexes, soft_positives, assume_unique=True)
+            candidates.append(np.unique(np.concatenate([self.neg_cache[query_index], neg_indexes])))
+        query_features = np.stack([self.get_query_features(q, cache) for q in sampled_queries_indexes]).astype(np.float32)
+        best_pos = self._best_positives_batched(sampled_queries_indexes, cache, query_features)
+        index = self.index_cls(self.features_dim)
+        index.add(np.asarray(cache[np.arange(self.database_num)], dtype=np.float32))
+        _, I = index.search_subset(query_features, self.negs_num_per_query, candidates)
+        negs = np.empty((len(sampled_queries_indexes), self.negs_num_per_query), dtype=np.int32)
+        for r, (query_index, cand) in enumerate(zip(sampled_queries_indexes, candidates)):
+            negs[r] = cand[I[r]].astype(np.int32)        # -1 wraps to the last candidate, as in the reference
+            self.neg_cache[query_index] = negs[r].copy()
         self.triplets_global_indexes = np.concatenate(
             [sampled_queries_indexes.reshape(-1, 1).astype(np.int64), best_pos.reshape(-1, 1), negs.astype(np.int64)], axis=1)
         return self.triplets_global_indexes

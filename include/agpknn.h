@@ -113,6 +113,19 @@ AGP_API int agp_index_search_masked(agp_index* idx, int64_t nq, const float* x, 
                                     const int64_t* excl_offsets, const int64_t* excl_ids, float* D, int64_t* I,
                                     int out_mem_kind);
 
+/* Batched search over per-query candidate subsets (the compute_triplets_full driver): what the
+ * reference does per query with
+ *   faiss.IndexFlatL2(d).add(cache[neg_indexes]).search(q, k)
+ * (get_hardest_negatives_indexes, datasets/datasets_ws_kitti360.py:985-993, called from :1041 with a different,
+ * sorted-unique neg_indexes per query; copies in datasets_ws_nuscenes.py:1250-1258, datasets_ws.py:698-706).
+ * The index holds the database rows once; query q's candidates are the rows cand_ids[cand_offsets[q] ..
+ * cand_offsets[q+1]) of this index (HOST arrays, ids in [0, ntotal)).  Returns, per query, the k nearest of ITS list in
+ * the exact fp32 difference form, ascending, ties by list position, as POSITIONS inside the list (what a fresh index
+ * over the gathered rows returns), padded (3.4028235e38, -1). */
+AGP_API int agp_index_search_subset(agp_index* idx, int64_t nq, const float* x, int x_mem_kind, int k,
+                                    const int64_t* cand_offsets, const int64_t* cand_ids, float* D, int64_t* I,
+                                    int out_mem_kind);
+
 /* Nearest row of each query's own candidate list (N2; the reference's get_best_positive_index,
  * datasets/datasets_ws_kitti360.py:976-983, for all queries at once).  xq: nq x d; rows: the gathered
  * candidate features, list q = rows [offsets[q], offsets[q+1]); all HOST arrays.  best_pos[q] = position

@@ -285,6 +285,56 @@ def test_batched_mining_identical_to_the_per_query_loop():
     assert out[0].shape == (300, 12) and out[0].dtype == np.int64
 
 
+def test_full_batched_mining_identical_to_the_per_query_loop():
+    """compute_triplets_full (kitti360:1022-1049) batched through search_subset: same triplets AND the same neg_cache
+    over two consecutive refreshes (the second one feeds on the first one's neg_cache)."""
+    from agplace_b200 import mining
+    p = make_mining_problem(35, database_num=2500, queries_num=300, d=256)
+    p.cache[100:140] = p.cache[200:240]          # exact distance ties among the negatives
+    out, caches = [], []
+    for batched in (False, True):
+        miner = mining.TripletMiner(p.d, p.database_num, p.queries_num, p.hard, p.soft, negs_num_per_query=10,
+                                    neg_samples_num=600)
+        np.random.seed(5)
+        f = miner.compute_triplets_full_batched if batched else miner.compute_triplets_full
+        out.append([f(p.cache, 200).copy(), f(p.cache, 200).copy()])
+        caches.append(miner.neg_cache)
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    for a, b in zip(caches[0], caches[1]):
+        np.testing.assert_array_equal(a, b)
+    assert out[0][0].shape == (200, 12) and out[0][0].dtype == np.int64
+
+
+def test_search_subset_equals_a_fresh_index_over_each_list():
+    import agplace_b200
+    rng = np.random.default_rng(19)
+    xb = rng.standard_normal((900, 48)).astype(np.float32)
+    xb[300:330] = xb[10:40]                      # duplicates: ties resolve by position in the list
+    xq = rng.standard_normal((70, 48)).astype(np.float32)
+    cands = [np.sort(rng.choice(900, size=rng.integers(0, 400), replace=False)).astype(np.int64) for _ in range(70)]
+    cands[3] = np.array([], dtype=np.int64)      # empty list: all padding
+    cands[4] = np.array([7, 7, 310, 20], dtype=np.int64)   # repeated ids and fewer than k candidates
+    ix = agplace_b200.IndexFlatL2(48); ix.add(xb)
+    for k in (1, 10, 70):
+        D, I = ix.search_subset(xq, k, cands)
+        assert D.shape == (70, k) and I.dtype == np.int64
+        for q in range(70):
+            Dr, Ir = orc.knn_fp32(xq[q:q + 1], xb[cands[q]].reshape(-1, 48), k) if len(cands[q]) else (
+                np.full((1, k), np.float32(3.4028234663852886e38)), np.full((1, k), -1, dtype=np.int64))
+            ok, msg = orc.compare_knn(D[q:q + 1], I[q:q + 1], Dr, Ir)
+            assert ok, f"k={k} query {q}: {msg}"
+    # bit-identical to the engine's own one-query search over the gathered rows (the reference call pattern)
+    D, I = ix.search_subset(xq[:8], 10, cands[8:16])
+    for q in range(8):
+        one = agplace_b200.IndexFlatL2(48); one.add(xb[cands[8 + q]])
+        D1, I1 = one.search(xq[q:q + 1], 10)
+        np.testing.assert_array_equal(I[q], I1[0])
+        np.testing.assert_array_equal(D[q], D1[0])
+    with pytest.raises(RuntimeError):            # ids must be rows of the index
+        ix.search_subset(xq[:1], 5, [np.array([900], dtype=np.int64)])
+
+
 def test_search_masked_equals_search_on_the_surviving_rows():
     import agplace_b200
     rng = np.random.default_rng(17)
