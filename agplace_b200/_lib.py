@@ -19,6 +19,8 @@ MAX_K = 512
 # every symbol include/agpknn.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "agp_index_create": (c_int, [c_int, c_int, c_int, POINTER(c_void_p)]),
+    "agp_index_create_metric": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "agp_index_metric": (c_int, [c_void_p]),
     "agp_index_free": (None, [c_void_p]),
     "agp_index_add": (c_int, [c_void_p, c_int64, c_void_p, c_int]),
     "agp_index_search": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int]),

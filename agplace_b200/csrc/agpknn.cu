@@ -149,6 +149,7 @@ struct Buf {
 
 struct agp_index {
     int d = 0, d_pad = 0, device = 0, mode = 0, num_sms = 0;
+    int ip = 0;                   // 1: inner-product index (faiss.IndexFlatIP); 0: squared L2
     int64_t ntotal = 0, cap = 0, id_base = 0;
     float *xb = nullptr, *yn = nullptr, *wx = nullptr;
     uint8_t *xb_hi = nullptr, *xb_lo = nullptr;
@@ -303,7 +304,7 @@ static int ensure_screen_plane(agp_index* ix) {
             ix->scale_set = true;
         }
         LAUNCH(launch_prep_rows_screen(src, n, ix->d, ix->d_pad, ix->xs + static_cast<size_t>(ix->xs_rows) * row, nullptr, nullptr, nullptr,
-                                       ix->dbstats, 1, ix->num_sms * 32, ix->stream));
+                                       ix->dbstats, ix->ip ? 2 : 1, ix->num_sms * 32, ix->stream));
         ix->xs_rows = ix->ntotal;
     }
     return 0;
@@ -404,16 +405,16 @@ static int choose_splits(int n_qtiles, int n_dbtiles, int num_sms) {
 
 static int search_empty(agp_index* ix, int64_t nq, int k, float* D, int64_t* I) {
     // no database rows: emit padding through the merge kernel with zero lists
-    return DISPATCH_E32(k, launch_merge_keys, static_cast<const uint64_t*>(nullptr), nq, 0, k, ix->id_base, D, I, ix->stream);
+    return DISPATCH_E32(k, launch_merge_keys, static_cast<const uint64_t*>(nullptr), nq, 0, k, ix->id_base, D, I, ix->ip, ix->stream);
 }
 
 static int select_and_merge(agp_index* ix, const float* panel, int64_t ld, int nqp, int k, float* D, int64_t* I) {
     const int64_t n = ix->ntotal;
     int n_chunks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 2047) / 2048, (ix->num_sms * 16 + nqp - 1) / nqp)));
     CKR(ensure(ix->partial, static_cast<size_t>(nqp) * n_chunks * k * sizeof(uint64_t)));
-    CKR(DISPATCH_E32(k, launch_select_rows, panel, ld, n, k, nqp, n_chunks, static_cast<uint64_t*>(ix->partial.p), ix->stream));
+    CKR(DISPATCH_E32(k, launch_select_rows, panel, ld, n, k, nqp, n_chunks, static_cast<uint64_t*>(ix->partial.p), ix->ip, ix->stream));
     CKR(DISPATCH_E32(k, launch_merge_keys, static_cast<const uint64_t*>(ix->partial.p), static_cast<int64_t>(nqp), n_chunks, k,
-                     ix->id_base, D, I, ix->stream));
+                     ix->id_base, D, I, ix->ip, ix->stream));
     return 0;
 }
 
@@ -425,7 +426,7 @@ static int search_diff(agp_index* ix, const float* xq_dev, int64_t nq, int k, fl
     for (int64_t q0 = 0; q0 < nq; q0 += max_group) {
         const int g = static_cast<int>(std::min<int64_t>(max_group, nq - q0));
         ProfScope prof(ix);
-        LAUNCH(launch_diff_small(xq_dev + q0 * ix->d, g, ix->xb, n, ix->d, static_cast<float*>(ix->panel.p), ld, ix->num_sms, ix->stream));
+        LAUNCH(launch_diff_small(xq_dev + q0 * ix->d, g, ix->xb, n, ix->d, static_cast<float*>(ix->panel.p), ld, ix->num_sms, ix->ip, ix->stream));
         prof.stop();
         CKR(select_and_merge(ix, static_cast<const float*>(ix->panel.p), ld, g, k, D + q0 * k, I + q0 * k));
     }
@@ -443,7 +444,7 @@ static int search_simt(agp_index* ix, const float* xq_dev, int64_t nq, int k, fl
         const int rows = static_cast<int>(std::min<int64_t>(max_rows, nq - q0));
         ProfScope prof(ix);
         LAUNCH(launch_dist_simt(xq_dev + q0 * ix->d, static_cast<const float*>(ix->qn.p) + q0, rows, ix->xb, ix->yn, n, ix->d,
-                                static_cast<float*>(ix->panel.p), ld, ix->stream));
+                                static_cast<float*>(ix->panel.p), ld, ix->ip, ix->stream));
         prof.stop();
         CKR(select_and_merge(ix, static_cast<const float*>(ix->panel.p), ld, rows, k, D + q0 * k, I + q0 * k));
     }
@@ -658,6 +659,7 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         p.n_stages = n_stages;
         p.sched_mul = 8;
         p.flags = 0;
+        p.ip = ix->ip;
         { const char* e = getenv("AGP_SCREEN_SKIP_EPI"); p.debug_skip_epilogue = (e && atoi(e) != 0) ? 1 : 0; }
         { const char* e = getenv("AGP_SCREEN_SCHED"); if (e && atoi(e) >= 5) p.sched_mul = atoi(e); }     // quarters: 8 = x2, 6 = x1.5
         { const char* e = getenv("AGP_SCREEN_FLAGS"); if (e) p.flags = atoi(e); }
@@ -699,7 +701,7 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         CKR(DISPATCH_EV(E, launch_screen_finalize, static_cast<const uint64_t*>(ix->partial.p), static_cast<const int*>(ix->cand.p), slots,
                         static_cast<int64_t>(nqc), p.n_full_items, p.rem_splits, k, xq_dev + q0 * ix->d, ix->xb, ix->d, ix->d_pad,
                         static_cast<const float*>(ix->qn.p), static_cast<const float*>(ix->dq.p), ix->dbstats,
-                        static_cast<const int*>(ix->ovf.p), ovf_count, ovf_list, ix->id_base, D + q0 * k, I + q0 * k, ix->stream));
+                        static_cast<const int*>(ix->ovf.p), ovf_count, ovf_list, ix->id_base, D + q0 * k, I + q0 * k, ix->ip, ix->stream));
         CK(cudaMemcpyAsync(ix->h_count, ovf_count, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
         if (dbg) {
             std::vector<long long> h(static_cast<size_t>(grid) * 16);
@@ -772,10 +774,19 @@ int agp_device_count(void) {
 }
 
 int agp_index_create(int d, int device, int precision_mode, agp_index** out) {
+    return agp_index_create_metric(d, device, precision_mode, AGP_METRIC_L2, out);
+}
+
+int agp_index_metric(const agp_index* ix) { return ix && ix->ip ? AGP_METRIC_INNER_PRODUCT : AGP_METRIC_L2; }
+
+int agp_index_create_metric(int d, int device, int precision_mode, int metric, agp_index** out) {
     if (!out) return set_err(AGP_EINVAL, "out is null");
     *out = nullptr;
     if (d <= 0) return set_err(AGP_EINVAL, "d must be positive, got %d", d);
     if (precision_mode < 0 || precision_mode > 5) return set_err(AGP_EINVAL, "unknown precision_mode %d", precision_mode);
+    if (metric != AGP_METRIC_L2 && metric != AGP_METRIC_INNER_PRODUCT) return set_err(AGP_EINVAL, "unknown metric %d", metric);
+    if (metric == AGP_METRIC_INNER_PRODUCT && (precision_mode == AGP_PRECISION_3XTF32 || precision_mode == AGP_PRECISION_3XFP16))
+        return set_err(AGP_EINVAL, "inner-product indexes support precision auto, fp16_screen, fp32_simt and exact_diff");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -801,6 +812,7 @@ int agp_index_create(int d, int device, int precision_mode, agp_index** out) {
     ix->d_pad = static_cast<int>(round_up(d, TC_KPAD));
     ix->device = device;
     ix->mode = precision_mode;
+    ix->ip = metric == AGP_METRIC_INNER_PRODUCT ? 1 : 0;
     ix->num_sms = sms;
     ix->planes = (precision_mode == AGP_PRECISION_3XTF32 || precision_mode == AGP_PRECISION_3XFP16);
     ix->screen = (precision_mode == AGP_PRECISION_AUTO || precision_mode == AGP_PRECISION_FP16_SCREEN);
@@ -1006,6 +1018,7 @@ int agp_index_search_masked(agp_index* ix, int64_t nq, const float* x, int x_mem
     if (k <= 0) return set_err(AGP_EINVAL, "k must be positive, got %d", k);
     if (nq == 0) return 0;
     if (!x || !D || !I || !excl_offsets) return set_err(AGP_EINVAL, "x, D, I and excl_offsets must be non-null");
+    if (ix->ip) return set_err(AGP_EINVAL, "search_masked is defined for L2 indexes only");
     int64_t max_ex = 0;
     for (int64_t q = 0; q < nq; ++q) {
         const int64_t c = excl_offsets[q + 1] - excl_offsets[q];
@@ -1052,6 +1065,7 @@ int agp_index_search_subset(agp_index* ix, int64_t nq, const float* x, int x_mem
     if (k > AGP_MAX_K) return set_err(AGP_EINVAL, "k=%d exceeds AGP_MAX_K=%d", k, AGP_MAX_K);
     if (nq == 0) return 0;
     if (!x || !D || !I || !cand_offsets) return set_err(AGP_EINVAL, "x, D, I and cand_offsets must be non-null");
+    if (ix->ip) return set_err(AGP_EINVAL, "search_subset is defined for L2 indexes only");
     if (nq > 0x7fffffffLL) return set_err(AGP_EINVAL, "nq too large");
     if (cand_offsets[0] != 0) return set_err(AGP_EINVAL, "cand_offsets[0] must be 0");
     if (static_cast<size_t>(ix->d) * sizeof(float) > 48 * 1024) return set_err(AGP_EINVAL, "search_subset supports d <= 12288");

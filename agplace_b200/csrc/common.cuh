@@ -19,6 +19,18 @@ __device__ __forceinline__ uint64_t pack_key(float dis, uint32_t idx) {
 }
 __device__ __forceinline__ float key_dist(uint64_t k) { return __uint_as_float(static_cast<uint32_t>(k >> 32)); }
 __device__ __forceinline__ uint32_t key_idx(uint64_t k) { return static_cast<uint32_t>(k); }
+// Keys for values of either sign (inner-product search selects the smallest -<q, y>): the usual order-preserving map
+// of fp32 bits (flip all bits of negatives, the sign bit of non-negatives).
+__device__ __forceinline__ uint64_t pack_key_signed(float v, uint32_t idx) {
+    uint32_t u = __float_as_uint(v);
+    u ^= (u & 0x80000000u) ? 0xffffffffu : 0x80000000u;
+    return (static_cast<uint64_t>(u) << 32) | idx;
+}
+__device__ __forceinline__ float key_value_signed(uint64_t k) {
+    uint32_t u = static_cast<uint32_t>(k >> 32);
+    u ^= (u & 0x80000000u) ? 0x80000000u : 0xffffffffu;
+    return __uint_as_float(u);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) prep_rows_screen_kernel(const float* __re
         // aux chunk
         float a0, a1, a2;
         if (is_db) {
-            const float v = -0.5f * acc * inv;
+            const float v = is_db == 2 ? 0.f : -0.5f * acc * inv;      // inner-product planes carry no norm term
             bad = bad || !(fabsf(v) < 65504.f);
             const __half p1 = __float2half_rn(v);
             const float e1 = v - __half2float(p1);
@@ -250,8 +250,9 @@ __global__ void fill_f32_kernel(float* __restrict__ p, int64_t n, float v) {
 }
 
 // dist[q * ld + r] = sum_c (xq[q,c] - xb[r,c])^2
+// ip != 0: dist[q * ld + r] = -<xq[q], xb[r]>  (IndexFlatIP: the smallest negated products are the best matches)
 __global__ void __launch_bounds__(256) diff_small_kernel(const float* __restrict__ xq, int nq, const float* __restrict__ xb,
-                                                         int64_t n, int d, float* __restrict__ dist, int64_t ld) {
+                                                         int64_t n, int d, float* __restrict__ dist, int64_t ld, int ip) {
     extern __shared__ float sq[];   // [nq][d]
     for (int i = threadIdx.x; i < nq * d; i += blockDim.x) sq[i] = xq[i];
     __syncthreads();
@@ -270,11 +271,18 @@ __global__ void __launch_bounds__(256) diff_small_kernel(const float* __restrict
                 for (int q = 0; q < kMaxSmallNq; ++q) {
                     if (q < nq) {
                         const float4 u = reinterpret_cast<const float4*>(sq + q * d)[c];
-                        float t;
-                        t = u.x - v.x; acc[q] = fmaf(t, t, acc[q]);
-                        t = u.y - v.y; acc[q] = fmaf(t, t, acc[q]);
-                        t = u.z - v.z; acc[q] = fmaf(t, t, acc[q]);
-                        t = u.w - v.w; acc[q] = fmaf(t, t, acc[q]);
+                        if (ip) {
+                            acc[q] = fmaf(u.x, v.x, acc[q]);
+                            acc[q] = fmaf(u.y, v.y, acc[q]);
+                            acc[q] = fmaf(u.z, v.z, acc[q]);
+                            acc[q] = fmaf(u.w, v.w, acc[q]);
+                        } else {
+                            float t;
+                            t = u.x - v.x; acc[q] = fmaf(t, t, acc[q]);
+                            t = u.y - v.y; acc[q] = fmaf(t, t, acc[q]);
+                            t = u.z - v.z; acc[q] = fmaf(t, t, acc[q]);
+                            t = u.w - v.w; acc[q] = fmaf(t, t, acc[q]);
+                        }
                     }
                 }
             }
@@ -284,8 +292,8 @@ __global__ void __launch_bounds__(256) diff_small_kernel(const float* __restrict
 #pragma unroll
                 for (int q = 0; q < kMaxSmallNq; ++q) {
                     if (q < nq) {
-                        const float t = sq[q * d + c] - v;
-                        acc[q] = fmaf(t, t, acc[q]);
+                        const float t = ip ? sq[q * d + c] : sq[q * d + c] - v;
+                        acc[q] = fmaf(t, ip ? v : t, acc[q]);
                     }
                 }
             }
@@ -296,7 +304,7 @@ __global__ void __launch_bounds__(256) diff_small_kernel(const float* __restrict
                 float a = acc[q];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFull, a, o);
-                if (lane == 0) dist[q * ld + r] = a;
+                if (lane == 0) dist[q * ld + r] = ip ? -a : a;
             }
         }
     }
@@ -306,7 +314,7 @@ __global__ void __launch_bounds__(256) diff_small_kernel(const float* __restrict
 // dist[i * ld + j] = max(0, (qn[i] + yn[j]) - 2 * <xq_i, xb_j>)
 __global__ void __launch_bounds__(256) dist_simt_kernel(const float* __restrict__ xq, const float* __restrict__ qn, int nq,
                                                         const float* __restrict__ xb, const float* __restrict__ yn, int64_t n,
-                                                        int d, float* __restrict__ dist, int64_t ld) {
+                                                        int d, float* __restrict__ dist, int64_t ld, int ip) {
     constexpr int BM = 64, BN = 64, BK = 16;
     __shared__ float sa[BK][BM + 4];
     __shared__ float sb[BK][BN + 4];
@@ -348,11 +356,15 @@ __global__ void __launch_bounds__(256) dist_simt_kernel(const float* __restrict_
     for (int a = 0; a < 4; ++a) {
         const int qi = i0 + ty * 4 + a;
         if (qi >= nq) continue;
-        const float xn = qn[qi];
+        const float xn = ip ? 0.f : qn[qi];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int64_t bj = j0 + tx * 4 + b;
             if (bj >= n) continue;
+            if (ip) {           // IndexFlatIP: negated inner product, no clamp
+                dist[static_cast<int64_t>(qi) * ld + bj] = -acc[a][b];
+                continue;
+            }
             float dis = fmaf(-2.f, acc[a][b], xn + yn[bj]);
             dist[static_cast<int64_t>(qi) * ld + bj] = dis < 0.f ? 0.f : dis;
         }
@@ -549,19 +561,19 @@ cudaError_t launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st) {
 }
 
 cudaError_t launch_diff_small(const float* xq, int nq, const float* xb, int64_t n, int d, float* dist, int64_t ld, int num_sms,
-                              cudaStream_t st) {
+                              int ip, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(nq) * d * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(diff_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
     const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(num_sms) * 8)));
-    diff_small_kernel<<<blocks, 256, smem, st>>>(xq, nq, xb, n, d, dist, ld);
+    diff_small_kernel<<<blocks, 256, smem, st>>>(xq, nq, xb, n, d, dist, ld, ip);
     return cudaGetLastError();
 }
 
 cudaError_t launch_dist_simt(const float* xq, const float* qn, int nq, const float* xb, const float* yn, int64_t n, int d, float* dist,
-                             int64_t ld, cudaStream_t st) {
+                             int64_t ld, int ip, cudaStream_t st) {
     dim3 grid(static_cast<unsigned>((n + 63) / 64), static_cast<unsigned>((nq + 63) / 64));
-    dist_simt_kernel<<<grid, 256, 0, st>>>(xq, qn, nq, xb, yn, n, d, dist, ld);
+    dist_simt_kernel<<<grid, 256, 0, st>>>(xq, qn, nq, xb, yn, n, d, dist, ld, ip);
     return cudaGetLastError();
 }
 

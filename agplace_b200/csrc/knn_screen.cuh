@@ -404,8 +404,11 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             const float band2 = q < p.nq ? 2.f * screen_band(__ldg(p.qn + q), __ldg(p.dq + q), ymax2, dymax, sy, p.d_pad) : inf;
             // queries with an unbounded band (unrepresentable rows) are answered by the exact fallback: skip them here
             const bool valid = q < p.nq && band2 < inf;
-            const float qn = valid ? __ldg(p.qn + q) : 0.f;
-            const float Wq = valid ? -2.f * __ldg(p.sq + q) * sy : -1.f;      // dis~ = qn + Wq * acc'   (a negative power of two)
+            // L2:  dis~ = |q|^2 - 2 sq sy acc'.   Inner product (the plane's aux chunk is zero, acc' = q.y / (sq sy)):
+            // dis~ = B_q - sq sy acc' with B_q = |q| max|y| (1 + 1e-4) >= any product, so the screened value stays a
+            // non-negative "distance" and everything downstream (keys, bounds, band) is shared with the L2 path.
+            const float qn = !valid ? 0.f : p.ip ? sqrtf(__ldg(p.qn + q)) * sqrtf(ymax2) * 1.0001f : __ldg(p.qn + q);
+            const float Wq = valid ? (p.ip ? -1.f : -2.f) * __ldg(p.sq + q) * sy : -1.f;      // dis~ = qn + Wq * acc'   (a negative power of two)
             const float invW = 1.f / Wq;
             // a row is a candidate iff dis~ < lim = (best known bound of the k-th smallest dis~) + 2 band
             float lim = valid ? inf : -inf;
@@ -615,7 +618,7 @@ __global__ void __launch_bounds__(128) screen_finalize_kernel(const uint64_t* __
                                                               int d_pad, const float* __restrict__ qn, const float* __restrict__ dq,
                                                               const uint32_t* __restrict__ dbstats, const int* __restrict__ ovf_in,
                                                               int* __restrict__ ovf_count, int* __restrict__ ovf_list, int64_t id_base,
-                                                              float* __restrict__ D, int64_t* __restrict__ I) {
+                                                              float* __restrict__ D, int64_t* __restrict__ I, int ip) {
     constexpr int CAP = 32 * E;
     extern __shared__ uint64_t sstage[];   // [warps][CAP] keys | [warps][CAP] float exact distances | [warps][257] prefix
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
@@ -706,11 +709,18 @@ __global__ void __launch_bounds__(128) screen_finalize_kernel(const uint64_t* __
                 for (int u = 0; u < 4; ++u) b[u] = __ldg(reinterpret_cast<const float4*>(row[u]) + c);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    float t;
-                    t = a.x - b[u].x; acc[u] = fmaf(t, t, acc[u]);
-                    t = a.y - b[u].y; acc[u] = fmaf(t, t, acc[u]);
-                    t = a.z - b[u].z; acc[u] = fmaf(t, t, acc[u]);
-                    t = a.w - b[u].w; acc[u] = fmaf(t, t, acc[u]);
+                    if (ip) {            // exact finish of IndexFlatIP: the fp32 inner product itself
+                        acc[u] = fmaf(a.x, b[u].x, acc[u]);
+                        acc[u] = fmaf(a.y, b[u].y, acc[u]);
+                        acc[u] = fmaf(a.z, b[u].z, acc[u]);
+                        acc[u] = fmaf(a.w, b[u].w, acc[u]);
+                    } else {
+                        float t;
+                        t = a.x - b[u].x; acc[u] = fmaf(t, t, acc[u]);
+                        t = a.y - b[u].y; acc[u] = fmaf(t, t, acc[u]);
+                        t = a.z - b[u].z; acc[u] = fmaf(t, t, acc[u]);
+                        t = a.w - b[u].w; acc[u] = fmaf(t, t, acc[u]);
+                    }
                 }
             }
         } else {
@@ -718,8 +728,9 @@ __global__ void __launch_bounds__(128) screen_finalize_kernel(const uint64_t* __
                 const float a = __ldg(qrow + c);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const float t = a - __ldg(row[u] + c);
-                    acc[u] = fmaf(t, t, acc[u]);
+                    const float y = __ldg(row[u] + c);
+                    const float t = ip ? a : a - y;
+                    acc[u] = fmaf(t, ip ? y : t, acc[u]);
                 }
             }
         }
@@ -734,7 +745,8 @@ __global__ void __launch_bounds__(128) screen_finalize_kernel(const uint64_t* __
 #pragma unroll
     for (int j = 0; j < E; ++j) {
         const int i = j * 32 + lane;
-        key[j] = (i < nb) ? pack_key(sd[i], key_idx(buf[i])) : kEmptyKey;
+        // inner product: order by (-<q, y> ascending, id ascending) through the sign-aware key
+        key[j] = (i < nb) ? (ip ? pack_key_signed(-sd[i], key_idx(buf[i])) : pack_key(sd[i], key_idx(buf[i]))) : kEmptyKey;
     }
     warp_bitonic_sort<E>(key, lane);
 #pragma unroll
@@ -742,7 +754,7 @@ __global__ void __launch_bounds__(128) screen_finalize_kernel(const uint64_t* __
         const int i = j * 32 + lane;
         if (i < k) {
             const bool empty = key[j] == kEmptyKey;
-            D[q * k + i] = empty ? kFltMax : key_dist(key[j]);
+            D[q * k + i] = ip ? (empty ? -kFltMax : -key_value_signed(key[j])) : (empty ? kFltMax : key_dist(key[j]));
             I[q * k + i] = empty ? -1 : id_base + static_cast<int64_t>(key_idx(key[j]));
         }
     }
@@ -753,12 +765,12 @@ template <int E>
 cudaError_t launch_screen_finalize(const uint64_t* partial, const int* pcount, int slot_stride, int64_t nq, int n_full_items, int rem_splits, int k,
                                    const float* xq, const float* xb, int d, int d_pad, const float* qn, const float* dq,
                                    const uint32_t* dbstats, const int* ovf_in, int* ovf_count, int* ovf_list, int64_t id_base, float* D,
-                                   int64_t* I, cudaStream_t st) {
+                                   int64_t* I, int ip, cudaStream_t st) {
     constexpr int warps = 4;
     if (2 * rem_splits > kMaxRaggedLists) return cudaErrorInvalidValue;
     const size_t smem = warps * 32 * E * (sizeof(uint64_t) + sizeof(float)) + warps * (kMaxRaggedLists + 1) * sizeof(int);
     screen_finalize_kernel<E><<<static_cast<unsigned>((nq + warps - 1) / warps), warps * 32, smem, st>>>(
-        partial, pcount, slot_stride, nq, n_full_items, rem_splits, k, xq, xb, d, d_pad, qn, dq, dbstats, ovf_in, ovf_count, ovf_list, id_base, D, I);
+        partial, pcount, slot_stride, nq, n_full_items, rem_splits, k, xq, xb, d, d_pad, qn, dq, dbstats, ovf_in, ovf_count, ovf_list, id_base, D, I, ip);
     return cudaGetLastError();
 }
 

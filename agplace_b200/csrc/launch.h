@@ -57,6 +57,7 @@ struct ScreenParams {
     int n_stages;           // depth of the operand ring
     int debug_skip_epilogue;// development probe: epilogue hands every accumulator straight back
     int sched_mul;          // scheduled compactions after tiles 1, m, m^2, ... of an item, m = sched_mul / 4 (8 = doubling)
+    int ip;                 // 1: inner-product index (IndexFlatIP): screened value = B_q - <q, y>, B_q = |q| max|y| (>= any product)
     int flags;              // A/B switches (AGP_SCREEN_FLAGS): bit 0 = branchy scan instead of the predicated one, bit 2 = no pair exchange in the rounds
     const float* qn;        // [nq] |q|^2
     const float* sq;        // [nq] query row scale 2^eq
@@ -101,16 +102,16 @@ template <int E>
 cudaError_t launch_screen_finalize(const uint64_t* partial, const int* pcount, int slot_stride, int64_t nq, int n_full_items, int rem_splits, int k,
                                    const float* xq, const float* xb, int d, int d_pad, const float* qn, const float* dq,
                                    const uint32_t* dbstats, const int* ovf_in, int* ovf_count, int* ovf_list, int64_t id_base, float* D,
-                                   int64_t* I, cudaStream_t st);
+                                   int64_t* I, int ip, cudaStream_t st);
 template <int E>
 cudaError_t launch_select_rows(const float* dist, int64_t ld, int64_t n, int k, int nq, int n_chunks, uint64_t* partial,
-                               cudaStream_t st);
+                               int signed_keys, cudaStream_t st);
 template <int E>
 cudaError_t launch_merge_ragged(const uint64_t* partial, const int* pcount, int slot_stride, int64_t nq, int n_lists, int k,
                                 int64_t id_base, float* D, int64_t* I, cudaStream_t st);
 template <int E>
 cudaError_t launch_merge_keys(const uint64_t* partial, int64_t nq, int n_lists, int k, int64_t id_base, float* D, int64_t* I,
-                              cudaStream_t st);
+                              int ip, cudaStream_t st);
 template <int E>
 cudaError_t launch_merge_lists(const float* Din, int64_t d_stride, const int64_t* Iin, int64_t i_stride, bool by_id, int64_t nq,
                                int n_lists, int k, float* D, int64_t* I, cudaStream_t st);
@@ -145,9 +146,9 @@ cudaError_t launch_gather_rows(const float* x, const int* list, int n, int d, fl
 cudaError_t launch_scatter_results(const float* Dt, const int64_t* It, const int* list, int n, int k, float* D, int64_t* I, cudaStream_t st);
 cudaError_t launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st);
 cudaError_t launch_diff_small(const float* xq, int nq, const float* xb, int64_t n, int d, float* dist, int64_t ld, int num_sms,
-                              cudaStream_t st);
+                              int ip, cudaStream_t st);
 cudaError_t launch_dist_simt(const float* xq, const float* qn, int nq, const float* xb, const float* yn, int64_t n, int d, float* dist,
-                             int64_t ld, cudaStream_t st);
+                             int64_t ld, int ip, cudaStream_t st);
 cudaError_t launch_recall(const int64_t* I, int64_t nq, int k, const int64_t* pos_off, const int64_t* pos_ids, const int* ns, int n_ns,
                           unsigned long long* hits, cudaStream_t st);
 

@@ -41,7 +41,7 @@ __device__ __forceinline__ void warp_select_stream(uint64_t (&key)[E], int lane,
 
 template <int E>
 __global__ void __launch_bounds__(128) merge_keys_kernel(const uint64_t* __restrict__ partial, int64_t nq, int n_lists, int k,
-                                                         int64_t id_base, float* __restrict__ D, int64_t* __restrict__ I) {
+                                                         int64_t id_base, float* __restrict__ D, int64_t* __restrict__ I, int ip) {
     const int lane = threadIdx.x & 31;
     const int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(128) merge_keys_kernel(const uint64_t* __restr
         const int i = j * 32 + lane;
         if (i < k) {
             const bool empty = key[j] == kEmptyKey;
-            D[q * k + i] = empty ? kFltMax : key_dist(key[j]);
+            // ip: signed keys of -<q, y>; faiss pads inner-product results with (-FLT_MAX, -1)
+            D[q * k + i] = ip ? (empty ? -kFltMax : -key_value_signed(key[j])) : (empty ? kFltMax : key_dist(key[j]));
             I[q * k + i] = empty ? -1 : id_base + static_cast<int64_t>(key_idx(key[j]));
         }
     }
@@ -95,9 +96,9 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
 
 template <int E>
 cudaError_t launch_merge_keys(const uint64_t* partial, int64_t nq, int n_lists, int k, int64_t id_base, float* D, int64_t* I,
-                              cudaStream_t st) {
+                              int ip, cudaStream_t st) {
     constexpr int warps = 4;
-    merge_keys_kernel<E><<<static_cast<unsigned>((nq + warps - 1) / warps), warps * 32, 0, st>>>(partial, nq, n_lists, k, id_base, D, I);
+    merge_keys_kernel<E><<<static_cast<unsigned>((nq + warps - 1) / warps), warps * 32, 0, st>>>(partial, nq, n_lists, k, id_base, D, I, ip);
     return cudaGetLastError();
 }
 

@@ -22,7 +22,8 @@ namespace agp {
 // grid = (n_chunk_blocks, nq), block = 32 * kWarpsPerBlock; chunk id = blockIdx.x * warps + warp.
 template <int E>
 __global__ void __launch_bounds__(128) select_rows_kernel(const float* __restrict__ dist, int64_t ld, int64_t n, int k,
-                                                          int n_chunks, uint64_t* __restrict__ partial /*[nq][n_chunks][k]*/) {
+                                                          int n_chunks, uint64_t* __restrict__ partial /*[nq][n_chunks][k]*/,
+                                                          int signed_keys) {
     constexpr int CAP = 32 * E;
     extern __shared__ uint64_t sbuf[];    // [warps][CAP]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(128) select_rows_kernel(const float* __restric
         const bool take = v < thr;
         const unsigned m = __ballot_sync(kFull, take);
         if (m) {
-            if (take) buf[cnt + __popc(m & ((1u << lane) - 1))] = pack_key(v, static_cast<uint32_t>(c));
+            if (take) buf[cnt + __popc(m & ((1u << lane) - 1))] = signed_keys ? pack_key_signed(v, static_cast<uint32_t>(c)) : pack_key(v, static_cast<uint32_t>(c));
             cnt += __popc(m);
             if (cnt > CAP - 32) {
                 __syncwarp();
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(128) select_rows_kernel(const float* __restric
 #pragma unroll
                 for (int j = 0; j < E; ++j)
                     if (j * 32 + lane < k) buf[j * 32 + lane] = key[j];
-                if (cnt >= k) thr = key_dist(warp_get<E>(key, k - 1));
+                if (cnt >= k) thr = signed_keys ? key_value_signed(warp_get<E>(key, k - 1)) : key_dist(warp_get<E>(key, k - 1));
                 cnt = cnt < k ? cnt : k;
                 __syncwarp();
             }
@@ -72,11 +73,11 @@ __global__ void __launch_bounds__(128) select_rows_kernel(const float* __restric
 
 template <int E>
 cudaError_t launch_select_rows(const float* dist, int64_t ld, int64_t n, int k, int nq, int n_chunks, uint64_t* partial,
-                               cudaStream_t st) {
+                               int signed_keys, cudaStream_t st) {
     constexpr int warps = 4;
     dim3 grid(static_cast<unsigned>((n_chunks + warps - 1) / warps), static_cast<unsigned>(nq));
     const size_t smem = static_cast<size_t>(warps) * 32 * E * sizeof(uint64_t);
-    select_rows_kernel<E><<<grid, warps * 32, smem, st>>>(dist, ld, n, k, n_chunks, partial);
+    select_rows_kernel<E><<<grid, warps * 32, smem, st>>>(dist, ld, n, k, n_chunks, partial, signed_keys);
     return cudaGetLastError();
 }
 

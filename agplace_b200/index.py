@@ -23,6 +23,7 @@ import numpy as np
 
 from . import _lib
 
+METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
 FLT_MAX = np.float32(3.4028234663852886e38)
 
@@ -42,10 +43,12 @@ def default_device() -> int:
 class IndexFlatL2:
     """Exact brute-force squared-L2 index resident in one B200's HBM."""
 
+    _metric = METRIC_L2
+
     def __init__(self, d, device=None, precision=None):
         self.d = int(d)
         self.is_trained = True
-        self.metric_type = METRIC_L2
+        self.metric_type = self._metric
         self.device = default_device() if device is None else int(device)
         precision = precision or os.environ.get("AGP_PRECISION", "auto")
         if precision not in _lib.PRECISION:
@@ -53,8 +56,8 @@ class IndexFlatL2:
         self.precision = precision
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
-        _lib.check(self._lib.agp_index_create(self.d, self.device, _lib.PRECISION[precision], ctypes.byref(self._h)),
-                   "agp_index_create")
+        _lib.check(self._lib.agp_index_create_metric(self.d, self.device, _lib.PRECISION[precision], self._metric,
+                                                     ctypes.byref(self._h)), "agp_index_create_metric")
 
     # ------------------------------------------------------------------ faiss attributes
     @property
@@ -225,6 +228,40 @@ class IndexFlatL2:
         a, b = ctypes.c_int64(), ctypes.c_int64()
         _lib.check(self._lib.agp_index_get_stats(self._h, ctypes.byref(a), ctypes.byref(b)), "agp_index_get_stats")
         return a.value, b.value
+
+
+class IndexFlatIP(IndexFlatL2):
+    """Exact maximum-inner-product index (``faiss.IndexFlatIP``; reference anyloc/utilities.py:446, the cosine branch
+    of ``get_top_k_recall`` -- SURVEY 8f N3).  Same surface as :class:`IndexFlatL2`; ``search`` returns the k LARGEST
+    inner products, descending, ties by id, padded ``(-3.4028235e38, -1)``.  ``search_masked`` / ``search_subset`` are
+    L2-only (the mining helpers never use an inner-product index)."""
+
+    _metric = METRIC_INNER_PRODUCT
+
+
+def IndexFlat(d, metric=METRIC_L2, **kw):
+    """``faiss.IndexFlat(d, metric)``."""
+    if metric == METRIC_L2:
+        return IndexFlatL2(d, **kw)
+    if metric == METRIC_INNER_PRODUCT:
+        return IndexFlatIP(d, **kw)
+    raise ValueError(f"unsupported metric {metric!r}")
+
+
+class StandardGpuResources:
+    """Placeholder for ``faiss.StandardGpuResources()`` (reference anyloc/utilities.py:452): the engine owns its
+    device memory and streams, there is nothing to configure."""
+
+
+def index_cpu_to_gpu(res, device, index):
+    """``faiss.index_cpu_to_gpu(res, device, index)`` (reference anyloc/utilities.py:453).  Every index of this
+    package already lives on a GPU: an empty index is re-created on ``device`` if it was built for another one,
+    a populated index must already be there."""
+    if index.device == int(device):
+        return index
+    if index.ntotal:
+        raise RuntimeError(f"index holds {index.ntotal} vectors on cuda:{index.device}; create it on cuda:{device} instead")
+    return type(index)(index.d, device=int(device), precision=index.precision)
 
 
 def positives_to_csr(positives_per_query):

@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .index import IndexFlatL2, recall_hits
+from .index import IndexFlatIP, IndexFlatL2, recall_hits
 
 
 def compute_recall(args, queries_features, database_features, test_ds, test_method="hard_resize", index_cls=None,
@@ -54,3 +54,40 @@ def compute_recall_device(features_dim, recall_values, queries_features, databas
     _, predictions = index.search(queries_features, max(recall_values))
     hits = recall_hits(predictions, positives_per_query, recall_values)
     return hits.astype(np.float64) / queries_features.shape[0] * 100
+
+
+def get_top_k_recall(top_k, db, qu, gt_pos, method="cosine", norm_descs=True, use_gpu=True, use_percentage=True,
+                     sub_sample_db=1, sub_sample_qu=1):
+    """Mirror of reference anyloc/utilities.py:396-475: ``IndexFlatIP`` for ``method='cosine'``,
+    ``IndexFlatL2`` for ``'l2'``; descriptors are torch tensors (CPU or CUDA) or arrays.  The reference's
+    ``use_gpu=True`` branch needs faiss-gpu; here every index is a GPU index, so the flag changes nothing.
+    Returns ``(distances, indices, recalls)`` with ``recalls`` a dict keyed by the ``top_k`` values."""
+    import torch
+    import torch.nn.functional as F
+    db = torch.as_tensor(db)
+    qu = torch.as_tensor(qu)
+    if len(qu.shape) == 1:
+        qu = qu.unsqueeze(0)
+    if norm_descs:
+        db = F.normalize(db)
+        qu = F.normalize(qu)
+    D = db.shape[1]
+    if method == "cosine":
+        index = IndexFlatIP(D)
+    elif method == "l2":
+        index = IndexFlatL2(D)
+    else:
+        raise NotImplementedError(f"Method: {method}")
+    index.add(db)
+    distances, indices = index.search(qu, max(top_k))
+    recalls = dict(zip(top_k, [0] * len(top_k)))
+    ind_host = indices.cpu().numpy() if hasattr(indices, "cpu") else np.asarray(indices)
+    for i_qu, qu_retr in enumerate(ind_host):
+        for i_rec in top_k:
+            correct_retr = gt_pos[i_qu * sub_sample_qu]
+            if np.any(np.isin(qu_retr[:i_rec] * sub_sample_db, correct_retr)):
+                recalls[i_rec] += 1
+    if use_percentage:
+        for k in recalls:
+            recalls[k] /= len(ind_host)
+    return distances, indices, recalls

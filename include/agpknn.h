@@ -54,10 +54,21 @@ enum agp_error {
 
 #define AGP_MAX_K 512
 
+/* faiss MetricType values (faiss.METRIC_INNER_PRODUCT = 0, faiss.METRIC_L2 = 1). */
+enum agp_metric { AGP_METRIC_INNER_PRODUCT = 0, AGP_METRIC_L2 = 1 };
+
 /* faiss.IndexFlatL2(d)  -- reference test.py:27, datasets/datasets_ws_kitti360.py:978,987,
  * datasets/datasets_ws_nuscenes.py:1243,1252, datasets_ws.py:691,700.
  * `device` is the CUDA ordinal that owns the index (one process per GPU drives one shard). */
 AGP_API int agp_index_create(int d, int device, int precision_mode, agp_index** out);
+
+/* faiss.IndexFlatIP(d)  -- reference anyloc/utilities.py:446 (get_top_k_recall, method="cosine") -- or
+ * IndexFlatL2 when metric == AGP_METRIC_L2.  An inner-product index returns, per query, the k rows with the LARGEST
+ * <q, y>, descending, ties by id, D = the fp32 inner products, missing results (-3.4028235e38, -1) as in faiss.  Same
+ * kernels: the fp16 plane carries no norm term and the screened value is B_q - <q, y> with B_q = |q| max|y|; the finish
+ * recomputes the fp32 inner products of the certified band.  agp_index_search_masked / _subset are L2-only. */
+AGP_API int agp_index_create_metric(int d, int device, int precision_mode, int metric, agp_index** out);
+AGP_API int agp_index_metric(const agp_index* idx);
 
 /* Index destructor (SWIG __del__).  Frees every device allocation, stream and event. */
 AGP_API void agp_index_free(agp_index* idx);

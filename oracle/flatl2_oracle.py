@@ -203,6 +203,50 @@ def knn_fp32(xq, xb, k, path=None):
     return D, I
 
 
+def knn_ip_fp64(xq, xb, k):
+    """Exact maximum inner product in fp64; descending product, ties by index; padded (-FLT_MAX, -1)."""
+    xq = np.asarray(xq, dtype=np.float64)
+    xb = np.asarray(xb, dtype=np.float64)
+    nq, n = xq.shape[0], xb.shape[0]
+    D = np.full((nq, k), -float(FLT_MAX), dtype=np.float64)
+    I = np.full((nq, k), -1, dtype=np.int64)
+    m = min(k, n)
+    if m:
+        ip = xq @ xb.T
+        order = np.argsort(-ip, axis=1, kind="stable")[:, :m]
+        D[:, :m] = np.take_along_axis(ip, order, 1)
+        I[:, :m] = order
+    return D, I
+
+
+def knn_ip_fp32(xq, xb, k, path=None):
+    """faiss ``knn_inner_product`` restated (``IndexFlatIP.search``; reference anyloc/utilities.py:446,457): fp32
+    ``fvec_inner_product`` per pair for ``nq < 20``, sgemm blocks of 4096 x 1024 otherwise, the k LARGEST products
+    per query (min-heap result handler, strict admission: on boundary ties the lower id stays), output descending,
+    padded (-FLT_MAX, -1).  Ties inside the list are ordered by ascending id here; faiss's own order of exactly
+    equal products cannot be checked in this image (PARITY UNPINNED, see the module docstring)."""
+    xq = np.ascontiguousarray(xq, dtype=np.float32)
+    xb = np.ascontiguousarray(xb, dtype=np.float32)
+    nq, n = xq.shape[0], xb.shape[0]
+    D = np.full((nq, k), -FLT_MAX, dtype=np.float32)
+    I = np.full((nq, k), -1, dtype=np.int64)
+    m = min(k, n)
+    if nq == 0 or m == 0:
+        return D, I
+    if path is None:
+        path = "seq" if nq < BLAS_THRESHOLD else "blas"
+    for i0 in range(0, nq, BS_X):
+        q = xq[i0:i0 + BS_X]
+        if path == "seq":
+            ip = np.stack([np.einsum("ij,j->i", xb, qi, dtype=np.float32) for qi in q])
+        else:
+            ip = np.concatenate([q @ xb[j0:j0 + BS_Y].T for j0 in range(0, n, BS_Y)], axis=1)
+        order = np.argsort(-ip, axis=1, kind="stable")[:, :m]
+        D[i0:i0 + BS_X, :m] = np.take_along_axis(ip, order, 1)
+        I[i0:i0 + BS_X, :m] = order
+    return D, I
+
+
 class IndexFlatL2:
     """Restatement of the SWIG-wrapped ``faiss.IndexFlatL2`` surface the reference uses."""
 

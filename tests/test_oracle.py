@@ -111,3 +111,21 @@ def test_compare_knn_rejects_wrong_answers():
     assert not orc.compare_knn(D, Ibad, D, I)[0]
     Dbad = D.copy(); Dbad[4, 1] *= 1.001
     assert not orc.compare_knn(Dbad, I, D, I)[0]
+
+
+def test_inner_product_oracle_matches_fp64_and_orders_ties_by_id():
+    """knn_ip_fp32 (IndexFlatIP restatement, reference anyloc/utilities.py:446-457) against fp64 brute force."""
+    rng = np.random.default_rng(21)
+    xb = rng.standard_normal((500, 24)).astype(np.float32)
+    xb[100:110] = xb[5:15]                      # exact ties
+    for nq in (3, 40):                          # seq and blas branches
+        xq = rng.standard_normal((nq, 24)).astype(np.float32)
+        D, I = orc.knn_ip_fp32(xq, xb, 12)
+        D64, I64 = orc.knn_ip_fp64(xq, xb, 12)
+        ok, msg = orc.compare_knn(D, I, D64, I64, xq=xq, xb=xb, abs_floor_eps=8 * 2.0 ** -24)
+        assert ok, msg
+        assert np.all(np.diff(D, axis=1) <= 0)
+    D, I = orc.knn_ip_fp32(xq[:2], xb[:4], 6)   # k > n: (-FLT_MAX, -1) padding
+    assert np.all(I[:, 4:] == -1) and np.all(D[:, 4:] == -orc.FLT_MAX)
+    D, I = orc.knn_ip_fp32(xb[5:6], xb, 3)      # xb[5] == xb[100]: equal products, lower id first
+    assert list(I[0, :2]) == [5, 100]
