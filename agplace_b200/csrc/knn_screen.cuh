@@ -32,6 +32,7 @@
 // per-column loads, one FMNMX3 per three elements.  Storage rows without a vector carry aux = -inf.
 // Algorithmic work per pair tile step: 2 * 256 * 256 * d flop, issued once (+ 16/d for the aux step).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "knn_tc.cuh"
 #include "merge.cuh"
@@ -693,22 +694,26 @@ __global__ void __launch_bounds__(128) screen_finalize_kernel(const uint64_t* __
     }
     const int nb = fill;      // certified band: every row that can be in the true top-k is among buf[0..nb)
 
-    // exact distances of the band
+    // exact distances of the band: 8 rows (8 independent 16-byte loads per lane) in flight -- this phase is an HBM gather
+    // of nb rows of 4 d bytes and the only one of the kernel that is bandwidth-bound
     const float* qrow = xq + q * d;
     const bool vec = ((d & 3) == 0) && (((reinterpret_cast<uintptr_t>(xq) | reinterpret_cast<uintptr_t>(xb)) & 15) == 0);
-    for (int r0 = 0; r0 < nb; r0 += 4) {
-        const float* row[4];
+    constexpr int RB = 8;
+    for (int r0 = 0; r0 < nb; r0 += RB) {
+        const float* row[RB];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) row[u] = xb + static_cast<int64_t>(key_idx(buf[min(r0 + u, nb - 1)])) * d;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int u = 0; u < RB; ++u) row[u] = xb + static_cast<int64_t>(key_idx(buf[min(r0 + u, nb - 1)])) * d;
+        float acc[RB];
+#pragma unroll
+        for (int u = 0; u < RB; ++u) acc[u] = 0.f;
         if (vec) {
             for (int c = lane; c < (d >> 2); c += 32) {
                 const float4 a = __ldg(reinterpret_cast<const float4*>(qrow) + c);
-                float4 b[4];
+                float4 b[RB];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) b[u] = __ldg(reinterpret_cast<const float4*>(row[u]) + c);
+                for (int u = 0; u < RB; ++u) b[u] = __ldg(reinterpret_cast<const float4*>(row[u]) + c);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < RB; ++u) {
                     if (ip) {            // exact finish of IndexFlatIP: the fp32 inner product itself
                         acc[u] = fmaf(a.x, b[u].x, acc[u]);
                         acc[u] = fmaf(a.y, b[u].y, acc[u]);
@@ -727,7 +732,7 @@ __global__ void __launch_bounds__(128) screen_finalize_kernel(const uint64_t* __
             for (int c = lane; c < d; c += 32) {
                 const float a = __ldg(qrow + c);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < RB; ++u) {
                     const float y = __ldg(row[u] + c);
                     const float t = ip ? a : a - y;
                     acc[u] = fmaf(t, ip ? y : t, acc[u]);
@@ -735,29 +740,45 @@ __global__ void __launch_bounds__(128) screen_finalize_kernel(const uint64_t* __
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < RB; ++u) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(kFull, acc[u], o);
         }
-        if (lane < 4 && r0 + lane < nb) sd[r0 + lane] = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+        float mine_v = acc[0];
+#pragma unroll
+        for (int u = 1; u < RB; ++u) mine_v = lane == u ? acc[u] : mine_v;
+        if (lane < RB && r0 + lane < nb) sd[r0 + lane] = mine_v;
     }
     __syncwarp();
+    // final order by (exact value, id): the band is ~k + a few rows, so the sort is sized by nb, not by the slot count
+    auto emit = [&](auto tag) {
+        constexpr int EF = decltype(tag)::value;
+        uint64_t fk[EF];
 #pragma unroll
-    for (int j = 0; j < E; ++j) {
-        const int i = j * 32 + lane;
-        // inner product: order by (-<q, y> ascending, id ascending) through the sign-aware key
-        key[j] = (i < nb) ? (ip ? pack_key_signed(-sd[i], key_idx(buf[i])) : pack_key(sd[i], key_idx(buf[i]))) : kEmptyKey;
-    }
-    warp_bitonic_sort<E>(key, lane);
-#pragma unroll
-    for (int j = 0; j < E; ++j) {
-        const int i = j * 32 + lane;
-        if (i < k) {
-            const bool empty = key[j] == kEmptyKey;
-            D[q * k + i] = ip ? (empty ? -kFltMax : -key_value_signed(key[j])) : (empty ? kFltMax : key_dist(key[j]));
-            I[q * k + i] = empty ? -1 : id_base + static_cast<int64_t>(key_idx(key[j]));
+        for (int j = 0; j < EF; ++j) {
+            const int i = j * 32 + lane;
+            // inner product: order by (-<q, y> ascending, id ascending) through the sign-aware key
+            fk[j] = (i < nb) ? (ip ? pack_key_signed(-sd[i], key_idx(buf[i])) : pack_key(sd[i], key_idx(buf[i]))) : kEmptyKey;
         }
-    }
+        warp_bitonic_sort<EF>(fk, lane);
+#pragma unroll
+        for (int j = 0; j < EF; ++j) {
+            const int i = j * 32 + lane;
+            if (i < k) {
+                const bool empty = fk[j] == kEmptyKey;
+                D[q * k + i] = ip ? (empty ? -kFltMax : -key_value_signed(fk[j])) : (empty ? kFltMax : key_dist(fk[j]));
+                I[q * k + i] = empty ? -1 : id_base + static_cast<int64_t>(key_idx(fk[j]));
+            }
+        }
+        // ranks beyond the sorted span (k > 32 * EF can only happen when fewer than k rows exist): faiss padding
+        for (int i = EF * 32 + lane; i < k; i += 32) {
+            D[q * k + i] = ip ? -kFltMax : kFltMax;
+            I[q * k + i] = -1;
+        }
+    };
+    if (E > 2 && nb <= 64) emit(std::integral_constant<int, 2>{});
+    else if (E > 4 && nb <= 128) emit(std::integral_constant<int, 4>{});
+    else emit(std::integral_constant<int, E>{});
     if (over && lane == 0) ovf_list[atomicAdd(ovf_count, 1)] = static_cast<int>(q);
 }
 
