@@ -655,25 +655,44 @@ __global__ void __launch_bounds__(128) screen_finalize_kernel(const uint64_t* __
 
     uint64_t key[E];
     int fill = 0, done = 0;
-    // sort the staged keys, keep the band below k-th + 2 band; `last` = nothing more will be staged
+    // keep the band below (k-th smallest screened distance) + 2 band of the staged keys; `last` = nothing more will be
+    // staged.  Only the SET matters (the exact finish orders it), so the k-th is found by a bitwise search over the fp32
+    // bit pattern (31 warp-wide counts; distances are non-negative, so the pattern is monotone) instead of a full sort.
     auto sort_keep = [&](bool last) {
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < E; ++j) key[j] = (j * 32 + lane < fill) ? buf[j * 32 + lane] : kEmptyKey;
-        warp_bitonic_sort<E>(key, lane);
-        const float kth = (fill >= k) ? key_dist(warp_get<E>(key, k - 1)) : inf;
-        const float flim = kth + band2;
-        int mine = 0;
+        float kth = inf;
+        if (fill >= k) {
+            uint32_t v = 0;
+            for (int b = 30; b >= 0; --b) {
+                const uint32_t cand = v | ((1u << b) - 1u);      // largest pattern with this prefix and bit b clear
+                int c = 0;
 #pragma unroll
-        for (int j = 0; j < E; ++j) mine += (key[j] != kEmptyKey && key_dist(key[j]) < flim) ? 1 : 0;
-        int nkeep = __reduce_add_sync(kFull, mine);
-        if (!last && nkeep > CAP - 32) {          // no room to stage the rest next to the band
-            over = true;
-            nkeep = k;
+                for (int j = 0; j < E; ++j) c += (static_cast<uint32_t>(key[j] >> 32) <= cand) ? 1 : 0;     // empty keys: 0xffffffff
+                if (__reduce_add_sync(kFull, c) < k) v |= 1u << b;
+            }
+            kth = __uint_as_float(v);
         }
+        auto compact = [&](float lim, bool inclusive) {
+            int base = 0;
 #pragma unroll
-        for (int j = 0; j < E; ++j)
-            if (j * 32 + lane < nkeep) buf[j * 32 + lane] = key[j];
+            for (int j = 0; j < E; ++j) {
+                const float dv = key_dist(key[j]);
+                const bool keep = key[j] != kEmptyKey && (inclusive ? dv <= lim : dv < lim);
+                const unsigned m = __ballot_sync(kFull, keep);
+                const int pos = base + __popc(m & ((1u << lane) - 1u));
+                if (keep && pos < CAP) buf[pos] = key[j];
+                base += __popc(m);
+            }
+            return base;
+        };
+        int nkeep = compact(kth + band2, false);
+        if (!last && nkeep > CAP - 32) {          // no room to stage the rest next to the band: the query goes to the fallback
+            over = true;
+            __syncwarp();
+            nkeep = min(compact(kth, true), CAP - 32);
+        }
         fill = nkeep;
         __syncwarp();
     };
