@@ -240,6 +240,34 @@ __device__ __forceinline__ void sc_compact_lanes(uint64_t* wbuf, int& cnt, float
     }
 }
 
+// Ascending bitonic sort of 32 values held in registers (all indices static after unrolling: 240 compare-exchanges =
+// 480 FMNMX), and a select-chain read of element idx (warp-uniform).  Used once per sweep, by the bootstrap below.
+__device__ __forceinline__ void sc_sort32(float (&v)[32]) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int l = i ^ stride;
+                if (l > i) {
+                    const bool up = (i & size) == 0;
+                    const float a = v[i], b = v[l];
+                    const float lo = fminf(a, b), hi = fmaxf(a, b);
+                    v[i] = up ? lo : hi;
+                    v[l] = up ? hi : lo;
+                }
+            }
+        }
+    }
+}
+__device__ __forceinline__ float sc_pick32(const float (&v)[32], int idx) {
+    float x = v[0];
+#pragma unroll
+    for (int j = 1; j < 32; ++j) x = (j == idx) ? v[j] : x;
+    return x;
+}
+
 template <int E>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_b, const ScreenParams p) {
@@ -395,6 +423,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         long long n_hits = 0, t_scan = 0, n_tiles = 0, t_compact1 = 0;
         const bool f_pred_on = (p.flags & 1) == 0;      // AGP_SCREEN_FLAGS bit 0 selects the branchy scan (A/B switch)
         const bool f_xchg = (p.flags & 4) == 0;         // bit 2 turns the pair exchange of the rounds off (A/B switch)
+        const bool f_boot = (p.flags & 8) == 0;         // bit 3 turns the first-tile bootstrap off (A/B switch)
         uint32_t tempty_leader[2];
         tempty_leader[0] = mapa_u32(smem_u32(&tempty[0]), 0);
         tempty_leader[1] = mapa_u32(smem_u32(&tempty[1]), 0);
@@ -532,6 +561,39 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                         }
                     }
                 };
+                // Bootstrap of a sweep that starts without a bound: instead of admitting all 128 columns of the first tile
+                // and reading them back twice in a compaction round, the tile is read twice from TMEM.  Pass A sorts each
+                // 32-column chunk in registers; the min over the 4 chunks of their ceil(k/4)-th largest accumulator has at
+                // least k columns at or above it, i.e. it is a valid bound of the list's k-th best (and the ceil(kh/4)-th
+                // one of its kh-th best, published for the partner half).  Pass B is the normal scan against that bound.
+                bool booted = false;
+                // (the decision uses nothing a partner warp could see differently: the rounds' named barrier needs both
+                // warps of a lane group to agree on whether round 1 happens)
+                if (f_boot && t == it.t0 && p.k <= 128) {
+                    const int rk = (p.k + 3) >> 2, rh = (kh + 3) >> 2;
+                    float xk = inf, xh = inf;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        tmem_ld32(tcol + cc * 32, ra);
+                        tmem_ld_wait();
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
+                        sc_sort32(v);
+                        xk = fminf(xk, sc_pick32(v, 32 - rk));
+                        xh = fminf(xh, sc_pick32(v, 32 - rh));
+                    }
+                    if (valid) {
+                        const float dk = fmaf(xk, Wq, qn), dh = fmaf(xh, Wq, qn);     // screened distances of the two bounds
+                        if (dk < inf) {
+                            atomicMin(my_gthr, __float_as_uint(fmaxf(dk, 0.f)));
+                            lim = fminf(lim, fmaxf(dk, 0.f) + band2);
+                        }
+                        if (dh < inf) atomicMin(my_hthr, __float_as_uint(fmaxf(dh, 0.f)));
+                    }
+                    thr = (lim - qn) * invW;
+                    booted = true;
+                }
                 long long c4 = p.dbg ? clock64() : 0;
                 const int cnt_before = cnt;
                 // software pipeline over the 4 chunks: the next tcgen05.ld is in flight while this chunk is scanned
@@ -558,7 +620,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                 bool do_compact = __any_sync(kFull, cnt > CAP - TC_BN / 2);
                 bool scheduled = false;
                 if (t - it.t0 + 1 == next_sched) {
-                    scheduled = true;
+                    scheduled = !booted;            // a bootstrapped first tile already has its bound: skip round 1
                     ++round;
                     // rounds after tiles 1, m, m^2, ... with m = sched_mul / 4 (at least one tile apart)
                     const int nb = max(sched_base + 1, (sched_base * p.sched_mul) >> 2);
@@ -566,7 +628,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     sched_base = nb;
                     next_sched = nb + (round >= 3 ? ((cluster_id & 7) * width) >> 4 : 0);
                     // with the pair exchange both warps of a lane group must enter the round (named barrier inside)
-                    do_compact = do_compact || (f_xchg && !wide) || __any_sync(kFull, cnt > p.k + 8);
+                    if (!booted) do_compact = do_compact || (f_xchg && !wide) || __any_sync(kFull, cnt > p.k + 8);
                 }
                 if (do_compact) {
                     long long c3 = p.dbg ? clock64() : 0;

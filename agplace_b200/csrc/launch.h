@@ -58,7 +58,7 @@ struct ScreenParams {
     int debug_skip_epilogue;// development probe: epilogue hands every accumulator straight back
     int sched_mul;          // scheduled compactions after tiles 1, m, m^2, ... of an item, m = sched_mul / 4 (8 = doubling)
     int ip;                 // 1: inner-product index (IndexFlatIP): screened value = B_q - <q, y>, B_q = |q| max|y| (>= any product)
-    int flags;              // A/B switches (AGP_SCREEN_FLAGS): bit 0 = branchy scan instead of the predicated one, bit 2 = no pair exchange in the rounds
+    int flags;              // A/B switches (AGP_SCREEN_FLAGS): bit 0 = branchy scan instead of the predicated one, bit 2 = no pair exchange in the rounds, bit 3 = no first-tile bootstrap
     const float* qn;        // [nq] |q|^2
     const float* sq;        // [nq] query row scale 2^eq
     const float* dq;        // [nq] |q - fp16 plane| (rounded up)

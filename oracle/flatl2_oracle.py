@@ -18,10 +18,15 @@ faiss's published IndexFlatL2 algorithm instead of importing it:
   ``oracle/flatl2_ref.c`` (``oracle/_build/liboracle.so``).  A slow pure-numpy
   variant (:func:`knn_fp32_numpy`) exists to cross-check the C code.
 
-PARITY UNPINNED: the reference holds no golden vectors or tests at this boundary and
-faiss cannot be executed here; the oracle is pinned against ``O64`` and the
-hand-written known-answer vectors in ``tests/golden`` only.  If ``import faiss``
-ever succeeds, :func:`faiss_available` reports it and tests compare against it too.
+PARITY PIN: the reference holds no golden vectors or tests at this boundary and faiss cannot be
+executed here.  The oracle is pinned against (i) the one known-answer vector real faiss has
+published for IndexFlatL2 -- the output of its own first tutorial (tutorial/python/1-Flat.py, faiss
+wiki "Getting started": 100k x 64 database, ``np.random.seed(1234)``, k = 4; transcribed into
+``tests/golden/faiss_tutorial_1flat.json``): all 40 neighbour ids and the 20 printed distances are
+reproduced on both code paths (``tests/test_oracle.py``); (ii) ``O64``; (iii) the hand-written
+known-answer vectors in ``tests/golden``.  Everything beyond that single published vector (tie
+order, padding, the inner-product variant) is "against the restatement".  If ``import faiss`` ever
+succeeds, :func:`faiss_available` reports it and tests compare against it too.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py`` (cpu_baseline /
 ``--impl reference``) may import this module.
@@ -224,7 +229,7 @@ def knn_ip_fp32(xq, xb, k, path=None):
     ``fvec_inner_product`` per pair for ``nq < 20``, sgemm blocks of 4096 x 1024 otherwise, the k LARGEST products
     per query (min-heap result handler, strict admission: on boundary ties the lower id stays), output descending,
     padded (-FLT_MAX, -1).  Ties inside the list are ordered by ascending id here; faiss's own order of exactly
-    equal products cannot be checked in this image (PARITY UNPINNED, see the module docstring)."""
+    equal products cannot be checked in this image (no published vector covers the inner-product metric: restatement only)."""
     xq = np.ascontiguousarray(xq, dtype=np.float32)
     xb = np.ascontiguousarray(xb, dtype=np.float32)
     nq, n = xq.shape[0], xb.shape[0]

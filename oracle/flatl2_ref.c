@@ -19,10 +19,13 @@
  *   k >= 100 : reservoir of capacity 2k, strict admission, shrink, final sort
  *   padding  : (FLT_MAX, -1) when fewer than k database rows exist
  *
- * PARITY UNPINNED: the reference ships no golden vectors / tests for this path and
- * faiss cannot be run here, so this restatement is pinned only against an
- * independent fp64 brute force (oracle/flatl2_oracle.py) and hand-written
- * known-answer vectors (tests/golden).
+ * PARITY PIN: the reference ships no golden vectors / tests for this path and faiss
+ * cannot be run here.  The restatement is pinned against the one known-answer vector
+ * real faiss publishes (the output of its tutorial/python/1-Flat.py, transcribed into
+ * tests/golden/faiss_tutorial_1flat.json: all ids and printed distances reproduced),
+ * an independent fp64 brute force (oracle/flatl2_oracle.py) and hand-written
+ * known-answer vectors (tests/golden); beyond that single published vector every
+ * parity statement is "against the restatement".
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this library.  The sgemm of the nq >= 20 path is supplied by the

@@ -52,3 +52,22 @@ def make_mining_problem(seed, database_num=600, queries_num=80, d=32):
     cache = np.concatenate([xb, xq]).astype(np.float32)
     return SimpleNamespace(xb=xb, xq=xq, hard=hard, soft=soft, cache=cache, database_num=database_num,
                            queries_num=queries_num, d=d, rng=rng)
+
+
+def faiss_tutorial_data():
+    """The data of faiss's own tutorial (tutorial/python/1-Flat.py): legacy np.random.seed(1234) stream, which is
+    stable across numpy versions.  Returns (xb, xq, published) with the published outputs of real faiss."""
+    import json
+    from pathlib import Path
+    pub = json.loads((Path(__file__).parent / "golden" / "faiss_tutorial_1flat.json").read_text())
+    d, nb, nq = 64, 100000, 10000
+    state = np.random.get_state()
+    try:
+        np.random.seed(1234)
+        xb = np.random.random((nb, d)).astype("float32")
+        xb[:, 0] += np.arange(nb) / 1000.0
+        xq = np.random.random((nq, d)).astype("float32")
+        xq[:, 0] += np.arange(nq) / 1000.0
+    finally:
+        np.random.set_state(state)
+    return xb, xq, pub

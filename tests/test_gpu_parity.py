@@ -428,6 +428,24 @@ def test_full_size_cfg2_properties():
     np.testing.assert_array_equal(Ib, I); np.testing.assert_array_equal(Db, D)
 
 
+@pytest.mark.parametrize("precision", MODES)
+def test_engine_reproduces_the_published_output_of_the_faiss_tutorial(precision):
+    """Real faiss output (tests/golden/faiss_tutorial_1flat.json: faiss's tutorial/python/1-Flat.py as published on
+    its wiki) reproduced by the CUDA engine through the C ABI: every neighbour id, distances to printed precision."""
+    from tests.helpers import faiss_tutorial_data
+    xb, xq, pub = faiss_tutorial_data()
+    ix = agp().IndexFlatL2(64, precision=precision); ix.add(xb)
+    D, I = ix.search(xb[:5], 4)
+    np.testing.assert_array_equal(I, np.array(pub["sanity_I"]))
+    np.testing.assert_allclose(D, np.array(pub["sanity_D"]), rtol=1e-5, atol=2e-5)
+    D, I = ix.search(xq, 4)
+    np.testing.assert_array_equal(I[:5], np.array(pub["search_I_first5"]))
+    np.testing.assert_array_equal(I[-5:], np.array(pub["search_I_last5"]))
+    Dr, Ir = orc.knn_fp32(xq, xb, 4)
+    ok, msg = orc.compare_knn(D, I, Dr, Ir, xq=xq, xb=xb, abs_floor_eps=8 * 2.0 ** -24)
+    assert ok, msg
+
+
 def test_native_library_was_used():
     from agplace_b200 import _lib
     before = _lib.kernel_launches()

@@ -129,3 +129,20 @@ def test_inner_product_oracle_matches_fp64_and_orders_ties_by_id():
     assert np.all(I[:, 4:] == -1) and np.all(D[:, 4:] == -orc.FLT_MAX)
     D, I = orc.knn_ip_fp32(xb[5:6], xb, 3)      # xb[5] == xb[100]: equal products, lower id first
     assert list(I[0, :2]) == [5, 100]
+
+
+def test_oracle_reproduces_the_published_output_of_the_faiss_tutorial():
+    """The one known-answer vector that real faiss has published for IndexFlatL2: its first tutorial
+    (tutorial/python/1-Flat.py, faiss wiki 'Getting started').  The restatement must reproduce every id and the
+    distances to the printed precision, on both of faiss's code paths (5 queries: nq < 20, difference form;
+    10000 queries: sgemm blocks)."""
+    from tests.helpers import faiss_tutorial_data
+    xb, xq, pub = faiss_tutorial_data()
+    D, I = orc.knn_fp32(xb[:5], xb, 4)                     # "sanity check" of the tutorial
+    np.testing.assert_array_equal(I, np.array(pub["sanity_I"]))
+    np.testing.assert_allclose(D, np.array(pub["sanity_D"]), rtol=2e-7, atol=1e-6)
+    D, I = orc.knn_fp32(xq, xb, 4)                         # the actual search
+    np.testing.assert_array_equal(I[:5], np.array(pub["search_I_first5"]))
+    np.testing.assert_array_equal(I[-5:], np.array(pub["search_I_last5"]))
+    D5, I5 = orc.knn_fp32(xb[:5], xb, 4, path="blas")      # same answers through the expansion form
+    np.testing.assert_array_equal(I5, np.array(pub["sanity_I"]))
