@@ -143,10 +143,13 @@ def run_reference(args):
         return 0
     xb, xq = make_host_data(c)
     cores = os.cpu_count() or 1
-    # bounded sample: enough queries for ~1-2 s of CPU work per step (>= 20 so the sgemm branch is the one timed)
-    probe = xq[: min(256, c["nq"])]
-    rate, _ = cpu_search_rate(xb, probe, c["k"])
-    sample_q = int(min(c["nq"], max(64, rate * 1.5)))
+    # bounded sample: the CPU path is only efficient on large query blocks (faiss multiplies 4096 queries at a time), so
+    # the rate is probed on 1024 queries (after a throw-away call) and a step is sized for ~2 s of CPU work -- a whole
+    # --steps K run stays within ~2 minutes -- rather than on a sliver of the batch that would understate the CPU
+    cpu_search_rate(xb, xq[: min(256, c["nq"])], c["k"])
+    rate, _ = cpu_search_rate(xb, xq[: min(1024, c["nq"])], c["k"])
+    per_step_s = min(2.0, 120.0 / max(args.steps + min(args.warmup, 2), 1))
+    sample_q = int(min(c["nq"], max(256, rate * per_step_s)))
     sample = xq[:sample_q]
     for _ in range(max(1, min(args.warmup, 2))):
         orc.knn_fp32(sample, xb, c["k"])
