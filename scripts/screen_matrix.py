@@ -16,13 +16,13 @@ xq = rng.standard_normal((nq, d)).astype(np.float32); xq /= np.linalg.norm(xq, a
 ix = agp.IndexFlatL2(d, precision="fp16_screen"); ix.add(xb)
 xq_d = torch.from_numpy(xq).cuda()
 
-variants = [dict(), dict(FLAGS=4), dict(SCHED=10), dict(SCHED=7), dict(FLAGS=1)]
+variants = [dict(), dict(PF=2), dict(PF=4), dict(PF=8), dict(PF=16), dict(STAGES=4), dict(STAGES=3)]
 variants = variants + variants          # second pass: order / warm-up effects show as a difference between the passes
 if len(sys.argv) > 2:
     variants = [dict()] + [json.loads(a) for a in sys.argv[2:]]
 ref = None
 for v in variants:
-    for key in ("FLAGS", "E", "SCHED"):
+    for key in ("FLAGS", "E", "SCHED", "PF", "STAGES"):
         os.environ.pop("AGP_SCREEN_" + key, None)
     for key, val in v.items():
         os.environ["AGP_SCREEN_" + key] = str(val)
