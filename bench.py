@@ -286,6 +286,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    rank_spread = {}
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -296,9 +298,10 @@ def run_ours(args):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            t = torch.tensor([ms, -ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)      # slowest rank (the reported time) and fastest rank (diagnostic)
+            ms = float(t[0].item())
+            rank_spread["fastest_rank_ms_per_step"] = -float(t[1].item()) / steps
         barrier()
         return ms
 
@@ -311,6 +314,7 @@ def run_ours(args):
     if sampler:
         sampler.start()
     ms = timed(step_device, args.steps)
+    spread_device = dict(rank_spread)
     clocks = sampler.stop() if sampler else None
     launches = _lib.kernel_launches() - launches0
     kernel_ms, kernel_n = local.get_profile(reset=True)
@@ -365,6 +369,8 @@ def run_ours(args):
         "roofline": roofline,
         "clocks": clocks,
     }
+    if world > 1 and spread_device:     # ms_per_step is the SLOWEST rank's; the fastest rank shows how much of it is rank spread
+        line["rank_spread"] = spread_device
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and xb_local is not None:
         from oracle import flatl2_oracle as orc
