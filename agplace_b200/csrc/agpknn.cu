@@ -1230,4 +1230,66 @@ int agp_recall_at_n(int device, void* stream_v, const int64_t* I, int mem_kind, 
     return 0;
 }
 
+// N4: radius neighbours (sklearn NearestNeighbors.radius_neighbors restated on the GPU), two-phase CSR.
+static int radius_common(int device, int64_t n_db, int dim, const double* db, int64_t nq, const double* q, double radius, int64_t* counts,
+                         const int64_t* offsets, int64_t* ids) {
+    if (n_db < 0 || nq < 0) return set_err(AGP_EINVAL, "n_db and nq must be >= 0");
+    if (dim < 1 || dim > 8) return set_err(AGP_EINVAL, "dim must be in 1..8, got %d", dim);
+    if (!(radius >= 0.0)) return set_err(AGP_EINVAL, "radius must be >= 0");
+    if ((n_db > 0 && !db) || (nq > 0 && !q)) return set_err(AGP_EINVAL, "null pointer");
+    const bool fill = ids != nullptr || offsets != nullptr;
+    if (fill ? !offsets : !counts) return set_err(AGP_EINVAL, "null pointer");
+    if (nq == 0) return 0;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_err(AGP_ENODEV, "no CUDA device visible: agpknn has no CPU fallback");
+    }
+    CK(cudaSetDevice(device));
+    const int64_t total = fill ? offsets[nq] : 0;
+    if (fill && total > 0 && !ids) return set_err(AGP_EINVAL, "ids is null");
+    double *d_db = nullptr, *d_q = nullptr;
+    int64_t *d_a = nullptr, *d_ids = nullptr;      // d_a: counts (count phase) or offsets (fill phase)
+    int rc = 0;
+    auto cleanup = [&]() { cudaFree(d_db); cudaFree(d_q); cudaFree(d_a); cudaFree(d_ids); };
+#define CKD(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            rc = set_err(AGP_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            cleanup();                                                                              \
+            return rc;                                                                              \
+        }                                                                                           \
+    } while (0)
+    CKD(cudaMalloc(&d_db, static_cast<size_t>(std::max<int64_t>(n_db, 1)) * dim * sizeof(double)));
+    CKD(cudaMalloc(&d_q, static_cast<size_t>(nq) * dim * sizeof(double)));
+    CKD(cudaMalloc(&d_a, static_cast<size_t>(nq + 1) * sizeof(int64_t)));
+    if (n_db > 0) CKD(cudaMemcpy(d_db, db, static_cast<size_t>(n_db) * dim * sizeof(double), cudaMemcpyHostToDevice));
+    CKD(cudaMemcpy(d_q, q, static_cast<size_t>(nq) * dim * sizeof(double), cudaMemcpyHostToDevice));
+    g_launches.fetch_add(1);
+    if (!fill) {
+        CKD(launch_radius(false, d_db, n_db, dim, d_q, nq, radius * radius, d_a, nullptr, nullptr, nullptr));
+        CKD(cudaMemcpy(counts, d_a, static_cast<size_t>(nq) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    } else {
+        CKD(cudaMalloc(&d_ids, static_cast<size_t>(std::max<int64_t>(total, 1)) * sizeof(int64_t)));
+        CKD(cudaMemcpy(d_a, offsets, static_cast<size_t>(nq + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+        CKD(launch_radius(true, d_db, n_db, dim, d_q, nq, radius * radius, nullptr, d_a, d_ids, nullptr));
+        if (total > 0) CKD(cudaMemcpy(ids, d_ids, static_cast<size_t>(total) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        else CKD(cudaDeviceSynchronize());
+    }
+    cleanup();
+#undef CKD
+    return 0;
+}
+
+int agp_radius_count(int device, int64_t n_db, int dim, const double* db, int64_t nq, const double* q, double radius, int64_t* counts) {
+    return radius_common(device, n_db, dim, db, nq, q, radius, counts, nullptr, nullptr);
+}
+
+int agp_radius_fill(int device, int64_t n_db, int dim, const double* db, int64_t nq, const double* q, double radius,
+                    const int64_t* offsets, int64_t* ids) {
+    if (!offsets) return set_err(AGP_EINVAL, "offsets is null");
+    return radius_common(device, n_db, dim, db, nq, q, radius, nullptr, offsets, ids);
+}
+
 }  // extern "C"

@@ -484,6 +484,54 @@ __global__ void __launch_bounds__(128) best_of_lists_kernel(const float* __restr
     }
 }
 
+// N4: radius neighbours in the UTM plane -- what the reference computes with sklearn,
+//   knn = NearestNeighbors(); knn.fit(database_utms); knn.radius_neighbors(queries_utms, radius=r, return_distance=False)
+// (datasets/datasets_ws_kitti360.py:613-618 soft positives, :740-745 hard positives; copies in datasets_ws_nuscenes.py).
+// fp64 like sklearn: a database point is a neighbour iff sum_c (x_c - q_c)^2 <= r^2.  One warp per query scans the database
+// coalesced; FILL = false counts, FILL = true writes the ids in ascending order at the query's CSR offset (so the result
+// feeds K5 directly).  nq x n fp64 pair tests: ~1 ms at cfg2 size, no spatial index needed.
+template <bool FILL>
+__global__ void __launch_bounds__(128) radius_kernel(const double* __restrict__ db, int64_t n, int dim, const double* __restrict__ q,
+                                                     int64_t nq, double r2, int64_t* __restrict__ counts,
+                                                     const int64_t* __restrict__ offsets, int64_t* __restrict__ ids) {
+    const int lane = threadIdx.x & 31;
+    const int64_t qi = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    double qc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) qc[c] = c < dim ? q[qi * dim + c] : 0.0;
+    int64_t run = 0;
+    const int64_t out0 = FILL ? offsets[qi] : 0;
+    for (int64_t base = 0; base < n; base += 32) {
+        const int64_t j = base + lane;
+        bool hit = false;
+        if (j < n) {
+            double d2 = 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (c < dim) {
+                    const double t = db[j * dim + c] - qc[c];
+                    d2 += t * t;
+                }
+            }
+            hit = d2 <= r2;
+        }
+        const unsigned m = __ballot_sync(kFull, hit);
+        if (FILL && hit) ids[out0 + run + __popc(m & ((1u << lane) - 1u))] = j;
+        run += __popc(m);
+    }
+    if (!FILL && lane == 0) counts[qi] = run;
+}
+
+cudaError_t launch_radius(bool fill, const double* db, int64_t n, int dim, const double* q, int64_t nq, double r2, int64_t* counts,
+                          const int64_t* offsets, int64_t* ids, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    const unsigned blocks = static_cast<unsigned>((nq + 3) / 4);
+    if (fill) radius_kernel<true><<<blocks, 128, 0, st>>>(db, n, dim, q, nq, r2, counts, offsets, ids);
+    else radius_kernel<false><<<blocks, 128, 0, st>>>(db, n, dim, q, nq, r2, counts, offsets, ids);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------ launchers
 cudaError_t launch_mask_select(const float* Dp, const int64_t* Ip, int kp, const int64_t* ex_off, const int64_t* ex_ids, int64_t nq, int k,
                                float* D, int64_t* I, cudaStream_t st) {

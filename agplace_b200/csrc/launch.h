@@ -145,6 +145,9 @@ cudaError_t launch_best_of_lists(const float* xq, const float* rows, int d, cons
 cudaError_t launch_gather_rows(const float* x, const int* list, int n, int d, float* out, cudaStream_t st);
 cudaError_t launch_scatter_results(const float* Dt, const int64_t* It, const int* list, int n, int k, float* D, int64_t* I, cudaStream_t st);
 cudaError_t launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st);
+// fp64 radius neighbours (k_misc.cu:radius_kernel): fill = false -> counts[nq]; fill = true -> ids at the CSR offsets, ascending
+cudaError_t launch_radius(bool fill, const double* db, int64_t n, int dim, const double* q, int64_t nq, double r2, int64_t* counts,
+                          const int64_t* offsets, int64_t* ids, cudaStream_t st);
 cudaError_t launch_diff_small(const float* xq, int nq, const float* xb, int64_t n, int d, float* dist, int64_t ld, int num_sms,
                               int ip, cudaStream_t st);
 cudaError_t launch_dist_simt(const float* xq, const float* qn, int nq, const float* xb, const float* yn, int64_t n, int d, float* dist,

@@ -322,3 +322,34 @@ def recall_hits(predictions, positives_per_query, recall_values, device=None):
                                    ctypes.c_void_p(offsets.ctypes.data), ctypes.c_void_p(ids.ctypes.data),
                                    ctypes.c_void_p(ns.ctypes.data), len(ns), ctypes.c_void_p(hits.ctypes.data)), "agp_recall_at_n")
     return hits
+
+
+def radius_neighbors(database_xy, queries_xy, radius, device=None, return_csr=False):
+    """GPU restatement of the reference's positives computation,
+    ``NearestNeighbors().fit(database_utms).radius_neighbors(queries_utms, radius=r, return_distance=False)``
+    (datasets/datasets_ws_kitti360.py:613-618, 740-745): fp64, inclusive radius.  Returns an object array of int64 id
+    arrays like sklearn (ids ascending; sklearn's order is the tree's), or ``(offsets, ids)`` CSR with
+    ``return_csr=True`` -- the layout ``recall_hits`` and the C ABI consume."""
+    lib = _lib.load()
+    device = default_device() if device is None else int(device)
+    db = np.ascontiguousarray(database_xy, dtype=np.float64)
+    q = np.ascontiguousarray(queries_xy, dtype=np.float64)
+    assert db.ndim == 2 and q.ndim == 2 and db.shape[1] == q.shape[1]
+    n, dim = db.shape
+    nq = q.shape[0]
+    counts = np.zeros(nq, dtype=np.int64)
+    _lib.check(lib.agp_radius_count(device, n, dim, ctypes.c_void_p(db.ctypes.data), nq, ctypes.c_void_p(q.ctypes.data),
+                                    float(radius), ctypes.c_void_p(counts.ctypes.data)), "agp_radius_count")
+    offsets = np.zeros(nq + 1, dtype=np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    ids = np.empty(max(int(offsets[-1]), 1), dtype=np.int64)
+    _lib.check(lib.agp_radius_fill(device, n, dim, ctypes.c_void_p(db.ctypes.data), nq, ctypes.c_void_p(q.ctypes.data),
+                                   float(radius), ctypes.c_void_p(offsets.ctypes.data), ctypes.c_void_p(ids.ctypes.data)),
+               "agp_radius_fill")
+    ids = ids[: int(offsets[-1])]
+    if return_csr:
+        return offsets, ids
+    out = np.empty(nq, dtype=object)
+    for i in range(nq):
+        out[i] = ids[offsets[i]:offsets[i + 1]]
+    return out

@@ -159,6 +159,20 @@ AGP_API int agp_merge_topk(int device, void* cuda_stream, int64_t nq, int k, int
 AGP_API int agp_recall_at_n(int device, void* cuda_stream, const int64_t* I, int mem_kind, int64_t nq, int k,
                     const int64_t* pos_offsets, const int64_t* pos_ids, const int* ns, int n_ns, int64_t* hit_counts);
 
+/* Radius neighbours in the UTM plane -- the reference's
+ *   knn = NearestNeighbors(); knn.fit(database_utms); knn.radius_neighbors(queries_utms, radius=r, return_distance=False)
+ * (datasets/datasets_ws_kitti360.py:613-618 soft positives, :740-745 hard positives; datasets_ws_nuscenes.py:907-912,
+ * 1032-1037), which produces the positives_per_query that recall@N and the mining consume.  fp64 like sklearn
+ * (neighbour iff sum_c (x_c - q_c)^2 <= r^2), HOST arrays, two phases so the caller sizes the CSR:
+ *   agp_radius_count -> counts[nq];   offsets = exclusive prefix sum (offsets[nq] = total);
+ *   agp_radius_fill  -> ids[offsets[q] .. offsets[q+1]) = the neighbours of query q, ascending
+ * (sklearn returns them in tree order; the reference only uses them as sets and through argmin/setdiff1d results that do
+ * not depend on the order except on exact feature-distance ties).  dim in 1..8 (the reference uses 2). */
+AGP_API int agp_radius_count(int device, int64_t n_db, int dim, const double* db, int64_t nq, const double* q, double radius,
+                             int64_t* counts);
+AGP_API int agp_radius_fill(int device, int64_t n_db, int dim, const double* db, int64_t nq, const double* q, double radius,
+                            const int64_t* offsets, int64_t* ids);
+
 /* Diagnostics. */
 AGP_API const char* agp_last_error(void);
 AGP_API int agp_device_count(void);
