@@ -25,6 +25,12 @@ import threading
 import time
 from pathlib import Path
 
+# The reference arm must use every host thread it can: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+# throttle the CPU restatement (OpenBLAS sgemm + OpenMP heaps) to one core -- undo that before numpy/OpenBLAS load.
+if "reference" in sys.argv[1:] and any(a.startswith("--impl") for a in sys.argv[1:]):
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
