@@ -16,13 +16,13 @@ xq = rng.standard_normal((nq, d)).astype(np.float32); xq /= np.linalg.norm(xq, a
 ix = agp.IndexFlatL2(d, precision="fp16_screen"); ix.add(xb)
 xq_d = torch.from_numpy(xq).cuda()
 
-variants = [dict(), dict(PF=2), dict(PF=4), dict(PF=8), dict(PF=16), dict(STAGES=4), dict(STAGES=3)]
+variants = [dict(), dict(FLAGS=1), dict(FLAGS=4), dict(FLAGS=8), dict(E=16), dict(SCHED=6), dict(SCHED=10)]
 variants = variants + variants          # second pass: order / warm-up effects show as a difference between the passes
 if len(sys.argv) > 2:
     variants = [dict()] + [json.loads(a) for a in sys.argv[2:]]
 ref = None
 for v in variants:
-    for key in ("FLAGS", "E", "SCHED", "PF", "STAGES"):
+    for key in ("FLAGS", "E", "SCHED", "STAGES"):
         os.environ.pop("AGP_SCREEN_" + key, None)
     for key, val in v.items():
         os.environ["AGP_SCREEN_" + key] = str(val)

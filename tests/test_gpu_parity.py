@@ -446,6 +446,35 @@ def test_engine_reproduces_the_published_output_of_the_faiss_tutorial(precision)
     assert ok, msg
 
 
+def test_screen_variants_return_identical_results(monkeypatch):
+    """The screen kernel's alternative code paths -- the branchy scan (also the fallback when a candidate bundle
+    straddles a 4 GB line), rounds without the pair exchange, sweeps without the first-tile bootstrap, 512-slot lists --
+    are selected per search through AGP_SCREEN_FLAGS / AGP_SCREEN_E; the exact finish makes every variant return the
+    same bits.  Shapes cover whole waves, the split remainder ("wide" groups) and a ragged last tile."""
+    rng = np.random.default_rng(23)
+    for (n, nq, d, k) in [(30011, 19200, 64, 20), (9000, 1500, 128, 50), (5000, 300, 32, 100)]:
+        xb = rng.standard_normal((n, d)).astype(np.float32)
+        xq = rng.standard_normal((nq, d)).astype(np.float32)
+        ix = agp().IndexFlatL2(d, precision="fp16_screen"); ix.add(xb)
+        monkeypatch.delenv("AGP_SCREEN_FLAGS", raising=False)
+        monkeypatch.delenv("AGP_SCREEN_E", raising=False)
+        D0, I0 = ix.search(xq, k)
+        sample = np.arange(0, nq, max(1, nq // 200))
+        Dr, Ir = orc.knn_fp32(xq[sample], xb, k)
+        ok, msg = orc.compare_knn(D0[sample], I0[sample], Dr, Ir, xq=xq[sample], xb=xb, abs_floor_eps=8 * 2.0 ** -24)
+        assert ok, msg
+        for flags, e in [(1, None), (4, None), (8, None), (13, None), (0, 16), (5, 16)]:
+            monkeypatch.setenv("AGP_SCREEN_FLAGS", str(flags))
+            if e is None:
+                monkeypatch.delenv("AGP_SCREEN_E", raising=False)
+            else:
+                monkeypatch.setenv("AGP_SCREEN_E", str(e))
+            D, I = ix.search(xq, k)
+            np.testing.assert_array_equal(I, I0, err_msg=f"flags={flags} E={e} shape={(n, nq, d, k)}")
+            np.testing.assert_array_equal(D, D0)
+        assert ix.get_stats()[1] == 0
+
+
 def test_native_library_was_used():
     from agplace_b200 import _lib
     before = _lib.kernel_launches()
