@@ -183,8 +183,8 @@ __device__ __forceinline__ void sc_compact_lanes(uint64_t* wbuf, int& cnt, float
         }
     }
     // smallest bucket edge with at least k entries at or below it
-    // ... and, for the group-wide bound, with at least kh = ceil(k / L): if ALL L lists of a group have that many entries
-    // at or below x, the query has k rows at or below x (see the caller).
+    // ... and, for the pair bound, with at least kh = ceil(k / 2): if BOTH halves have that many entries at or below x,
+    // the query has k rows at or below x (see the caller).
     float pd = inf, pdh = inf;
     int cum = 0;
     bool found = false, foundh = false;
@@ -443,15 +443,13 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             // a row is a candidate iff dis~ < lim = (best known bound of the k-th smallest dis~) + 2 band
             float lim = valid ? inf : -inf;
             uint32_t* my_gthr = valid ? p.gthr + q : nullptr;
-            // Group-wide bound: hthr[list] = bound of the ceil(k/L)-th best of one list; the max over the L lists of a group
-            // bounds the query's k-th best over everything the whole group has swept -- far tighter than any single list's
-            // own k-th.  Group = the two column halves of this (query, range); for a split remainder with few ranges, ALL
-            // 2 x ranges lists of the query (they run concurrently on different clusters).
-            const bool wide = it.pt >= p.n_full_items && 2 * p.rem_splits <= 16;
-            const int L = wide ? 2 * p.rem_splits : 2;
-            const int kh = (p.k + L - 1) / L;
+            // Pair bound: hthr[list] = bound of the ceil(k/2)-th best of one column half; the max over the two halves of this
+            // (query, range) bounds the query's k-th best over everything both have swept -- far tighter than a single
+            // list's own k-th.  (Groups of all 2 x ranges lists of a split query were tried: the max over many lists of a
+            // low order statistic is too noisy; pair groups plus the exchange inside a round measured faster everywhere.)
+            const int kh = (p.k + 1) >> 1;
             uint32_t* my_hthr = valid ? p.hthr + (sc_list_base(p, q) + it.split * 2 + half) : nullptr;
-            const uint32_t* grp_hthr = valid ? p.hthr + (sc_list_base(p, q) + (wide ? 0 : it.split * 2)) : nullptr;
+            const uint32_t* grp_hthr = valid ? p.hthr + (sc_list_base(p, q) + it.split * 2) : nullptr;
             int* my_ovf = valid ? p.ovf + q : nullptr;
             const size_t slot = sc_list_base(p, q < p.nq ? q : 0) + it.split * 2 + half;
             uint64_t* wbuf = p.partial + (sc_list_base(p, (qt * TC_BM + g * 32) >> 5, 8) + it.split * 2 + half) * (32 * CAP);
@@ -465,10 +463,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             int next_sched = 1, sched_base = 1, round = 0;
             for (int t = it.t0; t < it.t1; ++t) {
                 if (my_gthr) {
-                    float grp_bound = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (j < L) grp_bound = fmaxf(grp_bound, __uint_as_float(__ldcg(grp_hthr + j)));
+                    const float grp_bound = fmaxf(__uint_as_float(__ldcg(grp_hthr)), __uint_as_float(__ldcg(grp_hthr + 1)));
                     lim = fminf(lim, fminf(__uint_as_float(__ldcg(my_gthr)), grp_bound) + band2);
                 }
                 float thr = (lim - qn) * invW;              // acc' > thr  <=>  dis~ < lim
@@ -628,11 +623,11 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     sched_base = nb;
                     next_sched = nb + (round >= 3 ? ((cluster_id & 7) * width) >> 4 : 0);
                     // with the pair exchange both warps of a lane group must enter the round (named barrier inside)
-                    if (!booted) do_compact = do_compact || (f_xchg && !wide) || __any_sync(kFull, cnt > p.k + 8);
+                    if (!booted) do_compact = do_compact || f_xchg || __any_sync(kFull, cnt > p.k + 8);
                 }
                 if (do_compact) {
                     long long c3 = p.dbg ? clock64() : 0;
-                    float* xc = (scheduled && f_xchg && !wide) ? xchg_all + (warp - 2) * 32 : nullptr;
+                    float* xc = (scheduled && f_xchg) ? xchg_all + (warp - 2) * 32 : nullptr;
                     float* xp = xchg_all + ((warp - 2) ^ 4) * 32;
                     sc_compact_lanes<E>(wbuf, cnt, lim, band2, lane, p.k, kh, my_gthr, my_hthr, my_ovf, xc, xp, 1 + g);
                     if (p.dbg) { t_compact += clock64() - c3; n_compact += 1; if (t == it.t0) t_compact1 += clock64() - c3; }
