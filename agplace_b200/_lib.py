@@ -37,6 +37,7 @@ SIGNATURES = {
     "agp_index_search_subset": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "agp_best_of_lists": (c_int, [c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "agp_merge_topk": (c_int, [c_int, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "agp_merge_topk_metric": (c_int, [c_int, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "agp_recall_at_n": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "agp_radius_count": (c_int, [c_int, c_int64, c_int, c_void_p, c_int64, c_void_p, c_double, c_void_p]),
     "agp_radius_fill": (c_int, [c_int, c_int64, c_int, c_void_p, c_int64, c_void_p, c_double, c_void_p, c_void_p]),

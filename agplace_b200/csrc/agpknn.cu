@@ -1160,6 +1160,13 @@ int agp_best_of_lists(int device, int64_t nq, int d, const float* xq, const floa
 
 int agp_merge_topk(int device, void* stream, int64_t nq, int k, int n_lists, const float* D_lists, int64_t d_list_stride,
                    const int64_t* I_lists, int64_t i_list_stride, int64_t id_bound, float* D_out, int64_t* I_out) {
+    return agp_merge_topk_metric(device, stream, nq, k, n_lists, D_lists, d_list_stride, I_lists, i_list_stride, id_bound, AGP_METRIC_L2,
+                                 D_out, I_out);
+}
+
+int agp_merge_topk_metric(int device, void* stream, int64_t nq, int k, int n_lists, const float* D_lists, int64_t d_list_stride,
+                          const int64_t* I_lists, int64_t i_list_stride, int64_t id_bound, int metric, float* D_out, int64_t* I_out) {
+    if (metric != AGP_METRIC_L2 && metric != AGP_METRIC_INNER_PRODUCT) return set_err(AGP_EINVAL, "unknown metric %d", metric);
     if (k <= 0 || k > AGP_MAX_K) return set_err(AGP_EINVAL, "k=%d out of range 1..%d", k, AGP_MAX_K);
     if (nq < 0 || n_lists < 0) return set_err(AGP_EINVAL, "negative size");
     if (nq == 0) return 0;
@@ -1168,7 +1175,7 @@ int agp_merge_topk(int device, void* stream, int64_t nq, int k, int n_lists, con
     CK(cudaSetDevice(device));
     const bool by_id = id_bound > 0 && id_bound <= 0x100000000LL;
     return DISPATCH_E32(k, launch_merge_lists, D_lists, d_list_stride, I_lists, i_list_stride, by_id, nq, n_lists, k, D_out, I_out,
-                        static_cast<cudaStream_t>(stream));
+                        metric == AGP_METRIC_INNER_PRODUCT ? 1 : 0, static_cast<cudaStream_t>(stream));
 }
 
 int agp_recall_at_n(int device, void* stream_v, const int64_t* I, int mem_kind, int64_t nq, int k, const int64_t* pos_offsets,

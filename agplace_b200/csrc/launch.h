@@ -114,7 +114,7 @@ cudaError_t launch_merge_keys(const uint64_t* partial, int64_t nq, int n_lists, 
                               int ip, cudaStream_t st);
 template <int E>
 cudaError_t launch_merge_lists(const float* Din, int64_t d_stride, const int64_t* Iin, int64_t i_stride, bool by_id, int64_t nq,
-                               int n_lists, int k, float* D, int64_t* I, cudaStream_t st);
+                               int n_lists, int k, float* D, int64_t* I, int ip, cudaStream_t st);
 
 // top-k of each query's own candidate list (positions), exact fp32 difference form (merge.cuh:subset_topk_kernel)
 template <int E>

@@ -67,7 +67,7 @@ template <int E>
 __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restrict__ Din, int64_t d_stride,
                                                           const int64_t* __restrict__ Iin, int64_t i_stride, bool by_id,
                                                           int64_t nq, int n_lists, int k, float* __restrict__ D,
-                                                          int64_t* __restrict__ I) {
+                                                          int64_t* __restrict__ I, int ip) {
     const int lane = threadIdx.x & 31;
     const int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
@@ -76,14 +76,16 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
         const int64_t g = i / k, r = i - g * k;
         const int64_t id = Iin[g * i_stride + q * k + r];
         if (id < 0) return kEmptyKey;
-        return pack_key(Din[g * d_stride + q * k + r], by_id ? static_cast<uint32_t>(id) : static_cast<uint32_t>(i));
+        // inner-product lists hold products, best = largest: order by -<q, y> through the sign-aware key
+        const uint32_t payload = by_id ? static_cast<uint32_t>(id) : static_cast<uint32_t>(i);
+        return ip ? pack_key_signed(-Din[g * d_stride + q * k + r], payload) : pack_key(Din[g * d_stride + q * k + r], payload);
     });
 #pragma unroll
     for (int j = 0; j < E; ++j) {
         const int i = j * 32 + lane;
         if (i < k) {
             const bool empty = key[j] == kEmptyKey;
-            D[q * k + i] = empty ? kFltMax : key_dist(key[j]);
+            D[q * k + i] = ip ? (empty ? -kFltMax : -key_value_signed(key[j])) : (empty ? kFltMax : key_dist(key[j]));
             int64_t id = -1;
             if (!empty) {
                 const uint32_t pl = key_idx(key[j]);
@@ -104,10 +106,10 @@ cudaError_t launch_merge_keys(const uint64_t* partial, int64_t nq, int n_lists, 
 
 template <int E>
 cudaError_t launch_merge_lists(const float* Din, int64_t d_stride, const int64_t* Iin, int64_t i_stride, bool by_id, int64_t nq,
-                               int n_lists, int k, float* D, int64_t* I, cudaStream_t st) {
+                               int n_lists, int k, float* D, int64_t* I, int ip, cudaStream_t st) {
     constexpr int warps = 4;
     merge_lists_kernel<E><<<static_cast<unsigned>((nq + warps - 1) / warps), warps * 32, 0, st>>>(Din, d_stride, Iin, i_stride, by_id, nq,
-                                                                                                  n_lists, k, D, I);
+                                                                                                  n_lists, k, D, I, ip);
     return cudaGetLastError();
 }
 

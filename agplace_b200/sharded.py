@@ -21,10 +21,10 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .index import IndexFlatL2, _is_torch
+from .index import METRIC_INNER_PRODUCT, METRIC_L2, IndexFlatIP, IndexFlatL2, _is_torch
 
 
-def _cuda_merge(D_lists, d_stride, I_lists, i_stride, nq, k, n_lists, id_bound):
+def _cuda_merge(D_lists, d_stride, I_lists, i_stride, nq, k, n_lists, id_bound, metric=METRIC_L2):
     """K4 across shards on the GPU through the C ABI (device tensors in, device tensors out)."""
     import torch
     if not D_lists.is_cuda:
@@ -35,9 +35,9 @@ def _cuda_merge(D_lists, d_stride, I_lists, i_stride, nq, k, n_lists, id_bound):
     I = torch.empty((nq, k), dtype=torch.int64, device=dev)
     lib = _lib.load()
     stream = torch.cuda.current_stream(dev).cuda_stream
-    _lib.check(lib.agp_merge_topk(dev.index, ctypes.c_void_p(stream), nq, k, n_lists, ctypes.c_void_p(D_lists.data_ptr()), d_stride,
-                                  ctypes.c_void_p(I_lists.data_ptr()), i_stride, id_bound, ctypes.c_void_p(D.data_ptr()),
-                                  ctypes.c_void_p(I.data_ptr())), "agp_merge_topk")
+    _lib.check(lib.agp_merge_topk_metric(dev.index, ctypes.c_void_p(stream), nq, k, n_lists, ctypes.c_void_p(D_lists.data_ptr()),
+                                         d_stride, ctypes.c_void_p(I_lists.data_ptr()), i_stride, id_bound, int(metric),
+                                         ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr())), "agp_merge_topk_metric")
     return D, I
 
 
@@ -48,6 +48,9 @@ def shard_bounds(n, world):
 
 
 class ShardedIndexFlatL2:
+    _metric = METRIC_L2
+    _local_cls = IndexFlatL2
+
     def __init__(self, d, group=None, device=None, precision=None, shard="db", index_cls=None, merge_fn=None,
                  result_device=None):
         import torch.distributed as dist
@@ -61,11 +64,11 @@ class ShardedIndexFlatL2:
         self.world = dist.get_world_size(group)
         self.shard = shard
         self.is_trained = True
-        self.metric_type = 1
+        self.metric_type = self._metric
         self._ntotal = 0
-        index_cls = index_cls or IndexFlatL2
+        index_cls = index_cls or self._local_cls
         kwargs = {}
-        if index_cls is IndexFlatL2:
+        if index_cls is self._local_cls:
             kwargs = dict(device=device, precision=precision)
         self.local = index_cls(self.d, **kwargs)
         self._merge = merge_fn or _cuda_merge
@@ -194,7 +197,10 @@ class ShardedIndexFlatL2:
             # int64 view must start 8-byte aligned: d_bytes is a multiple of 8
             I_lists = recv.view(torch.int64)[d_bytes // 8:]
             id_bound = self._ntotal
-            Dg, Ig = self._merge(D_lists, stride // 4, I_lists, stride // 8, nq, k, self.world, id_bound)
+            if self._metric == METRIC_L2:
+                Dg, Ig = self._merge(D_lists, stride // 4, I_lists, stride // 8, nq, k, self.world, id_bound)
+            else:
+                Dg, Ig = self._merge(D_lists, stride // 4, I_lists, stride // 8, nq, k, self.world, id_bound, self._metric)
 
         if D is not None:
             (D if _is_torch(D) else torch.from_numpy(D)).copy_(Dg)
@@ -207,3 +213,11 @@ class ShardedIndexFlatL2:
         if as_numpy and I is None:
             Ig = Ig.cpu().numpy()
         return Dg, Ig
+
+
+class ShardedIndexFlatIP(ShardedIndexFlatL2):
+    """Row- or query-sharded ``IndexFlatIP``: same exchange, the merge orders the per-shard lists by descending product
+    (ties by global id) and pads with ``(-3.4028235e38, -1)``."""
+
+    _metric = METRIC_INNER_PRODUCT
+    _local_cls = IndexFlatIP

@@ -153,6 +153,12 @@ AGP_API int agp_merge_topk(int device, void* cuda_stream, int64_t nq, int k, int
                            int64_t d_list_stride, const int64_t* I_lists, int64_t i_list_stride, int64_t id_bound,
                            float* D_out, int64_t* I_out);
 
+/* The same merge for lists of either metric: AGP_METRIC_INNER_PRODUCT lists hold products, descending, padded
+ * (-3.4028235e38, -1) -- the per-shard results of row-sharded IndexFlatIP indexes. */
+AGP_API int agp_merge_topk_metric(int device, void* cuda_stream, int64_t nq, int k, int n_lists, const float* D_lists,
+                                  int64_t d_list_stride, const int64_t* I_lists, int64_t i_list_stride, int64_t id_bound,
+                                  int metric, float* D_out, int64_t* I_out);
+
 /* Recall@N  -- reference test.py:72-83.  I: nq x k int64 (host or device).  positives in CSR form:
  * pos_offsets[nq+1], pos_ids (unsorted, host or device like I).  hit_counts[i] = number of
  * queries whose first correct prediction has rank < ns[i]  (recall = 100 * hits / nq). */

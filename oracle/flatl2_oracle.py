@@ -263,6 +263,8 @@ class IndexFlatL2:
         self._chunks = []
         self._xb = np.empty((0, self.d), dtype=np.float32)
 
+    _knn = staticmethod(lambda x, xb, k: knn_fp32(x, xb, k))
+
     def add(self, x):
         n, d = x.shape
         assert d == self.d
@@ -287,7 +289,7 @@ class IndexFlatL2:
         x = np.ascontiguousarray(x, dtype="float32")
         assert d == self.d
         assert k > 0
-        Dn, In = knn_fp32(x, self._base(), int(k))
+        Dn, In = self._knn(x, self._base(), int(k))
         if D is None:
             D = Dn
         else:
@@ -299,6 +301,16 @@ class IndexFlatL2:
             assert I.shape == (n, k)
             I[...] = In
         return D, I
+
+
+class IndexFlatIP(IndexFlatL2):
+    """Restatement of ``faiss.IndexFlatIP`` (reference anyloc/utilities.py:446): same surface, :func:`knn_ip_fp32`."""
+
+    _knn = staticmethod(lambda x, xb, k: knn_ip_fp32(x, xb, k))
+
+    def __init__(self, d):
+        super().__init__(d)
+        self.metric_type = 0  # faiss.METRIC_INNER_PRODUCT
 
 
 # --------------------------------------------------------------------------------------

@@ -15,19 +15,21 @@ def reference_recall_loop(predictions, positives_per_query, recall_values):
     return recalls / len(predictions) * 100
 
 
-def numpy_merge(D_lists, d_stride, I_lists, i_stride, nq, k, n_lists, id_bound):
-    """CPU checker for the cross-shard merge (same argument convention as sharded._cuda_merge)."""
+def numpy_merge(D_lists, d_stride, I_lists, i_stride, nq, k, n_lists, id_bound, metric=1):
+    """CPU checker for the cross-shard merge (same argument convention as sharded._cuda_merge); metric 0 = inner
+    product (largest first, padding -FLT_MAX), 1 = L2."""
     import torch
     Dl = D_lists.cpu().numpy().reshape(-1)
     Il = I_lists.cpu().numpy().reshape(-1)
-    D = np.full((nq, k), np.float32(3.4028234663852886e38), np.float32)
+    sign = -1.0 if metric == 0 else 1.0
+    D = np.full((nq, k), np.float32(sign * 3.4028234663852886e38), np.float32)
     I = np.full((nq, k), -1, np.int64)
     for q in range(nq):
         ds = np.concatenate([Dl[g * d_stride + q * k: g * d_stride + (q + 1) * k] for g in range(n_lists)])
         ids = np.concatenate([Il[g * i_stride + q * k: g * i_stride + (q + 1) * k] for g in range(n_lists)])
         keep = ids >= 0
         ds, ids = ds[keep], ids[keep]
-        order = np.lexsort((ids, ds))[:k]
+        order = np.lexsort((ids, sign * ds))[:k]
         D[q, :len(order)] = ds[order]
         I[q, :len(order)] = ids[order]
     return torch.from_numpy(D), torch.from_numpy(I)

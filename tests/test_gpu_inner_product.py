@@ -148,3 +148,37 @@ def test_faiss_style_helpers_and_l2_only_entry_points():
         ix.search_subset(np.zeros((1, 8), np.float32), 1, [np.array([0])])
     with pytest.raises(RuntimeError):
         a.IndexFlatIP(8, precision="3xtf32")
+
+
+def test_virtual_shards_merge_equals_single_inner_product_index():
+    """agp_merge_topk_metric over per-shard IndexFlatIP results (what ShardedIndexFlatIP exchanges) = one index."""
+    import ctypes
+    import torch
+    from agplace_b200 import _lib
+    from agplace_b200.sharded import shard_bounds
+    rng = np.random.default_rng(9)
+    n, nq, d, k, G = 3001, 130, 24, 40, 3
+    xb = rng.integers(-4, 5, size=(n, d)).astype(np.float32)          # lattice: exact ties across shards
+    xq = rng.integers(-4, 5, size=(nq, d)).astype(np.float32)
+    single = agp().IndexFlatIP(d); single.add(xb)
+    Ds, Is = single.search(xq, k)
+    xq_dev = torch.from_numpy(xq).cuda()
+    Dl = torch.empty((G, nq, k), dtype=torch.float32, device="cuda")
+    Il = torch.empty((G, nq, k), dtype=torch.int64, device="cuda")
+    keep = []
+    for g, (a, b) in enumerate(shard_bounds(n, G)):
+        sh = agp().IndexFlatIP(d); sh.add(xb[a:b]); sh.set_id_base(a)
+        sh.search(xq_dev, k, D=Dl[g], I=Il[g])
+        keep.append(sh)
+    D = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    I = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    lib = _lib.load()
+    _lib.check(lib.agp_merge_topk_metric(0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), nq, k, G,
+                                         ctypes.c_void_p(Dl.data_ptr()), nq * k, ctypes.c_void_p(Il.data_ptr()), nq * k, n, 0,
+                                         ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr())), "agp_merge_topk_metric")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(D.cpu().numpy(), Ds)
+    np.testing.assert_array_equal(I.cpu().numpy(), Is)
+    Dr, Ir = orc.knn_ip_fp32(xq, xb, k)
+    np.testing.assert_array_equal(Is, Ir)
+    np.testing.assert_array_equal(Ds, Dr)

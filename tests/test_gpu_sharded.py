@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, shard, out_dir):
+def _worker(rank, world, port, shard, out_dir, metric="l2"):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, str(ROOT))
@@ -26,11 +26,11 @@ def _worker(rank, world, port, shard, out_dir):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        from agplace_b200.sharded import ShardedIndexFlatL2
+        from agplace_b200.sharded import ShardedIndexFlatIP, ShardedIndexFlatL2
         rng = np.random.default_rng(5)
         xb = rng.standard_normal((30011, 128)).astype(np.float32)
         xq = rng.standard_normal((777, 128)).astype(np.float32)
-        ix = ShardedIndexFlatL2(128, device=rank, shard=shard)
+        ix = (ShardedIndexFlatIP if metric == "ip" else ShardedIndexFlatL2)(128, device=rank, shard=shard)
         ix.add(xb[:20000]); ix.add(xb[20000:])
         D, I = ix.search(xq, 40)                                   # numpy in -> numpy out
         Dt, It = ix.search(torch.from_numpy(xq).cuda(), 100)       # CUDA in -> CUDA out
@@ -70,3 +70,26 @@ def test_nccl_sharded_equals_single(tmp_path, shard):
             a, b = shard_bounds(len(xq), world)[r]
             np.testing.assert_array_equal(got["Il"], Is[a:b])
             np.testing.assert_array_equal(got["Dl"], Ds[a:b])
+
+
+def test_nccl_sharded_inner_product_equals_single(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, "db", str(tmp_path), "ip"), nprocs=world, join=True)
+    import agplace_b200 as agp
+    rng = np.random.default_rng(5)
+    xb = rng.standard_normal((30011, 128)).astype(np.float32)
+    xq = rng.standard_normal((777, 128)).astype(np.float32)
+    single = agp.IndexFlatIP(128, device=0)
+    single.add(xb)
+    Ds, Is = single.search(xq, 40)
+    Ds2, Is2 = single.search(xq, 100)
+    for r in range(world):
+        got = np.load(tmp_path / f"r{r}.npz")
+        np.testing.assert_array_equal(got["I"], Is)
+        np.testing.assert_array_equal(got["D"], Ds)
+        np.testing.assert_array_equal(got["I2"], Is2)
+        np.testing.assert_array_equal(got["D2"], Ds2)

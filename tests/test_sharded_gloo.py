@@ -20,6 +20,46 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _worker_ip(rank, world, port, shard, out_dir):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from agplace_b200.sharded import ShardedIndexFlatIP
+        from oracle import flatl2_oracle as orc
+        from tests.helpers import numpy_merge
+        rng = np.random.default_rng(78)
+        xb = rng.integers(-5, 6, size=(401, 12)).astype(np.float32)      # lattice: exact product ties across shards
+        xq = rng.integers(-5, 6, size=(33, 12)).astype(np.float32)
+        ix = ShardedIndexFlatIP(12, shard=shard, index_cls=orc.IndexFlatIP, merge_fn=numpy_merge,
+                                result_device=torch.device("cpu"))
+        assert ix.metric_type == 0
+        ix.add(xb[:250]); ix.add(xb[250:])
+        D, I = ix.search(xq, 9)
+        D2, I2 = ix.search(xq, 450)                                      # k > ntotal: (-FLT_MAX, -1) padding survives the merge
+        np.savez(Path(out_dir) / f"r{rank}.npz", D=D, I=I, D2=D2, I2=I2)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shard", ["db", "query"])
+def test_two_rank_sharded_inner_product_equals_single(tmp_path, shard):
+    world, port = 2, _free_port()
+    mp.spawn(_worker_ip, args=(world, port, shard, str(tmp_path)), nprocs=world, join=True)
+    from oracle import flatl2_oracle as orc
+    rng = np.random.default_rng(78)
+    xb = rng.integers(-5, 6, size=(401, 12)).astype(np.float32)
+    xq = rng.integers(-5, 6, size=(33, 12)).astype(np.float32)
+    Dr, Ir = orc.knn_ip_fp32(xq, xb, 9)
+    Dr2, Ir2 = orc.knn_ip_fp32(xq, xb, 450)
+    for r in range(world):
+        got = np.load(tmp_path / f"r{r}.npz")
+        np.testing.assert_array_equal(got["D"], Dr)
+        np.testing.assert_array_equal(got["I"], Ir)       # ties across shards resolve by global id
+        np.testing.assert_array_equal(got["D2"], Dr2)
+        np.testing.assert_array_equal(got["I2"], Ir2)
+
+
 def _worker(rank, world, port, shard, out_dir):
     sys.path.insert(0, str(ROOT))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
