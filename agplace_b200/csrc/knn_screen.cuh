@@ -268,10 +268,13 @@ __device__ __forceinline__ float sc_pick32(const float (&v)[32], int idx) {
     return x;
 }
 
-template <int E>
+// DBG = true is the instrumented build of the same kernel (cycle counters in p.dbg, AGP_TC_DEBUG=1); the product launch
+// uses DBG = false, which frees the counters' ~20 registers at the 168-register ceiling.
+template <int E, bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_b, const ScreenParams p) {
     constexpr int CAP = 32 * E;
+    const bool dbg_on = DBG && p.dbg != nullptr;
     extern __shared__ uint8_t smem_raw[];
     // identical carve-up in both CTAs of the pair (the dynamic window starts at the same offset in each)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -362,7 +365,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             uint32_t phase = 0, qphase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            long long w_full = 0, w_tempty = 0, t_begin = p.dbg ? clock64() : 0;
+            long long w_full = 0, w_tempty = 0, t_begin = dbg_on ? clock64() : 0;
             for (int item = cluster_id; item < n_items; item += n_clusters) {
                 const ScItem it = sc_decode_item(p, item);
                 if (p.q_resident) {
@@ -371,15 +374,15 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     tc_fence_after();
                 }
                 for (int t = it.t0; t < it.t1; ++t) {
-                    long long c0 = p.dbg ? clock64() : 0;
+                    long long c0 = dbg_on ? clock64() : 0;
                     mbar_wait(&tempty[acc], acc_phase ^ 1);
-                    if (p.dbg) w_tempty += clock64() - c0;
+                    if (dbg_on) w_tempty += clock64() - c0;
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + acc * TC_BN;
                     for (int kc = 0; kc < num_kc; ++kc) {
-                        long long c1 = p.dbg ? clock64() : 0;
+                        long long c1 = dbg_on ? clock64() : 0;
                         mbar_wait(&full[stage], phase);
-                        if (p.dbg) w_full += clock64() - c1;
+                        if (dbg_on) w_full += clock64() - c1;
                         tc_fence_after();
                         const uint32_t sb = smem_u32(ring + stage * stage_bytes);
                         const uint32_t sa = p.q_resident ? smem_u32(q_region + kc * SC_CHUNK_BYTES) : sb + SC_CHUNK_BYTES;
@@ -403,7 +406,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                 }
                 if (p.q_resident) tc_commit_pair(qempty, 0x3);
             }
-            if (p.dbg) {
+            if (dbg_on) {
                 p.dbg[blockIdx.x * 16 + 0] = clock64() - t_begin;
                 p.dbg[blockIdx.x * 16 + 1] = w_full;
                 p.dbg[blockIdx.x * 16 + 2] = w_tempty;
@@ -419,7 +422,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         const float sy = __uint_as_float(__ldg(p.dbstats + 2));
         int acc = 0;
         uint32_t acc_phase = 0;
-        long long w_tfull = 0, t_compact = 0, n_compact = 0, e_begin = p.dbg ? clock64() : 0;
+        long long w_tfull = 0, t_compact = 0, n_compact = 0, e_begin = dbg_on ? clock64() : 0;
         long long n_hits = 0, t_scan = 0, n_tiles = 0, t_compact1 = 0;
         const bool f_pred_on = (p.flags & 1) == 0;      // AGP_SCREEN_FLAGS bit 0 selects the branchy scan (A/B switch)
         const bool f_xchg = (p.flags & 4) == 0;         // bit 2 turns the pair exchange of the rounds off (A/B switch)
@@ -467,9 +470,9 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     lim = fminf(lim, fminf(__uint_as_float(__ldcg(my_gthr)), grp_bound) + band2);
                 }
                 float thr = (lim - qn) * invW;              // acc' > thr  <=>  dis~ < lim
-                long long c2 = p.dbg ? clock64() : 0;
+                long long c2 = dbg_on ? clock64() : 0;
                 mbar_wait(&tfull[acc], acc_phase);
-                if (p.dbg) w_tfull += clock64() - c2;
+                if (dbg_on) w_tfull += clock64() - c2;
                 tc_fence_after();
                 const uint32_t tcol = tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * TC_BN + half * (TC_BN / 2);
                 const int colbase = t * TC_BN + half * (TC_BN / 2);
@@ -589,7 +592,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     thr = (lim - qn) * invW;
                     booted = true;
                 }
-                long long c4 = p.dbg ? clock64() : 0;
+                long long c4 = dbg_on ? clock64() : 0;
                 const int cnt_before = cnt;
                 // software pipeline over the 4 chunks: the next tcgen05.ld is in flight while this chunk is scanned
                 tmem_ld32(tcol, ra);
@@ -609,7 +612,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                 if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
                 if (f_pred) scan_pred(rb, colbase + 96); else scan(rb, colbase + 96);
                 if (f_pred) cnt = static_cast<int>((wp_lo - static_cast<uint32_t>(wbase)) >> 8);
-                if (p.dbg) { t_scan += clock64() - c4; n_tiles += 1; n_hits += cnt - cnt_before; }
+                if (dbg_on) { t_scan += clock64() - c4; n_tiles += 1; n_hits += cnt - cnt_before; }
                 // Compaction happens only here, between tiles, where nothing but the list state is live.  A tile appends
                 // at most 128 entries to a list, so "room for 128" at every tile start rules out overflow inside a tile.
                 bool do_compact = __any_sync(kFull, cnt > CAP - TC_BN / 2);
@@ -626,18 +629,18 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     if (!booted) do_compact = do_compact || f_xchg || __any_sync(kFull, cnt > p.k + 8);
                 }
                 if (do_compact) {
-                    long long c3 = p.dbg ? clock64() : 0;
+                    long long c3 = dbg_on ? clock64() : 0;
                     float* xc = (scheduled && f_xchg) ? xchg_all + (warp - 2) * 32 : nullptr;
                     float* xp = xchg_all + ((warp - 2) ^ 4) * 32;
                     sc_compact_lanes<E>(wbuf, cnt, lim, band2, lane, p.k, kh, my_gthr, my_hthr, my_ovf, xc, xp, 1 + g);
-                    if (p.dbg) { t_compact += clock64() - c3; n_compact += 1; if (t == it.t0) t_compact1 += clock64() - c3; }
+                    if (dbg_on) { t_compact += clock64() - c3; n_compact += 1; if (t == it.t0) t_compact1 += clock64() - c3; }
                 }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
             if (q < p.nq) p.pcount[slot] = cnt;
         }
-        if (p.dbg && warp == 2 && lane == 0) {
+        if (dbg_on && warp == 2 && lane == 0) {
             p.dbg[blockIdx.x * 16 + 3] = clock64() - e_begin;
             p.dbg[blockIdx.x * 16 + 4] = w_tfull;
             p.dbg[blockIdx.x * 16 + 5] = t_compact;
@@ -656,9 +659,15 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 
 template <int E>
 cudaError_t launch_knn_screen(const CUtensorMap& tq, const CUtensorMap& tb, const ScreenParams& p, int grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(knn_screen_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    knn_screen_kernel<E><<<grid, TC_THREADS, smem, st>>>(tq, tb, p);
+    if (p.dbg) {
+        cudaError_t e = cudaFuncSetAttribute(knn_screen_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        knn_screen_kernel<E, true><<<grid, TC_THREADS, smem, st>>>(tq, tb, p);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(knn_screen_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        knn_screen_kernel<E, false><<<grid, TC_THREADS, smem, st>>>(tq, tb, p);
+    }
     return cudaGetLastError();
 }
 
