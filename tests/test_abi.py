@@ -60,3 +60,21 @@ def test_cubin_is_sm100a_with_tcgen05_and_tma():
     assert "sm_100a" in out
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
         assert mnemonic in out, f"{mnemonic} missing from SASS"
+
+
+def test_faiss_shim_exports_the_names_the_reference_uses():
+    """`import faiss` resolves to the engine when faiss_shim/ is ahead on sys.path: every faiss name AGPlace touches
+    (test.py:27, datasets_ws_*.py, anyloc/utilities.py:446-453, model/aggregation.py:170) must exist there."""
+    import importlib
+    import sys
+    sys.path.insert(0, str(ROOT / "faiss_shim"))
+    try:
+        sys.modules.pop("faiss", None)
+        faiss = importlib.import_module("faiss")
+        for name in ("IndexFlatL2", "IndexFlatIP", "IndexFlat", "METRIC_L2", "METRIC_INNER_PRODUCT", "StandardGpuResources",
+                     "index_cpu_to_gpu", "Kmeans"):
+            assert hasattr(faiss, name), name
+        assert faiss.METRIC_L2 == 1 and faiss.METRIC_INNER_PRODUCT == 0
+    finally:
+        sys.path.remove(str(ROOT / "faiss_shim"))
+        sys.modules.pop("faiss", None)
