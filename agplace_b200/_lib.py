@@ -33,6 +33,8 @@ SIGNATURES = {
     "agp_index_set_profiling": (c_int, [c_void_p, c_int]),
     "agp_index_get_profile": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), c_int]),
     "agp_index_get_stats": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
+    "agp_index_set_knob": (c_int, [c_void_p, c_char_p, c_int]),
+    "agp_index_screen_probe": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "agp_index_search_masked": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "agp_index_search_subset": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "agp_best_of_lists": (c_int, [c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

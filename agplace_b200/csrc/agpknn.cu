@@ -225,7 +225,26 @@ struct Buf {
     size_t bytes = 0;
 };
 
+// A/B and diagnostic switches of one index (agp_index_set_knob).  The product launch path reads no environment variable;
+// switches that change results (skip_epi, skip_mma: bandwidth probes) exist only in -DAGP_DEBUG_KNOBS builds
+// (AGP_BUILD_DEBUG=1 python -m agplace_b200.build), which also seed these from AGP_SCREEN_* / AGP_TC_* at index creation.
+struct Knobs {
+    int screen_flags = 0;     // ScreenParams::flags (bit 0 branchy scan, bit 2 no pair exchange, bit 3 no first-tile bootstrap)
+    int screen_e = 0;         // candidate slots per list / 32 (8 or 16), 0 = automatic
+    int screen_stages = 0;    // operand ring depth, 0 = as many as fit
+    int screen_sched = 8;     // compaction schedule multiplier in quarters (8 = doubling)
+    int tc_e = 0;             // 3xTF32 / 3xFP16 kernel: register budget override
+    int tc_rerank = 1;        // 3xTF32 / 3xFP16: exact re-rank of k + margin candidates
+    int tc_compact_sort = 0;  // 3xTF32 / 3xFP16: exact warp sort instead of the pivot compaction
+    int tc_share_bound = 1;   // 3xTF32 / 3xFP16: share the pruning bound across lists
+    int cycle_counters = 0;   // instrumented kernel build + per-launch cycle report on stderr
+    int skip_epi = 0, skip_mma = 0;   // AGP_DEBUG_KNOBS builds only
+};
+
 struct agp_index {
+    Knobs kn;
+    float* probe_dump = nullptr;      // agp_index_screen_probe: device buffer [nq][probe_ld] for dis~
+    int64_t probe_ld = 0;
     int d = 0, d_pad = 0, device = 0, mode = 0, num_sms = 0;
     int ip = 0;                   // 1: inner-product index (faiss.IndexFlatIP); 0: squared L2
     int64_t ntotal = 0, cap = 0, id_base = 0;
@@ -393,10 +412,9 @@ static int ensure_screen_plane(agp_index* ix) {
 // ------------------------------------------------------------------------------------------ dispatch helpers
 // register budget of the fused epilogue: 32*E candidate slots with enough slack above k that the
 // reservoir is compacted rarely (slots - 32 - k new admissions per sort); E <= 16
-static int tc_regs_for_k(int k) {
-    const char* env_e = getenv("AGP_TC_E");      // development override
-    if (env_e) {
-        const int e = atoi(env_e);
+static int tc_regs_for_k(int k, int override_e = 0) {
+    if (override_e) {
+        const int e = override_e;
         if ((e == 2 || e == 4 || e == 8 || e == 16) && 32 * e - 32 > k) return e;
     }
     int e = 2;
@@ -406,7 +424,7 @@ static int tc_regs_for_k(int k) {
 
 #define DISPATCH_E(k, fn, ...)                                                                   \
     [&]() -> int {                                                                               \
-        switch (tc_regs_for_k(k)) {                                                              \
+        switch (tc_regs_for_k(k, ix->kn.tc_e)) {                                                              \
             case 2: LAUNCH(fn<2>(__VA_ARGS__)); return 0;                                        \
             case 4: LAUNCH(fn<4>(__VA_ARGS__)); return 0;                                        \
             case 8: LAUNCH(fn<8>(__VA_ARGS__)); return 0;                                        \
@@ -516,7 +534,8 @@ static int search_diff(agp_index* ix, const float* xq_dev, int64_t nq, int k, fl
 static int search_simt(agp_index* ix, const float* xq_dev, int64_t nq, int k, float* D, int64_t* I) {
     const int64_t n = ix->ntotal;
     const int64_t ld = round_up(n, 32);
-    const int64_t max_rows = std::max<int64_t>(1, std::min<int64_t>(nq, (static_cast<int64_t>(128) << 20) / ld));
+    // select_rows / merge_keys put the query on grid.y (<= 65535)
+    const int64_t max_rows = std::max<int64_t>(1, std::min<int64_t>({nq, (static_cast<int64_t>(128) << 20) / ld, int64_t(65535)}));
     CKR(ensure(ix->panel, static_cast<size_t>(max_rows) * ld * sizeof(float)));
     CKR(ensure(ix->qn, static_cast<size_t>(nq) * sizeof(float)));
     LAUNCH(launch_prep_rows(false, xq_dev, nq, ix->d, ix->d_pad, static_cast<float*>(ix->qn.p), nullptr, nullptr, ix->num_sms * 32, ix->stream));
@@ -537,16 +556,14 @@ static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, floa
     // exact re-rank (default on): the tensor cores select kc = k + margin candidates (split-operand product,
     // expansion form), then their distances are recomputed in the fp32 difference form and the best k kept.
     // The margin absorbs selection flips at the k-th boundary caused by the ~1e-6 tensor-core error.
-    const char* env_rr = getenv("AGP_TC_RERANK");
-    const bool rerank = !(env_rr && atoi(env_rr) == 0);
+    const bool rerank = ix->kn.tc_rerank != 0;
     const int kc = rerank ? k + std::max(8, k / 8) : k;
-    const int E = tc_regs_for_k(kc);
+    const int E = tc_regs_for_k(kc, ix->kn.tc_e);
     const int n_dbtiles = static_cast<int>((n + TC_BN - 1) / TC_BN);
     const int64_t max_chunk = 65536;
     // development knob (not part of the ABI): TMA-only bandwidth probe
     const int eb = ix->elem_bytes;
-    const char* env_skip = getenv("AGP_TC_SKIP_MMA");
-    const int skip_mma = (env_skip && atoi(env_skip) != 0) ? 1 : 0;
+    const int skip_mma = ix->kn.skip_mma;
     CUtensorMap m_bhi, m_blo;
     CKR(make_plane_map(&m_bhi, ix->xb_hi, n, ix->d_pad, TC_BN, eb));
     CKR(make_plane_map(&m_blo, ix->xb_lo, n, ix->d_pad, TC_BN, eb));
@@ -571,7 +588,7 @@ static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, floa
         p.sq = static_cast<const float*>(ix->sq.p);
         p.wx = ix->wx;
         p.debug_skip_mma = skip_mma;
-        { const char* e = getenv("AGP_TC_COMPACT"); p.compact_mode = (e && strcmp(e, "sort") == 0) ? 1 : 0; }
+        p.compact_mode = ix->kn.tc_compact_sort;
         p.nq = nqc;
         p.d_pad = ix->d_pad;
         p.k = kc;
@@ -595,16 +612,14 @@ static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, floa
         p.pcount = static_cast<int*>(ix->cand.p);
         CK(cudaMemsetAsync(ix->cand.p, 0, static_cast<size_t>(nqc) * n_lists * sizeof(int), ix->stream));
         p.partial = static_cast<uint64_t*>(ix->partial.p);
-        const char* env_share = getenv("AGP_TC_SHARE_BOUND");
         p.gthr = nullptr;
-        if (!(env_share && atoi(env_share) == 0)) {
+        if (ix->kn.tc_share_bound) {
             CKR(ensure(ix->gthr, static_cast<size_t>(nqc) * sizeof(uint32_t)));
             LAUNCH(launch_fill_f32(static_cast<float*>(ix->gthr.p), nqc, HUGE_VALF, ix->stream));
             p.gthr = static_cast<uint32_t*>(ix->gthr.p);
         }
         p.dbg = nullptr;
-        const char* env_dbg = getenv("AGP_TC_DEBUG");
-        const bool dbg = env_dbg && atoi(env_dbg) != 0;
+        const bool dbg = ix->kn.cycle_counters != 0;
         if (dbg) {
             CKR(ensure(ix->dbg, static_cast<size_t>(grid) * 16 * sizeof(long long)));
             CK(cudaMemsetAsync(ix->dbg.p, 0, static_cast<size_t>(grid) * 16 * sizeof(long long), ix->stream));
@@ -652,11 +667,10 @@ static int search_tc(agp_index* ix, const float* xq_dev, int64_t nq, int k, floa
 }
 
 // register budget of the single-pass screen: slots for k + the certified band, with room to admit between compactions
-static int screen_regs_for_k(int k) {
-    const char* env_e = getenv("AGP_SCREEN_E");      // development override
+static int screen_regs_for_k(int k, int override_e) {
     const int kc_est = k + std::max(16, k / 4);
-    if (env_e) {
-        const int e = atoi(env_e);
+    if (override_e) {
+        const int e = override_e;
         if ((e == 8 || e == 16) && 32 * e - 128 >= kc_est + 16) return e;
     }
     // a list must hold k + band next to one whole tile (128 columns) of new admissions
@@ -677,7 +691,7 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
     const int64_t n = ix->ntotal;
     if (k > 256 || !ix->screen || (ix->num_sms & 1)) return search_simt(ix, xq_dev, nq, k, D, I);
     CKR(ensure_screen_plane(ix));
-    const int E = screen_regs_for_k(k);
+    const int E = screen_regs_for_k(k, ix->kn.screen_e);
     const int slots = 32 * E;
     const int n_dbtiles = static_cast<int>((n + TC_BN - 1) / TC_BN);
     const int ld = ix->d_pad + 64;                 // plane row pitch: scaled row + aux chunk
@@ -688,7 +702,7 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
     const int stage_bytes = resident ? chunk_bytes : 2 * chunk_bytes;
     const int smem_max = 227 * 1024;
     int n_stages = std::min(8, (smem_max - 1024 - SC_BAR_BYTES - SC_XCHG_BYTES - q_bytes) / stage_bytes);
-    { const char* e = getenv("AGP_SCREEN_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= n_stages) n_stages = atoi(e); }
+    if (ix->kn.screen_stages >= 2 && ix->kn.screen_stages <= n_stages) n_stages = ix->kn.screen_stages;
     const size_t smem = 1024 + static_cast<size_t>(q_bytes) + static_cast<size_t>(n_stages) * stage_bytes + SC_BAR_BYTES + SC_XCHG_BYTES;
     CUtensorMap m_b;
     // whole 256-row tiles: rows between ntotal and the tile end are storage padding masked by yn = +inf
@@ -737,12 +751,12 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         p.n_items = p.n_full_items + rem_tiles * p.rem_splits;
         p.q_resident = resident;
         p.n_stages = n_stages;
-        p.sched_mul = 8;
-        p.flags = 0;
+        p.sched_mul = ix->kn.screen_sched >= 5 ? ix->kn.screen_sched : 8;      // quarters: 8 = x2, 6 = x1.5
+        p.flags = ix->kn.screen_flags;
         p.ip = ix->ip;
-        { const char* e = getenv("AGP_SCREEN_SKIP_EPI"); p.debug_skip_epilogue = (e && atoi(e) != 0) ? 1 : 0; }
-        { const char* e = getenv("AGP_SCREEN_SCHED"); if (e && atoi(e) >= 5) p.sched_mul = atoi(e); }     // quarters: 8 = x2, 6 = x1.5
-        { const char* e = getenv("AGP_SCREEN_FLAGS"); if (e) p.flags = atoi(e); }
+        p.debug_skip_epilogue = ix->kn.skip_epi;
+        p.dump = ix->probe_dump;
+        p.dump_ld = ix->probe_ld;
         const int grid = 2 * std::min(p.n_items, clusters);
         const size_t n_lists_total = static_cast<size_t>(p.n_full_items) * 2 * TC_BM * 2 + static_cast<size_t>(rem_tiles) * 2 * TC_BM * 2 * p.rem_splits;
         CKR(ensure(ix->cand, n_lists_total * sizeof(int)));
@@ -766,8 +780,7 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         p.gthr = static_cast<uint32_t*>(ix->gthr.p);
         p.ovf = static_cast<int*>(ix->ovf.p);
         p.dbg = nullptr;
-        const char* env_dbg = getenv("AGP_TC_DEBUG");
-        const bool dbg = env_dbg && atoi(env_dbg) != 0;
+        const bool dbg = ix->kn.cycle_counters != 0;
         if (dbg) {
             CKR(ensure(ix->dbg, static_cast<size_t>(grid) * 16 * sizeof(long long)));
             CK(cudaMemsetAsync(ix->dbg.p, 0, static_cast<size_t>(grid) * 16 * sizeof(long long), ix->stream));
@@ -960,6 +973,17 @@ int agp_index_create_metric(int d, int device, int precision_mode, int metric, a
         return set_err(AGP_ECUDA, "stream creation failed: %s", cudaGetErrorString(e));
     }
     ix->stream = ix->own_stream;
+#ifdef AGP_DEBUG_KNOBS
+    {   // development builds only: seed the switches from the environment (scripts/screen_matrix.py, scripts/tc_probe.py)
+        auto env_int = [](const char* name, int& v) { const char* e = getenv(name); if (e) v = atoi(e); };
+        env_int("AGP_SCREEN_FLAGS", ix->kn.screen_flags); env_int("AGP_SCREEN_E", ix->kn.screen_e);
+        env_int("AGP_SCREEN_STAGES", ix->kn.screen_stages); env_int("AGP_SCREEN_SCHED", ix->kn.screen_sched);
+        env_int("AGP_SCREEN_SKIP_EPI", ix->kn.skip_epi); env_int("AGP_TC_SKIP_MMA", ix->kn.skip_mma);
+        env_int("AGP_TC_E", ix->kn.tc_e); env_int("AGP_TC_RERANK", ix->kn.tc_rerank);
+        env_int("AGP_TC_SHARE_BOUND", ix->kn.tc_share_bound); env_int("AGP_TC_DEBUG", ix->kn.cycle_counters);
+        const char* c = getenv("AGP_TC_COMPACT"); if (c && strcmp(c, "sort") == 0) ix->kn.tc_compact_sort = 1;
+    }
+#endif
     if (pool_alloc(device, reinterpret_cast<void**>(&ix->dbstats), 4 * sizeof(uint32_t)) != cudaSuccess ||
         cudaMemsetAsync(ix->dbstats, 0, 4 * sizeof(uint32_t), ix->stream) != cudaSuccess) {
         pool_stream_release(device, ix->own_stream);
@@ -1018,6 +1042,63 @@ int agp_index_set_stream(agp_index* ix, void* s, int use_own_stream) {
         CK(cudaStreamWaitEvent(ns, ix->ev_order, 0));
         ix->stream = ns;
     }
+    return 0;
+}
+
+int agp_index_set_knob(agp_index* ix, const char* name, int value) {
+    if (!ix || !name) return set_err(AGP_EINVAL, "index or name is null");
+    struct { const char* n; int* v; } table[] = {
+        {"screen_flags", &ix->kn.screen_flags}, {"screen_e", &ix->kn.screen_e}, {"screen_stages", &ix->kn.screen_stages},
+        {"screen_sched", &ix->kn.screen_sched}, {"tc_e", &ix->kn.tc_e}, {"tc_rerank", &ix->kn.tc_rerank},
+        {"tc_compact_sort", &ix->kn.tc_compact_sort}, {"tc_share_bound", &ix->kn.tc_share_bound}, {"cycle_counters", &ix->kn.cycle_counters},
+#ifdef AGP_DEBUG_KNOBS
+        {"skip_epi", &ix->kn.skip_epi}, {"skip_mma", &ix->kn.skip_mma},
+#endif
+    };
+    for (auto& t : table)
+        if (strcmp(t.n, name) == 0) { *t.v = value; return 0; }
+    return set_err(AGP_EINVAL, "unknown knob '%s' (result-changing probes need an AGP_DEBUG_KNOBS build)", name);
+}
+
+int agp_index_screen_probe(agp_index* ix, int64_t nq, const float* x, float* dis, float* band) {
+    if (!ix || !x || !dis || !band) return set_err(AGP_EINVAL, "null pointer");
+    if (!ix->screen || ix->ip) return set_err(AGP_EINVAL, "screen_probe needs an L2 index in precision auto or fp16_screen");
+    if (nq <= 0 || nq > 65536 || ix->ntotal <= 0) return set_err(AGP_EINVAL, "need 1 <= nq <= 65536 and a non-empty index");
+    if (nq * ix->ntotal > (int64_t(1) << 28)) return set_err(AGP_EINVAL, "nq * ntotal too large for a probe");
+    if (ix->num_sms & 1) return set_err(AGP_EINVAL, "the screen kernel needs an even SM count");
+    ENTER(ix);
+    const int64_t n = ix->ntotal, ld = round_up(n, TC_BN);
+    const int k = static_cast<int>(std::min<int64_t>(10, n));
+    Buf dump;
+    CKR(ensure(dump, static_cast<size_t>(nq) * ld * sizeof(float)));
+    CKR(ensure(ix->q_raw, static_cast<size_t>(nq) * ix->d * sizeof(float)));
+    CKR(ensure(ix->d_out, static_cast<size_t>(nq) * k * sizeof(float)));
+    CKR(ensure(ix->i_out, static_cast<size_t>(nq) * k * sizeof(int64_t)));
+    CK(cudaMemsetAsync(dump.p, 0xff, static_cast<size_t>(nq) * ld * sizeof(float), ix->stream));        // NaN = never written
+    CK(cudaMemcpyAsync(ix->q_raw.p, x, static_cast<size_t>(nq) * ix->d * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+    ix->probe_dump = static_cast<float*>(dump.p);
+    ix->probe_ld = ld;
+    int rc = search_screen(ix, static_cast<const float*>(ix->q_raw.p), nq, k, static_cast<float*>(ix->d_out.p), static_cast<int64_t*>(ix->i_out.p));
+    ix->probe_dump = nullptr;
+    ix->probe_ld = 0;
+    std::vector<float> qn(nq), dq(nq);
+    uint32_t st[4] = {0, 0, 0, 0};
+    cudaError_t e = cudaSuccess;
+    if (rc == 0) {
+        e = cudaMemcpy2DAsync(dis, static_cast<size_t>(n) * sizeof(float), dump.p, static_cast<size_t>(ld) * sizeof(float),
+                              static_cast<size_t>(n) * sizeof(float), static_cast<size_t>(nq), cudaMemcpyDeviceToHost, ix->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(qn.data(), ix->qn.p, nq * sizeof(float), cudaMemcpyDeviceToHost, ix->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dq.data(), ix->dq.p, nq * sizeof(float), cudaMemcpyDeviceToHost, ix->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(st, ix->dbstats, sizeof(st), cudaMemcpyDeviceToHost, ix->stream);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(ix->stream);
+    free_buf(dump);
+    if (rc != 0) return rc;
+    CK(e);
+    CK(e2);
+    float ymax2, dymax, sy;
+    memcpy(&ymax2, &st[0], 4); memcpy(&dymax, &st[1], 4); memcpy(&sy, &st[2], 4);
+    for (int64_t q = 0; q < nq; ++q) band[q] = screen_band(qn[q], dq[q], ymax2, dymax, sy, ix->d_pad);
     return 0;
 }
 
@@ -1180,7 +1261,35 @@ int agp_index_search_masked(agp_index* ix, int64_t nq, const float* x, int x_mem
     CKR(ensure(ix->mk_ids, static_cast<size_t>(std::max<int64_t>(n_ex, 1)) * sizeof(int64_t)));
     CK(cudaMemcpyAsync(ix->mk_off.p, excl_offsets, static_cast<size_t>(nq + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ix->stream));
     if (n_ex > 0) CK(cudaMemcpyAsync(ix->mk_ids.p, excl_ids, static_cast<size_t>(n_ex) * sizeof(int64_t), cudaMemcpyHostToDevice, ix->stream));
-    CKR(agp_index_search(ix, nq, x, x_mem_kind, kp, static_cast<float*>(ix->mk_d.p), static_cast<int64_t*>(ix->mk_i.p), AGP_MEM_DEVICE));
+    // Ids in this call are POSITIONS in the index (the exclusion lists are): the shard base is not applied.
+    const int64_t saved_base = ix->id_base;
+    ix->id_base = 0;
+    int rc_search;
+    if (kp > 256 && nq >= kMaxSmallNq && ix->ntotal > 0) {
+        // Beyond the tensor-core screen's 256 results the batch is answered by the fp32 FMA tiles in the EXPANSION form
+        // (|q|^2 + |y|^2 - 2 q.y), whose distances -- and therefore near-tie order -- differ from the difference form every
+        // other path of this call returns.  Fetch a margin of extra candidates and re-rank all of them in the exact fp32
+        // difference form (merge.cuh:rerank), so D and the (distance, id) order are path-independent.
+        const int kc = static_cast<int>(std::min<int64_t>({static_cast<int64_t>(kp) + 16, int64_t(AGP_MAX_K), std::max<int64_t>(ix->ntotal, kp)}));
+        const float* xq_dev = x;
+        rc_search = 0;
+        if (x_mem_kind != AGP_MEM_DEVICE) {
+            rc_search = ensure(ix->q_raw, static_cast<size_t>(nq) * ix->d * sizeof(float));
+            if (rc_search == 0) rc_search = copy_h2d(ix, ix->q_raw.p, x, static_cast<size_t>(nq) * ix->d * sizeof(float));
+            xq_dev = static_cast<const float*>(ix->q_raw.p);
+        }
+        if (rc_search == 0) rc_search = ensure(ix->cand_d, static_cast<size_t>(nq) * kc * sizeof(float));
+        if (rc_search == 0) rc_search = ensure(ix->cand_i, static_cast<size_t>(nq) * kc * sizeof(int64_t));
+        if (rc_search == 0)
+            rc_search = search_simt(ix, xq_dev, nq, kc, static_cast<float*>(ix->cand_d.p), static_cast<int64_t*>(ix->cand_i.p));
+        if (rc_search == 0)
+            rc_search = DISPATCH_E32(kc, launch_rerank, xq_dev, ix->xb, ix->d, static_cast<const int64_t*>(ix->cand_i.p), kc, nq, kp,
+                                     static_cast<int64_t>(0), static_cast<float*>(ix->mk_d.p), static_cast<int64_t*>(ix->mk_i.p), ix->stream);
+    } else {
+        rc_search = agp_index_search(ix, nq, x, x_mem_kind, kp, static_cast<float*>(ix->mk_d.p), static_cast<int64_t*>(ix->mk_i.p), AGP_MEM_DEVICE);
+    }
+    ix->id_base = saved_base;
+    CKR(rc_search);
     float* D_dev = D;
     int64_t* I_dev = I;
     if (out_mem_kind != AGP_MEM_DEVICE) {

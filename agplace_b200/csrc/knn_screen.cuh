@@ -592,6 +592,22 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     thr = (lim - qn) * invW;
                     booted = true;
                 }
+                if (DBG && p.dump != nullptr) {
+                    // probe (agp_index_screen_probe): the screened distance of every column of this accumulator tile, exactly
+                    // as the scan below evaluates it (unclamped) -- tests compare it with fp64 truth against screen_band()
+#pragma unroll 1
+                    for (int cc = 0; cc < 4; ++cc) {
+                        tmem_ld32(tcol + cc * 32, ra);
+                        tmem_ld_wait();
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int64_t col = colbase + cc * 32 + j;
+                                if (col < p.dump_ld) p.dump[static_cast<int64_t>(q) * p.dump_ld + col] = fmaf(__uint_as_float(ra[j]), Wq, qn);
+                            }
+                        }
+                    }
+                }
                 long long c4 = dbg_on ? clock64() : 0;
                 const int cnt_before = cnt;
                 // software pipeline over the 4 chunks: the next tcgen05.ld is in flight while this chunk is scanned
@@ -659,7 +675,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 
 template <int E>
 cudaError_t launch_knn_screen(const CUtensorMap& tq, const CUtensorMap& tb, const ScreenParams& p, int grid, size_t smem, cudaStream_t st) {
-    if (p.dbg) {
+    if (p.dbg || p.dump) {
         cudaError_t e = cudaFuncSetAttribute(knn_screen_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
         knn_screen_kernel<E, true><<<grid, TC_THREADS, smem, st>>>(tq, tb, p);

@@ -69,6 +69,8 @@ struct ScreenParams {
     uint32_t* hthr;         // per list: upper bound of the ceil(k/2)-th best of that list (fp32 bits, +inf initially)
     int* ovf;               // [nq] set when a query's certified band did not fit its slots
     long long* dbg;
+    float* dump;            // instrumented build only (agp_index_screen_probe): dis~ of every (query, database row), [nq][dump_ld]
+    int64_t dump_ld;
 };
 
 // |screened distance - true distance| <= screen_band(): fp16 rounding of both operands (Cauchy-Schwarz on the

@@ -223,8 +223,25 @@ class IndexFlatL2:
         return ms.value, n.value
 
 
+    def set_knob(self, name: str, value: int):
+        """Development switch of this index (A/B variants of the screen kernel; ``include/agpknn.h:agp_index_set_knob``)."""
+        _lib.check(self._lib.agp_index_set_knob(self._h, name.encode(), int(value)), "agp_index_set_knob")
+
+    def screen_probe(self, x):
+        """Diagnostics: the screened distance the tensor-core kernel evaluates for every (query, row) and the certified
+        half band per query -- ``(dis~ fp32 [nq, ntotal], band fp32 [nq])``; see ``agp_index_screen_probe``."""
+        x = np.ascontiguousarray(x, dtype="float32")
+        n, d = x.shape
+        assert d == self.d
+        dis = np.empty((n, self.ntotal), dtype=np.float32)
+        band = np.empty(n, dtype=np.float32)
+        self._use_own_stream()
+        _lib.check(self._lib.agp_index_screen_probe(self._h, n, ctypes.c_void_p(x.ctypes.data), ctypes.c_void_p(dis.ctypes.data),
+                                                    ctypes.c_void_p(band.ctypes.data)), "agp_index_screen_probe")
+        return dis, band
+
     def get_stats(self):
-        """(queries answered by the single-pass screen, queries re-run through the 3xFP16 fallback)."""
+        """(queries answered by the single-pass screen, queries re-run through the exact fp32 fallback)."""
         a, b = ctypes.c_int64(), ctypes.c_int64()
         _lib.check(self._lib.agp_index_get_stats(self._h, ctypes.byref(a), ctypes.byref(b)), "agp_index_get_stats")
         return a.value, b.value

@@ -153,7 +153,22 @@ class TripletMiner:
         for q in sampled_queries_indexes:
             soft = np.asarray(self.soft_positives_per_query[q]).reshape(-1)
             exclude.append(np.flatnonzero(np.isin(sample, soft)).astype(np.int64))
-        _, I = index.search_masked(query_features, self.negs_num_per_query, exclude)
+        # the engine answers k + longest exclusion list <= 512 candidates per query (agp_index_search_masked); a query
+        # with more soft positives inside the sample than that takes the reference's own per-query route instead
+        k = self.negs_num_per_query
+        max_k = getattr(index, "MAX_MASKED", 512)
+        fits = np.array([k + len(e) <= max_k or len(sample) <= max_k for e in exclude], dtype=bool)
+        I = np.full((len(exclude), k), -1, dtype=np.int64)
+        if fits.any():
+            rows = np.flatnonzero(fits)
+            _, I[rows] = index.search_masked(query_features[rows], k, [exclude[r] for r in rows])
+        for r in np.flatnonzero(~fits):
+            keep = np.ones(len(sample), dtype=bool)
+            keep[exclude[r]] = False
+            sub = self.index_cls(self.features_dim)
+            sub.add(np.asarray(cache[sample[keep]], dtype=np.float32))
+            _, pos = sub.search(query_features[r].reshape(1, -1), k)
+            I[r] = np.where(pos[0] >= 0, np.flatnonzero(keep)[np.maximum(pos[0], 0)], -1)
         negs = sample[I].astype(np.int32)
         # I == -1 (fewer than negs_num_per_query candidates): the reference's numpy indexing neg_samples[neg_nums] wraps
         # to the LAST element of that query's own subset, i.e. the last sampled row that is not excluded

@@ -1,7 +1,8 @@
 """Host-side mirror of the reference's recall@N evaluation (call site A).
 
-``compute_recall`` follows reference test.py:24-84 for the default ``test_method='hard_resize'``
-path (the ``nearest_crop`` / ``maj_voting`` branches are dead code in the reference: test.py:160
+``compute_recall`` follows reference test.py:24-84 for every test_method that takes the plain
+search + recall path ('hard_resize', 'single_query', 'central_crop', 'five_crops'; the
+``nearest_crop`` / ``maj_voting`` branches are dead code in the reference: test.py:160
 uses an undefined ``images``), with the index class injectable so the same function runs against
 the CUDA engine (default) or, in tests, against the CPU oracle.
 
@@ -22,8 +23,14 @@ def compute_recall(args, queries_features, database_features, test_ds, test_meth
 
     ``args`` needs ``features_dim`` and ``recall_values``; ``test_ds`` needs ``queries_num`` and
     ``get_positives()`` (object array of per-query positive database ids)."""
-    if test_method != "hard_resize":
-        raise NotImplementedError("only the reference's live 'hard_resize' path is mirrored")
+    # test.py:24-84 special-cases only 'nearest_crop' and 'maj_voting' (five descriptors per query, dead code in the
+    # reference: test.py:160 uses an undefined ``images``); every other test_method ('hard_resize', 'single_query',
+    # 'central_crop', 'five_crops' after its mean over crops) goes through the plain search + recall below
+    assert test_method in ["hard_resize", "single_query", "central_crop", "five_crops", "nearest_crop", "maj_voting"], \
+        f"test_method can't be {test_method}"                       # test.py:92-93
+    if test_method in ("nearest_crop", "maj_voting"):
+        raise NotImplementedError(f"test_method={test_method!r} needs five descriptors per query; that branch of the "
+                                  "reference is dead code (test.py:160) and is not mirrored")
     index_cls = index_cls or IndexFlatL2
     faiss_index = index_cls(args.features_dim)                      # test.py:27
     faiss_index.add(database_features)                              # test.py:28

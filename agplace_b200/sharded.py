@@ -116,15 +116,23 @@ class ShardedIndexFlatL2:
 
     def reset(self):
         self.local.reset()
+        if hasattr(self.local, "set_id_base"):
+            self.local.set_id_base(0)
         self._chunks = []
         self._local_rows = 0
         self._ntotal = 0
 
     # ------------------------------------------------------------------ search
-    def _to_global(self, I_local):
+    def _engine_applies_base(self):
+        """One contiguous chunk on this rank: the engine adds its global start itself (agp_index_set_id_base).  The base
+        is re-derived from the chunk table before EVERY search and cleared otherwise, so no stale base survives an
+        add / search / add or a reset (it is engine state, not something to remember here)."""
+        return len(self._chunks) == 1 and hasattr(self.local, "set_id_base") and self.shard == "db"
+
+    def _to_global(self, I_local, base_applied=False):
         """local row -> global id through the per-chunk bases (monotone, so tie order is preserved)."""
         import torch
-        if len(self._chunks) == 1 and hasattr(self.local, "set_id_base"):
+        if base_applied:
             return I_local      # id_base already applied by the engine
         starts = torch.tensor([c[0] for c in self._chunks] or [0], dtype=torch.int64, device=I_local.device)
         gbase = torch.tensor([c[1] - c[0] for c in self._chunks] or [0], dtype=torch.int64, device=I_local.device)
@@ -148,8 +156,9 @@ class ShardedIndexFlatL2:
             xs = x[lo:hi]
         else:
             xs = x
-        if len(self._chunks) == 1 and hasattr(self.local, "set_id_base") and self.shard == "db":
-            self.local.set_id_base(self._chunks[0][1])
+        base_applied = self._engine_applies_base()
+        if hasattr(self.local, "set_id_base"):
+            self.local.set_id_base(self._chunks[0][1] if base_applied else 0)
         if isinstance(self.local, IndexFlatL2) and not (_is_torch(xs) and xs.is_cuda) and xs.shape[0]:
             # host queries: one H2D copy, then everything (search, exchange, merge) stays on the GPU
             xh = xs if _is_torch(xs) else torch.from_numpy(np.ascontiguousarray(xs, dtype=np.float32))
@@ -174,7 +183,7 @@ class ShardedIndexFlatL2:
             # pad every slice to `per` rows, all-gather, drop the padding
             rows = per
         else:
-            I_loc = self._to_global(I_loc)
+            I_loc = self._to_global(I_loc, base_applied)
             rows = nq
         d_bytes = (rows * k * 4 + 7) // 8 * 8
         i_bytes = rows * k * 8

@@ -41,6 +41,62 @@ def descriptors(n, d, seed, kind="db", dtype=np.float32, chunk=65536):
     return out
 
 
+# ------------------------------------------------------------------------------------------ counter-based rows
+# Databases too large to ship from the host (cfg4: 10 M x 512 = 20.5 GB; cfg5: 1 M x 4096) are generated on the GPU that
+# owns the shard.  So that ANY row can be regenerated bit-for-bit on the CPU (sampled verification of a 10 M-row search
+# against the oracle), element (row, col) is a pure function of (seed, row * d + col):
+#   z = splitmix64(seed * GOLDEN + row * d + col);  a = sum of z's four 16-bit fields - 131070   (Irwin-Hall, n = 4)
+#   x = float32(a) * float32(1 / (sigma_a * sqrt(d)))      -- one correctly rounded fp32 multiply of an exact integer
+# i.e. integer arithmetic plus a single IEEE operation: identical bits from numpy and from torch on CUDA.  Rows are
+# approximately unit-norm (|x| = 1 +- 1.3/sqrt(d)) with a bell-shaped, bounded element distribution.
+_SM_GOLDEN, _SM_M1, _SM_M2 = 0x9E3779B97F4A7C15, 0xBF58476D1CE4E5B9, 0x94D049BB133111EB
+_IH_SIGMA = float(np.sqrt(4.0 * (65536.0 ** 2 - 1.0) / 12.0))
+
+
+def _counter_scale(d):
+    return np.float32(1.0 / (_IH_SIGMA * np.sqrt(float(d))))
+
+
+def counter_rows(row_ids, d, seed, chunk=16384):
+    """Rows ``row_ids`` (any int64 array) of the counter-based database ``seed``, on the CPU (numpy)."""
+    row_ids = np.asarray(row_ids, dtype=np.int64).reshape(-1)
+    out = np.empty((len(row_ids), d), dtype=np.float32)
+    cols = np.arange(d, dtype=np.uint64)[None, :]
+    base = np.uint64((seed * _SM_GOLDEN) & 0xFFFFFFFFFFFFFFFF)
+    c = _counter_scale(d)
+    with np.errstate(over="ignore"):
+        for i0 in range(0, len(row_ids), chunk):
+            r = row_ids[i0:i0 + chunk].astype(np.uint64)[:, None]
+            z = r * np.uint64(d) + cols + base
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(_SM_M1)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(_SM_M2)
+            z = z ^ (z >> np.uint64(31))
+            m = np.uint64(0xFFFF)
+            a = ((z & m) + ((z >> np.uint64(16)) & m) + ((z >> np.uint64(32)) & m) + (z >> np.uint64(48))).astype(np.int64) - 131070
+            out[i0:i0 + chunk] = a.astype(np.float32) * c
+    return out
+
+
+def counter_rows_device(row0, row1, d, seed, device):
+    """Rows [row0, row1) of the same database as a CUDA tensor (torch integer ops: bit-identical to counter_rows)."""
+    import torch
+
+    def s64(v):          # two's-complement int64 view of a 64-bit constant
+        v &= 0xFFFFFFFFFFFFFFFF
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    def lsr(z, s):       # logical shift right of an int64 tensor
+        return (z >> s) & ((1 << (64 - s)) - 1)
+
+    r = torch.arange(row0, row1, dtype=torch.int64, device=device)[:, None]
+    z = r * d + torch.arange(d, dtype=torch.int64, device=device)[None, :] + s64(seed * _SM_GOLDEN)
+    z = (z ^ lsr(z, 30)) * s64(_SM_M1)
+    z = (z ^ lsr(z, 27)) * s64(_SM_M2)
+    z = z ^ lsr(z, 31)
+    a = (z & 0xFFFF) + ((z >> 16) & 0xFFFF) + ((z >> 32) & 0xFFFF) + ((z >> 48) & 0xFFFF) - 131070
+    return a.to(torch.float32) * float(_counter_scale(d))
+
+
 def clustered_queries(xb, nq, sigma, seed):
     """Each query = a random database row + sigma * N(0, I/d), renormalised (near-duplicate regime)."""
     rng = np.random.default_rng(seed)

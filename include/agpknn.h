@@ -113,6 +113,20 @@ AGP_API int agp_index_get_profile(agp_index* idx, double* kernel_ms, int64_t* ke
  * representable in the fp16 plane (diagnostics). */
 AGP_API int agp_index_get_stats(const agp_index* idx, int64_t* screened_queries, int64_t* fallback_queries);
 
+/* Development switches of one index (A/B variants of the screen kernel, register budgets, the instrumented build with
+ * cycle counters).  The library reads NO environment variable on the launch path; every switch reachable here leaves
+ * the results unchanged (tests/test_gpu_parity.py runs every variant and compares bits).  Result-changing bandwidth
+ * probes (skip_epi, skip_mma) exist only in -DAGP_DEBUG_KNOBS builds.  Unknown names: AGP_EINVAL. */
+AGP_API int agp_index_set_knob(agp_index* idx, const char* name, int value);
+
+/* Certification probe (no reference equivalent; SURVEY 5 "sanitizers/diagnostics"): runs the tensor-core screen kernel
+ * (instrumented build, same MMA / TMEM / epilogue arithmetic) over nq HOST queries and returns the screened distance
+ * dis~ the epilogue evaluates for EVERY (query, row) -- dis: host fp32 [nq][ntotal] -- and the certified half band
+ * screen_band(q) -- band: host fp32 [nq].  The selection is correct iff |dis~ - true distance| <= band; the tests assert
+ * that against fp64 truth on adversarial inputs at d = 512 and d = 4096 (this pins the tensor core's accumulation-error
+ * constant the band assumes).  L2 indexes in precision auto / fp16_screen; nq <= 65536, nq * ntotal <= 2^28. */
+AGP_API int agp_index_screen_probe(agp_index* idx, int64_t nq, const float* x, float* dis, float* band);
+
 /* Batched, masked search: one call for what the reference's mining loop does per query,
  *   neg = np.setdiff1d(sampled_database_indexes, soft_positives[q]); IndexFlatL2(d).add(cache[neg]).search(q, k)
  * (datasets/datasets_ws_kitti360.py:1088-1091 + 985-993; copies in datasets_ws_nuscenes.py, datasets_ws.py).

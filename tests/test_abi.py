@@ -75,6 +75,8 @@ def test_faiss_shim_exports_the_names_the_reference_uses():
                      "index_cpu_to_gpu", "Kmeans"):
             assert hasattr(faiss, name), name
         assert faiss.METRIC_L2 == 1 and faiss.METRIC_INNER_PRODUCT == 0
+        importlib.import_module("faiss.contrib.torch_utils")        # reference anyloc/utilities.py:14
     finally:
         sys.path.remove(str(ROOT / "faiss_shim"))
-        sys.modules.pop("faiss", None)
+        for m in [m for m in sys.modules if m == "faiss" or m.startswith("faiss.")]:
+            sys.modules.pop(m, None)

@@ -285,6 +285,56 @@ def test_batched_mining_identical_to_the_per_query_loop():
     assert out[0].shape == (300, 12) and out[0].dtype == np.int64
 
 
+def test_batched_mining_with_long_exclusion_lists():
+    """k + longest exclusion list > 256 left the tensor-core screen for the expansion-form fp32 tiles
+    (different distances and near-tie order), and > 512 failed outright.  Both regimes must still mine exactly the
+    per-query loop's triplets: the engine re-ranks in the exact difference form, the miner routes over-long lists
+    through the reference's own per-query call."""
+    from agplace_b200 import mining
+    p = make_mining_problem(37, database_num=2000, queries_num=120, d=128)
+    p.cache[100:140] = p.cache[200:240]                       # exact ties among the negatives
+    rng = np.random.default_rng(5)
+    for q in range(p.queries_num):                            # soft positives: 0, ~300 or ~700 of the 2000 rows
+        extra = rng.choice(p.database_num, size=(0, 600, 1400)[q % 3], replace=False)
+        p.soft[q] = np.union1d(p.soft[q], extra).astype(np.int64)
+    out = []
+    for batched in (False, True):
+        miner = mining.TripletMiner(p.d, p.database_num, p.queries_num, p.hard, p.soft, negs_num_per_query=10,
+                                    neg_samples_num=1000)
+        np.random.seed(9)
+        f = miner.compute_triplets_partial_batched if batched else miner.compute_triplets_partial
+        out.append(f(p.cache, 90))
+    np.testing.assert_array_equal(out[0], out[1])
+    # the engine call itself: 300 < k + |exclude| <= 512 answers, identical to a fresh index over the surviving rows
+    import agplace_b200
+    xb = p.cache[:1000]
+    xq = p.cache[p.database_num:p.database_num + 40]
+    excl = [np.sort(rng.choice(1000, size=rng.integers(260, 480), replace=False)).astype(np.int64) for _ in range(40)]
+    ix = agplace_b200.IndexFlatL2(p.d); ix.add(xb)
+    D, I = ix.search_masked(xq, 12, excl)
+    for q in range(40):
+        keep = np.setdiff1d(np.arange(1000), excl[q])
+        one = agplace_b200.IndexFlatL2(p.d); one.add(xb[keep])
+        D1, I1 = one.search(xq[q:q + 1], 12)
+        np.testing.assert_array_equal(I[q], keep[I1[0]])
+        np.testing.assert_array_equal(D[q], D1[0])
+    with pytest.raises(RuntimeError, match="AGP_MAX_K"):
+        ix.search_masked(xq[:25], 12, [np.arange(600, dtype=np.int64)] * 25)
+
+
+def test_counter_based_rows_are_identical_on_cpu_and_gpu():
+    """bench.py generates cfg4 / cfg5 shards on the device and regenerates sampled rows on the CPU for verification:
+    the two generators must agree bit for bit."""
+    import torch
+    from agplace_b200 import synth
+    for d, seed, (a, b) in [(512, 3, (9_990_000, 9_991_111)), (4096, 4, (123_456, 123_700)), (33, 1, (0, 500))]:
+        dev = synth.counter_rows_device(a, b, d, seed, torch.device("cuda", 0)).cpu().numpy()
+        cpu = synth.counter_rows(np.arange(a, b), d, seed)
+        np.testing.assert_array_equal(dev, cpu)
+        norms = np.linalg.norm(cpu.astype(np.float64), axis=1)
+        assert abs(norms.mean() - 1.0) < 0.02 and norms.std() < 2.0 / np.sqrt(d)
+
+
 def test_full_batched_mining_identical_to_the_per_query_loop():
     """compute_triplets_full (kitti360:1022-1049) batched through search_subset: same triplets AND the same neg_cache
     over two consecutive refreshes (the second one feeds on the first one's neg_cache)."""
@@ -446,33 +496,30 @@ def test_engine_reproduces_the_published_output_of_the_faiss_tutorial(precision)
     assert ok, msg
 
 
-def test_screen_variants_return_identical_results(monkeypatch):
+def test_screen_variants_return_identical_results():
     """The screen kernel's alternative code paths -- the branchy scan (also the fallback when a candidate bundle
     straddles a 4 GB line), rounds without the pair exchange, sweeps without the first-tile bootstrap, 512-slot lists --
-    are selected per search through AGP_SCREEN_FLAGS / AGP_SCREEN_E; the exact finish makes every variant return the
-    same bits.  Shapes cover whole waves, the split remainder ("wide" groups) and a ragged last tile."""
+    are selected per index through agp_index_set_knob (the library reads no environment variable); the exact finish
+    makes every variant return the same bits.  Shapes cover whole waves, the split remainder and a ragged last tile."""
     rng = np.random.default_rng(23)
     for (n, nq, d, k) in [(30011, 19200, 64, 20), (9000, 1500, 128, 50), (5000, 300, 32, 100)]:
         xb = rng.standard_normal((n, d)).astype(np.float32)
         xq = rng.standard_normal((nq, d)).astype(np.float32)
         ix = agp().IndexFlatL2(d, precision="fp16_screen"); ix.add(xb)
-        monkeypatch.delenv("AGP_SCREEN_FLAGS", raising=False)
-        monkeypatch.delenv("AGP_SCREEN_E", raising=False)
         D0, I0 = ix.search(xq, k)
         sample = np.arange(0, nq, max(1, nq // 200))
         Dr, Ir = orc.knn_fp32(xq[sample], xb, k)
         ok, msg = orc.compare_knn(D0[sample], I0[sample], Dr, Ir, xq=xq[sample], xb=xb, abs_floor_eps=8 * 2.0 ** -24)
         assert ok, msg
-        for flags, e in [(1, None), (4, None), (8, None), (13, None), (0, 16), (5, 16)]:
-            monkeypatch.setenv("AGP_SCREEN_FLAGS", str(flags))
-            if e is None:
-                monkeypatch.delenv("AGP_SCREEN_E", raising=False)
-            else:
-                monkeypatch.setenv("AGP_SCREEN_E", str(e))
+        for flags, e in [(1, 0), (4, 0), (8, 0), (13, 0), (0, 16), (5, 16)]:
+            ix.set_knob("screen_flags", flags)
+            ix.set_knob("screen_e", e)
             D, I = ix.search(xq, k)
             np.testing.assert_array_equal(I, I0, err_msg=f"flags={flags} E={e} shape={(n, nq, d, k)}")
             np.testing.assert_array_equal(D, D0)
         assert ix.get_stats()[1] == 0
+    with pytest.raises(RuntimeError, match="unknown knob"):
+        ix.set_knob("skip_epi", 1)      # result-changing probes do not exist in the product build
 
 
 def test_native_library_was_used():

@@ -108,3 +108,60 @@ def test_shard_bounds_cover_everything():
         for w in (1, 2, 3, 8):
             b = shard_bounds(n, w)
             assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+
+
+def _worker_interleaved(rank, world, port, out_dir):
+    """add / search / add / search / reset / add / search on a local index that honours set_id_base like the engine
+    (a stale engine id_base corrupted the global ids after the second add or a reset)."""
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from agplace_b200.sharded import ShardedIndexFlatL2
+        from oracle import flatl2_oracle as orc
+        from tests.helpers import numpy_merge
+
+        class BasedOracleIndex(orc.IndexFlatL2):
+            id_base = 0
+
+            def set_id_base(self, base):
+                self.id_base = int(base)
+
+            def search(self, x, k, **kw):
+                D, I = super().search(x, k, **kw)
+                return D, np.where(I >= 0, I + self.id_base, I)
+
+        rng = np.random.default_rng(79)
+        xb = rng.integers(-5, 6, size=(700, 8)).astype(np.float32)
+        xq = rng.integers(-5, 6, size=(30, 8)).astype(np.float32)
+        ix = ShardedIndexFlatL2(8, shard="db", index_cls=BasedOracleIndex, merge_fn=numpy_merge, result_device=torch.device("cpu"))
+        out = {}
+        ix.add(xb[:300])
+        out["D1"], out["I1"] = ix.search(xq, 7)            # one chunk per rank: the engine applies the base
+        ix.add(xb[300:500])
+        out["D2"], out["I2"] = ix.search(xq, 7)            # two non-contiguous chunks on every rank: the base must be cleared
+        ix.reset()
+        assert ix.local.id_base == 0 and ix.ntotal == 0
+        ix.add(xb[500:])
+        out["D3"], out["I3"] = ix.search(xq, 7)            # ids restart at 0 after reset
+        ix.add(xb[:100])
+        out["D4"], out["I4"] = ix.search(xq, 7)
+        np.savez(Path(out_dir) / f"r{rank}.npz", **out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_add_search_add_search_and_reset(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker_interleaved, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    from oracle import flatl2_oracle as orc
+    rng = np.random.default_rng(79)
+    xb = rng.integers(-5, 6, size=(700, 8)).astype(np.float32)
+    xq = rng.integers(-5, 6, size=(30, 8)).astype(np.float32)
+    want = {1: xb[:300], 2: xb[:500], 3: xb[500:], 4: np.concatenate([xb[500:], xb[:100]])}
+    for r in range(world):
+        got = np.load(tmp_path / f"r{r}.npz")
+        for step, rows in want.items():
+            Dr, Ir = orc.knn_fp32(xq, rows, 7)
+            np.testing.assert_array_equal(got[f"D{step}"], Dr, err_msg=f"step {step}")
+            np.testing.assert_array_equal(got[f"I{step}"], Ir, err_msg=f"step {step}")
