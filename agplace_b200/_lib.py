@@ -32,6 +32,7 @@ SIGNATURES = {
     "agp_index_set_id_base": (c_int, [c_void_p, c_int64]),
     "agp_index_set_profiling": (c_int, [c_void_p, c_int]),
     "agp_index_get_profile": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), c_int]),
+    "agp_index_get_profile_phases": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), c_int]),
     "agp_index_get_stats": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
     "agp_index_set_knob": (c_int, [c_void_p, c_char_p, c_int]),
     "agp_index_screen_probe": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),

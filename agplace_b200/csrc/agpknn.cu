@@ -185,7 +185,7 @@ private:
     struct Task { char* d; const char* s; size_t n; };
     CopyPool() {
         const unsigned hw = std::thread::hardware_concurrency();
-        const unsigned n = std::max(1u, std::min(3u, hw > 2 ? hw / 2 - 1 : 1u));
+        const unsigned n = std::max(1u, std::min(7u, hw > 2 ? hw / 2 - 1 : 1u));
         for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
         for (auto& t : workers_) t.detach();
     }
@@ -256,19 +256,28 @@ struct agp_index {
     int kind = KIND_TF32, elem_bytes = 4;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     Buf q_raw, q_hi, q_lo, qn, sq, cand, partial, panel, d_out, i_out, gthr, cand_d, cand_i, dbg;
-    Buf dq, ovf, ovf_list, ovf_x, ovf_d, ovf_i, hthr;
+    Buf dq, ovf, ovf_list, hthr;
     Buf mk_d, mk_i, mk_off, mk_ids;                  // masked search: k' result lists and the exclusion lists (CSR)     // single-pass screen: residual norms, overflow flags / list / fallback scratch
     uint32_t* dbstats = nullptr;                     // [4] max |y|^2, max |y - fp16(y)| over the database (fp32 bits)
-    int* h_count = nullptr;                          // pinned host word for the overflow count
+    unsigned long long* dev_stats = nullptr;         // device counter: queries answered by the exact fallback (read lazily by get_stats)
     uint8_t* stage[2] = {nullptr, nullptr};          // pinned staging buffers of large pageable transfers (lazy)
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
-    int64_t stat_screened = 0, stat_fallback = 0;
+    // host-buffer search pipeline (search_host_pipelined): copy streams, staging ring, per-chunk events
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    uint8_t* in_ring[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t in_ring_ev[3] = {nullptr, nullptr, nullptr};
+    uint8_t* out_slot[2] = {nullptr, nullptr};
+    size_t out_slot_bytes = 0;
+    std::vector<cudaEvent_t> pipe_ev;
+    int pipe_chunk = 0;                              // knob: queries per pipeline chunk (0 = automatic)
+    int64_t stat_screened = 0;
     bool profile = false;
     cudaEvent_t ev_order = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
-    double prof_ms = 0.0;
-    int64_t prof_launches = 0;
+    std::vector<int> ev_tag;                         // phase of each recorded event pair
+    double prof_ms[AGP_N_PHASES] = {0};
+    int64_t prof_launches[AGP_N_PHASES] = {0};
 };
 
 // scratch buffers belong to the index that is currently executing a call on this thread
@@ -450,8 +459,10 @@ static int tc_regs_for_k(int k, int override_e = 0) {
 struct ProfScope {
     agp_index* ix;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    explicit ProfScope(agp_index* i) : ix(i) {
+    explicit ProfScope(agp_index* i, int tag = AGP_PHASE_DISTANCE) : ix(i) {
         if (!ix->profile) return;
+        if (ix->ev_tag.size() <= ix->ev_used / 2) ix->ev_tag.resize(ix->ev_used / 2 + 1);
+        ix->ev_tag[ix->ev_used / 2] = tag;
         if (ix->ev_used + 2 > ix->ev_pool.size()) {
             cudaEvent_t a = nullptr, b = nullptr;
             if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
@@ -473,8 +484,9 @@ static void prof_collect(agp_index* ix) {
         float ms = 0.f;
         if (cudaEventSynchronize(ix->ev_pool[i + 1]) == cudaSuccess &&
             cudaEventElapsedTime(&ms, ix->ev_pool[i], ix->ev_pool[i + 1]) == cudaSuccess) {
-            ix->prof_ms += ms;
-            ix->prof_launches += 1;
+            const int tag = ix->ev_tag[i / 2];
+            ix->prof_ms[tag] += ms;
+            ix->prof_launches[tag] += 1;
         }
     }
     ix->ev_used = 0;
@@ -707,7 +719,6 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
     CUtensorMap m_b;
     // whole 256-row tiles: rows between ntotal and the tile end are storage padding masked by yn = +inf
     CKR(make_plane_map(&m_b, ix->xs, static_cast<int64_t>(n_dbtiles) * TC_BN, ix->d_pad, TC_BM, 2, ld));
-    if (!ix->h_count) CK(cudaMallocHost(&ix->h_count, sizeof(int)));
     const int clusters = ix->num_sms / 2;
     const int64_t max_chunk = 65536;
     for (int64_t q0 = 0; q0 < nq; q0 += max_chunk) {
@@ -722,11 +733,9 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         CKR(ensure(ix->qn, static_cast<size_t>(nqc) * sizeof(float)));
         CKR(ensure(ix->sq, static_cast<size_t>(nqc) * sizeof(float)));
         CKR(ensure(ix->dq, static_cast<size_t>(nqc) * sizeof(float)));
+        ProfScope prof_prep(ix, AGP_PHASE_PREP);
         LAUNCH(launch_prep_rows_screen(xq_dev + q0 * ix->d, nqc, ix->d, ix->d_pad, ix->q_hi.p, static_cast<float*>(ix->qn.p),
                                        static_cast<float*>(ix->sq.p), static_cast<float*>(ix->dq.p), nullptr, 0, ix->num_sms * 32, ix->stream));
-        if (rows_pad > nqc)
-            CK(cudaMemsetAsync(static_cast<uint8_t*>(ix->q_hi.p) + static_cast<size_t>(nqc) * ld * 2, 0,
-                               static_cast<size_t>(rows_pad - nqc) * ld * 2, ix->stream));
         CUtensorMap m_q;
         CKR(make_plane_map(&m_q, ix->q_hi.p, rows_pad, ix->d_pad, TC_BM, 2, ld));
         // whole waves of pair tiles sweep the database unsplit; the last partial wave is split to fill every pair
@@ -764,12 +773,13 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         CKR(ensure(ix->gthr, static_cast<size_t>(nqc) * sizeof(uint32_t)));
         CKR(ensure(ix->ovf, static_cast<size_t>(nqc) * sizeof(int)));
         CKR(ensure(ix->ovf_list, static_cast<size_t>(nqc + 1) * sizeof(int)));
-        CK(cudaMemsetAsync(ix->cand.p, 0, n_lists_total * sizeof(int), ix->stream));
-        CK(cudaMemsetAsync(ix->ovf.p, 0, static_cast<size_t>(nqc) * sizeof(int), ix->stream));
-        CK(cudaMemsetAsync(ix->ovf_list.p, 0, sizeof(int), ix->stream));
-        LAUNCH(launch_fill_f32(static_cast<float*>(ix->gthr.p), nqc, HUGE_VALF, ix->stream));
         CKR(ensure(ix->hthr, n_lists_total * sizeof(uint32_t)));
-        LAUNCH(launch_fill_f32(static_cast<float*>(ix->hthr.p), static_cast<int64_t>(n_lists_total), HUGE_VALF, ix->stream));
+        // one launch: list counters, overflow flags / list head, shared bounds (+inf), zero padding rows of the query plane
+        LAUNCH(launch_screen_init(static_cast<int*>(ix->cand.p), static_cast<uint32_t*>(ix->hthr.p), static_cast<int64_t>(n_lists_total),
+                                  static_cast<int*>(ix->ovf.p), static_cast<uint32_t*>(ix->gthr.p), nqc, static_cast<int*>(ix->ovf_list.p),
+                                  static_cast<uint8_t*>(ix->q_hi.p) + static_cast<size_t>(nqc) * ld * 2,
+                                  static_cast<size_t>(rows_pad - nqc) * ld * 2, ix->stream));
+        prof_prep.stop();
         p.hthr = static_cast<uint32_t*>(ix->hthr.p);
         p.qn = static_cast<const float*>(ix->qn.p);
         p.sq = static_cast<const float*>(ix->sq.p);
@@ -791,11 +801,19 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         ProfScope prof(ix);
         CKR(DISPATCH_EV(E, launch_knn_screen, m_q, m_b, p, grid, smem, ix->stream));
         prof.stop();
+        ProfScope prof_fin(ix, AGP_PHASE_FINISH);
         CKR(DISPATCH_EV(E, launch_screen_finalize, static_cast<const uint64_t*>(ix->partial.p), static_cast<const int*>(ix->cand.p), slots,
                         static_cast<int64_t>(nqc), p.n_full_items, p.rem_splits, k, xq_dev + q0 * ix->d, ix->xb, ix->d, ix->d_pad,
                         static_cast<const float*>(ix->qn.p), static_cast<const float*>(ix->dq.p), ix->dbstats,
                         static_cast<const int*>(ix->ovf.p), ovf_count, ovf_list, ix->id_base, D + q0 * k, I + q0 * k, ix->ip, ix->stream));
-        CK(cudaMemcpyAsync(ix->h_count, ovf_count, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+        // Flagged queries (certified band wider than the slots, rows the fp16 plane cannot represent) are answered exactly
+        // by a device-side pass over the overflow list: no host round trip, the search stays asynchronous.
+        prof_fin.stop();
+        ProfScope prof_ovf(ix, AGP_PHASE_FALLBACK);
+        LAUNCH(launch_ovf_exact(ovf_count, ovf_list, xq_dev + q0 * ix->d, ix->xb, n, ix->d, k, ix->id_base, ix->ip, D + q0 * k, I + q0 * k,
+                                ix->dev_stats, ix->num_sms, ix->stream));
+        prof_ovf.stop();
+        ix->stat_screened += nqc;
         if (dbg) {
             std::vector<long long> h(static_cast<size_t>(grid) * 16);
             CK(cudaMemcpyAsync(h.data(), ix->dbg.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
@@ -822,21 +840,6 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
             }
             fprintf(stderr, "[agp screen dbg] mma(leader): total=%.0f wait_full=%.0f wait_tempty=%.0f | epi(w2, all CTAs): total=%.0f wait_tfull=%.0f "
                             "compact=%.0f n_compact=%.0f hits(lane0,w2)=%.0f scan=%.0f tiles=%.0f compact_first=%.0f flags=%d sched=%d (cycles, mean)\n", sl[0], sl[1], sl[2], sa[3], sa[4], sa[5], sa[6], sa[7], sa[8], sa[9], sa[10], p.flags, p.sched_mul);
-        }
-        CK(cudaStreamSynchronize(ix->stream));
-        const int n_ovf = *ix->h_count;
-        ix->stat_screened += nqc;
-        if (n_ovf > 0) {
-            // certified band did not fit (or a row was not representable): answer those queries with fp32 FMA tiles instead
-            ix->stat_fallback += n_ovf;
-            CKR(ensure(ix->ovf_x, static_cast<size_t>(n_ovf) * ix->d * sizeof(float)));
-            CKR(ensure(ix->ovf_d, static_cast<size_t>(n_ovf) * k * sizeof(float)));
-            CKR(ensure(ix->ovf_i, static_cast<size_t>(n_ovf) * k * sizeof(int64_t)));
-            LAUNCH(launch_gather_rows(xq_dev + q0 * ix->d, ovf_list, n_ovf, ix->d, static_cast<float*>(ix->ovf_x.p), ix->stream));
-            CKR(search_simt(ix, static_cast<const float*>(ix->ovf_x.p), n_ovf, k, static_cast<float*>(ix->ovf_d.p),
-                            static_cast<int64_t*>(ix->ovf_i.p)));
-            LAUNCH(launch_scatter_results(static_cast<const float*>(ix->ovf_d.p), static_cast<const int64_t*>(ix->ovf_i.p), ovf_list, n_ovf, k,
-                                          D + q0 * k, I + q0 * k, ix->stream));
         }
     }
     return 0;
@@ -984,12 +987,14 @@ int agp_index_create_metric(int d, int device, int precision_mode, int metric, a
         const char* c = getenv("AGP_TC_COMPACT"); if (c && strcmp(c, "sort") == 0) ix->kn.tc_compact_sort = 1;
     }
 #endif
-    if (pool_alloc(device, reinterpret_cast<void**>(&ix->dbstats), 4 * sizeof(uint32_t)) != cudaSuccess ||
-        cudaMemsetAsync(ix->dbstats, 0, 4 * sizeof(uint32_t), ix->stream) != cudaSuccess) {
+    // one block: [0..3] database statistics (fp32 bits), [4..5] the 64-bit fallback counter
+    if (pool_alloc(device, reinterpret_cast<void**>(&ix->dbstats), 8 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemsetAsync(ix->dbstats, 0, 8 * sizeof(uint32_t), ix->stream) != cudaSuccess) {
         pool_stream_release(device, ix->own_stream);
         delete ix;
         return set_err(AGP_ENOMEM, "device allocation failed");
     }
+    ix->dev_stats = reinterpret_cast<unsigned long long*>(ix->dbstats + 4);
     *out = ix;
     return 0;
 }
@@ -1008,18 +1013,26 @@ void agp_index_free(agp_index* ix) {
     pool_free(ix->device, ix->xb_lo, static_cast<size_t>(ix->cap) * plane_row);
     pool_free(ix->device, ix->wx, static_cast<size_t>(ix->cap) * sizeof(float));
     pool_free(ix->device, ix->xs, static_cast<size_t>(ix->xs_cap) * screen_row_bytes(ix));
-    pool_free(ix->device, ix->dbstats, 4 * sizeof(uint32_t));
+    pool_free(ix->device, ix->dbstats, 8 * sizeof(uint32_t));
     free_buf(ix->sq);
     free_buf(ix->dq); free_buf(ix->hthr); free_buf(ix->mk_d); free_buf(ix->mk_i); free_buf(ix->mk_off); free_buf(ix->mk_ids);
-    free_buf(ix->ovf); free_buf(ix->ovf_list); free_buf(ix->ovf_x); free_buf(ix->ovf_d); free_buf(ix->ovf_i);
+    free_buf(ix->ovf); free_buf(ix->ovf_list);
     free_buf(ix->q_raw); free_buf(ix->q_hi); free_buf(ix->q_lo); free_buf(ix->qn); free_buf(ix->cand);
     free_buf(ix->gthr); free_buf(ix->dbg); free_buf(ix->cand_d); free_buf(ix->cand_i); free_buf(ix->partial); free_buf(ix->panel);
     free_buf(ix->d_out); free_buf(ix->i_out);
-    if (ix->h_count) cudaFreeHost(ix->h_count);
     for (int b = 0; b < 2; ++b) {
         if (ix->stage[b]) cudaFreeHost(ix->stage[b]);
         if (ix->stage_ev[b]) cudaEventDestroy(ix->stage_ev[b]);
     }
+    for (int b = 0; b < 3; ++b) {
+        if (ix->in_ring[b]) cudaFreeHost(ix->in_ring[b]);
+        if (ix->in_ring_ev[b]) cudaEventDestroy(ix->in_ring_ev[b]);
+    }
+    for (int b = 0; b < 2; ++b)
+        if (ix->out_slot[b]) cudaFreeHost(ix->out_slot[b]);
+    for (cudaEvent_t e : ix->pipe_ev) cudaEventDestroy(e);
+    if (ix->s_in) { cudaStreamSynchronize(ix->s_in); pool_stream_release(ix->device, ix->s_in); }
+    if (ix->s_out) { cudaStreamSynchronize(ix->s_out); pool_stream_release(ix->device, ix->s_out); }
     for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
     if (ix->ev_order) cudaEventDestroy(ix->ev_order);
     pool_stream_release(ix->device, ix->own_stream);
@@ -1051,6 +1064,7 @@ int agp_index_set_knob(agp_index* ix, const char* name, int value) {
         {"screen_flags", &ix->kn.screen_flags}, {"screen_e", &ix->kn.screen_e}, {"screen_stages", &ix->kn.screen_stages},
         {"screen_sched", &ix->kn.screen_sched}, {"tc_e", &ix->kn.tc_e}, {"tc_rerank", &ix->kn.tc_rerank},
         {"tc_compact_sort", &ix->kn.tc_compact_sort}, {"tc_share_bound", &ix->kn.tc_share_bound}, {"cycle_counters", &ix->kn.cycle_counters},
+        {"pipe_chunk", &ix->pipe_chunk},
 #ifdef AGP_DEBUG_KNOBS
         {"skip_epi", &ix->kn.skip_epi}, {"skip_mma", &ix->kn.skip_mma},
 #endif
@@ -1119,11 +1133,21 @@ int agp_index_get_profile(agp_index* ix, double* ms, int64_t* launches, int rese
     if (!ix) return set_err(AGP_EINVAL, "index is null");
     ENTER(ix);
     prof_collect(ix);
-    if (ms) *ms = ix->prof_ms;
-    if (launches) *launches = ix->prof_launches;
-    if (reset) {
-        ix->prof_ms = 0.0;
-        ix->prof_launches = 0;
+    if (ms) *ms = ix->prof_ms[AGP_PHASE_DISTANCE];
+    if (launches) *launches = ix->prof_launches[AGP_PHASE_DISTANCE];
+    if (reset)
+        for (int t = 0; t < AGP_N_PHASES; ++t) { ix->prof_ms[t] = 0.0; ix->prof_launches[t] = 0; }
+    return 0;
+}
+
+int agp_index_get_profile_phases(agp_index* ix, double* ms, int64_t* launches, int reset) {
+    if (!ix) return set_err(AGP_EINVAL, "index is null");
+    ENTER(ix);
+    prof_collect(ix);
+    for (int t = 0; t < AGP_N_PHASES; ++t) {
+        if (ms) ms[t] = ix->prof_ms[t];
+        if (launches) launches[t] = ix->prof_launches[t];
+        if (reset) { ix->prof_ms[t] = 0.0; ix->prof_launches[t] = 0; }
     }
     return 0;
 }
@@ -1151,7 +1175,14 @@ int agp_index_reset(agp_index* ix) {
 int agp_index_get_stats(const agp_index* ix, int64_t* screened_queries, int64_t* fallback_queries) {
     if (!ix) return set_err(AGP_EINVAL, "index is null");
     if (screened_queries) *screened_queries = ix->stat_screened;
-    if (fallback_queries) *fallback_queries = ix->stat_fallback;
+    if (fallback_queries) {
+        // the fallback runs on the device without telling the host: read its counter after the queued searches
+        unsigned long long v = 0;
+        CK(cudaSetDevice(ix->device));
+        CK(cudaStreamSynchronize(ix->stream));
+        CK(cudaMemcpy(&v, ix->dev_stats, sizeof(v), cudaMemcpyDeviceToHost));
+        *fallback_queries = static_cast<int64_t>(v);
+    }
     return 0;
 }
 
@@ -1184,6 +1215,185 @@ int agp_index_add(agp_index* ix, int64_t n, const float* x, int mem_kind) {
     return 0;
 }
 
+// device queries -> device results for [0, nq) on the index's stream (asynchronous)
+static int search_device(agp_index* ix, const float* xq_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
+    if (ix->ntotal == 0) return search_empty(ix, nq, k, D_dev, I_dev);
+    switch (ix->mode) {
+        case AGP_PRECISION_AUTO:
+            return (nq < kMaxSmallNq) ? search_diff(ix, xq_dev, nq, k, D_dev, I_dev) : search_screen(ix, xq_dev, nq, k, D_dev, I_dev);
+        case AGP_PRECISION_FP16_SCREEN: return search_screen(ix, xq_dev, nq, k, D_dev, I_dev);
+        case AGP_PRECISION_3XTF32:
+        case AGP_PRECISION_3XFP16: return search_tc(ix, xq_dev, nq, k, D_dev, I_dev);
+        case AGP_PRECISION_FP32_SIMT: return search_simt(ix, xq_dev, nq, k, D_dev, I_dev);
+        default: return search_diff(ix, xq_dev, nq, k, D_dev, I_dev);
+    }
+}
+
+// Host-buffer search as a three-stage pipeline (what the reference's call hands over: numpy arrays in, numpy arrays
+// out -- test.py:32).  The query batch is cut into chunks; for chunk c
+//     host memcpy into a pinned ring + H2D   (stream s_in)
+//  -> prep / screen / finish / fallback      (the index's stream, after the chunk's H2D event)
+//  -> D2H of (D, I) into a pinned slot       (stream s_out, after the chunk's compute event) + host memcpy out
+// run concurrently for chunks c + 1, c and c - 1.  No stage needs a host synchronisation of the compute stream (the
+// screen's overflow fallback is device-side), so the host thread only ever blocks on a staging slot or a finished chunk.
+// Chunks are whole waves of pair tiles (74 x 256 queries on B200) when the batch is large; a mid-sized batch is cut
+// unevenly (small first chunk: the GPU starts early; large later chunks: the kernel stays efficient).
+static int pipe_event(agp_index* ix, size_t i, cudaEvent_t* out) {
+    while (ix->pipe_ev.size() <= i) {
+        cudaEvent_t e = nullptr;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ix->pipe_ev.push_back(e);
+    }
+    *out = ix->pipe_ev[i];
+    return 0;
+}
+
+static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, int k, float* D, int64_t* I, int out_mem_kind) {
+    const bool x_host = x_mem_kind != AGP_MEM_DEVICE, out_host = out_mem_kind != AGP_MEM_DEVICE;
+    const size_t row_in = static_cast<size_t>(ix->d) * sizeof(float);
+    const size_t row_d = static_cast<size_t>(k) * sizeof(float), row_i = static_cast<size_t>(k) * sizeof(int64_t);
+    // ---- chunk schedule
+    std::vector<int64_t> cuts;       // chunk c = [cuts[c], cuts[c + 1])
+    cuts.push_back(0);
+    const int64_t wave = static_cast<int64_t>(ix->num_sms / 2) * 2 * TC_BM;      // queries one wave of pair tiles covers
+    const size_t moved = (x_host ? nq * row_in : 0) + (out_host ? nq * (row_d + row_i) : 0);
+    const bool batched_path = ix->ntotal > 0 && nq >= kMaxSmallNq;
+    if (ix->pipe_chunk > 0) {
+        for (int64_t a = ix->pipe_chunk; a < nq; a += ix->pipe_chunk) cuts.push_back(a);
+    } else if (batched_path && moved >= (size_t(4) << 20)) {
+        if (nq >= 3 * wave) {
+            for (int64_t a = wave; a < nq; a += wave) cuts.push_back(a);
+        } else if (nq >= 2048) {
+            const int64_t c1 = round_up(nq / 8, 256), c2 = round_up(nq / 2, 256);
+            if (c1 > 0 && c1 < nq) cuts.push_back(c1);
+            if (c2 > c1 && c2 < nq) cuts.push_back(c2);
+        }
+    }
+    cuts.push_back(nq);
+    const int n_chunks = static_cast<int>(cuts.size()) - 1;
+
+    const float* xq_dev = x;
+    if (x_host) {
+        CKR(ensure(ix->q_raw, static_cast<size_t>(nq) * row_in));
+        xq_dev = static_cast<const float*>(ix->q_raw.p);
+    }
+    float* D_dev = D;
+    int64_t* I_dev = I;
+    if (out_host) {
+        CKR(ensure(ix->d_out, static_cast<size_t>(nq) * row_d));
+        CKR(ensure(ix->i_out, static_cast<size_t>(nq) * row_i));
+        D_dev = static_cast<float*>(ix->d_out.p);
+        I_dev = static_cast<int64_t*>(ix->i_out.p);
+    }
+    if (n_chunks == 1 && !(x_host && nq * row_in >= kStageMin)) {
+        // small call (the mining shapes): one copy in, one launch sequence, one copy out, one synchronisation
+        if (x_host) CK(cudaMemcpyAsync(ix->q_raw.p, x, static_cast<size_t>(nq) * row_in, cudaMemcpyHostToDevice, ix->stream));
+        CKR(search_device(ix, xq_dev, nq, k, D_dev, I_dev));
+        if (out_host) {
+            CK(cudaMemcpyAsync(D, D_dev, static_cast<size_t>(nq) * row_d, cudaMemcpyDeviceToHost, ix->stream));
+            CK(cudaMemcpyAsync(I, I_dev, static_cast<size_t>(nq) * row_i, cudaMemcpyDeviceToHost, ix->stream));
+        }
+        if (out_host || x_host) CK(cudaStreamSynchronize(ix->stream));
+        return 0;
+    }
+
+    if (!ix->s_in) CK(pool_stream(ix->device, &ix->s_in));
+    if (!ix->s_out) CK(pool_stream(ix->device, &ix->s_out));
+    const bool stage_in = x_host && is_pageable(x);
+    const bool stage_out = out_host && (is_pageable(D) || is_pageable(I));
+    if (stage_in)
+        for (int b = 0; b < 3; ++b) {
+            if (!ix->in_ring[b]) CK(cudaHostAlloc(reinterpret_cast<void**>(&ix->in_ring[b]), kStageChunk, cudaHostAllocDefault));
+            if (!ix->in_ring_ev[b]) CK(cudaEventCreateWithFlags(&ix->in_ring_ev[b], cudaEventDisableTiming));
+        }
+    int64_t max_chunk = 0;
+    for (int c = 0; c < n_chunks; ++c) max_chunk = std::max(max_chunk, cuts[c + 1] - cuts[c]);
+    const size_t slot_bytes = static_cast<size_t>(max_chunk) * (row_d + row_i);
+    if (stage_out && ix->out_slot_bytes < slot_bytes) {
+        CK(cudaStreamSynchronize(ix->s_out));
+        for (int b = 0; b < 2; ++b) {
+            if (ix->out_slot[b]) CK(cudaFreeHost(ix->out_slot[b]));
+            ix->out_slot[b] = nullptr;
+            CK(cudaHostAlloc(reinterpret_cast<void**>(&ix->out_slot[b]), slot_bytes, cudaHostAllocDefault));
+        }
+        ix->out_slot_bytes = slot_bytes;
+    }
+    // the copy streams start after everything already queued on the compute stream (earlier calls own the scratch buffers)
+    cudaEvent_t ev_start;
+    CKR(pipe_event(ix, 0, &ev_start));
+    CK(cudaEventRecord(ev_start, ix->stream));
+    CK(cudaStreamWaitEvent(ix->s_in, ev_start, 0));
+    CK(cudaStreamWaitEvent(ix->s_out, ev_start, 0));
+
+    std::lock_guard<std::mutex> lk(g_copy_mu);      // one pipelined transfer at a time drives the copy workers
+    int ring_pos = 0, ring_used = 0;
+    auto drain = [&](int c) -> int {      // results of chunk c: wait for its D2H, copy out of the pinned slot
+        cudaEvent_t ev_out;
+        CKR(pipe_event(ix, 3 * c + 3, &ev_out));
+        CK(cudaEventSynchronize(ev_out));
+        if (stage_out) {
+            const int64_t a = cuts[c], m = cuts[c + 1] - cuts[c];
+            const uint8_t* slot = ix->out_slot[c & 1];
+            CopyPool::get().memcpy_parallel(D + a * k, slot, static_cast<size_t>(m) * row_d);
+            CopyPool::get().memcpy_parallel(I + a * k, slot + static_cast<size_t>(max_chunk) * row_d, static_cast<size_t>(m) * row_i);
+        }
+        return 0;
+    };
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t a = cuts[c], m = cuts[c + 1] - cuts[c];
+        cudaEvent_t ev_in, ev_done, ev_out;
+        CKR(pipe_event(ix, 3 * c + 1, &ev_in));
+        CKR(pipe_event(ix, 3 * c + 2, &ev_done));
+        CKR(pipe_event(ix, 3 * c + 3, &ev_out));
+        if (x_host) {
+            const char* src = reinterpret_cast<const char*>(x) + static_cast<size_t>(a) * row_in;
+            char* dst = static_cast<char*>(ix->q_raw.p) + static_cast<size_t>(a) * row_in;
+            const size_t bytes = static_cast<size_t>(m) * row_in;
+            if (!stage_in) {
+                CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ix->s_in));
+            } else {
+                for (size_t off = 0; off < bytes; off += kStageChunk) {
+                    const size_t len = std::min(kStageChunk, bytes - off);
+                    const int b = ring_pos;
+                    ring_pos = (ring_pos + 1) % 3;
+                    if (ring_used >= 3) CK(cudaEventSynchronize(ix->in_ring_ev[b]));      // the DMA that last read this slot is done
+                    else ++ring_used;
+                    CopyPool::get().memcpy_parallel(ix->in_ring[b], src + off, len);
+                    CK(cudaMemcpyAsync(dst + off, ix->in_ring[b], len, cudaMemcpyHostToDevice, ix->s_in));
+                    CK(cudaEventRecord(ix->in_ring_ev[b], ix->s_in));
+                }
+            }
+            CK(cudaEventRecord(ev_in, ix->s_in));
+            CK(cudaStreamWaitEvent(ix->stream, ev_in, 0));
+        }
+        CKR(search_device(ix, xq_dev + a * ix->d, m, k, D_dev + a * k, I_dev + a * k));
+        if (out_host) {
+            CK(cudaEventRecord(ev_done, ix->stream));
+            if (stage_out && c >= 2) CKR(drain(c - 2));      // frees the pinned slot this chunk's results go to
+            CK(cudaStreamWaitEvent(ix->s_out, ev_done, 0));
+            if (stage_out) {
+                uint8_t* slot = ix->out_slot[c & 1];
+                CK(cudaMemcpyAsync(slot, D_dev + a * k, static_cast<size_t>(m) * row_d, cudaMemcpyDeviceToHost, ix->s_out));
+                CK(cudaMemcpyAsync(slot + static_cast<size_t>(max_chunk) * row_d, I_dev + a * k, static_cast<size_t>(m) * row_i,
+                                   cudaMemcpyDeviceToHost, ix->s_out));
+            } else {
+                CK(cudaMemcpyAsync(D + a * k, D_dev + a * k, static_cast<size_t>(m) * row_d, cudaMemcpyDeviceToHost, ix->s_out));
+                CK(cudaMemcpyAsync(I + a * k, I_dev + a * k, static_cast<size_t>(m) * row_i, cudaMemcpyDeviceToHost, ix->s_out));
+            }
+            CK(cudaEventRecord(ev_out, ix->s_out));
+        }
+    }
+    if (out_host) {
+        for (int c = std::max(0, n_chunks - 2); c < n_chunks; ++c) CKR(drain(c));
+        // later work on the compute stream must not overwrite d_out / i_out under a pending D2H: all of them are done here
+    } else {
+        CK(cudaStreamSynchronize(ix->stream));      // host queries: the caller may reuse x once we return
+    }
+    if (stage_in)
+        for (int b = 0; b < std::min(ring_used, 3); ++b) CK(cudaEventSynchronize(ix->in_ring_ev[b]));
+    return 0;
+}
+
 int agp_index_search(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, int k, float* D, int64_t* I, int out_mem_kind) {
     if (!ix) return set_err(AGP_EINVAL, "index is null");
     if (nq < 0) return set_err(AGP_EINVAL, "nq must be >= 0");
@@ -1193,45 +1403,9 @@ int agp_index_search(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, 
     if (!x || !D || !I) return set_err(AGP_EINVAL, "x, D and I must be non-null");
     if (nq > 0x7fffffffLL) return set_err(AGP_EINVAL, "nq too large");
     ENTER(ix);
-
-    const float* xq_dev = x;
-    if (x_mem_kind != AGP_MEM_DEVICE) {
-        CKR(ensure(ix->q_raw, static_cast<size_t>(nq) * ix->d * sizeof(float)));
-        CKR(copy_h2d(ix, ix->q_raw.p, x, static_cast<size_t>(nq) * ix->d * sizeof(float)));
-        xq_dev = static_cast<const float*>(ix->q_raw.p);
-    }
-    float* D_dev = D;
-    int64_t* I_dev = I;
-    if (out_mem_kind != AGP_MEM_DEVICE) {
-        CKR(ensure(ix->d_out, static_cast<size_t>(nq) * k * sizeof(float)));
-        CKR(ensure(ix->i_out, static_cast<size_t>(nq) * k * sizeof(int64_t)));
-        D_dev = static_cast<float*>(ix->d_out.p);
-        I_dev = static_cast<int64_t*>(ix->i_out.p);
-    }
-
-    int rc = 0;
-    if (ix->ntotal == 0) {
-        rc = search_empty(ix, nq, k, D_dev, I_dev);
-    } else {
-        switch (ix->mode) {
-            case AGP_PRECISION_AUTO:
-                rc = (nq < kMaxSmallNq) ? search_diff(ix, xq_dev, nq, k, D_dev, I_dev) : search_screen(ix, xq_dev, nq, k, D_dev, I_dev);
-                break;
-            case AGP_PRECISION_FP16_SCREEN: rc = search_screen(ix, xq_dev, nq, k, D_dev, I_dev); break;
-            case AGP_PRECISION_3XTF32:
-            case AGP_PRECISION_3XFP16: rc = search_tc(ix, xq_dev, nq, k, D_dev, I_dev); break;
-            case AGP_PRECISION_FP32_SIMT: rc = search_simt(ix, xq_dev, nq, k, D_dev, I_dev); break;
-            default: rc = search_diff(ix, xq_dev, nq, k, D_dev, I_dev); break;
-        }
-    }
-    if (rc != 0) return rc;
-    if (out_mem_kind != AGP_MEM_DEVICE) {
-        CKR(copy_d2h_sync(ix, D, D_dev, static_cast<size_t>(nq) * k * sizeof(float)));
-        CKR(copy_d2h_sync(ix, I, I_dev, static_cast<size_t>(nq) * k * sizeof(int64_t)));
-    } else if (x_mem_kind != AGP_MEM_DEVICE) {
-        CK(cudaStreamSynchronize(ix->stream));
-    }
-    return 0;
+    if (x_mem_kind == AGP_MEM_DEVICE && out_mem_kind == AGP_MEM_DEVICE)
+        return search_device(ix, x, nq, k, D, I);      // asynchronous on the index's stream: nothing here waits for the GPU
+    return search_host_pipelined(ix, nq, x, x_mem_kind, k, D, I, out_mem_kind);
 }
 
 int agp_index_search_masked(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, int k, const int64_t* excl_offsets,

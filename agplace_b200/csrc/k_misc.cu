@@ -392,6 +392,163 @@ __global__ void __launch_bounds__(128) recall_kernel(const int64_t* __restrict__
 }
 
 
+// One launch resets everything a screened search needs (was: two fill kernels + three memsets): list counters, overflow
+// flags and list head, the shared bounds (+inf) and the zero padding rows of the query plane.
+__global__ void screen_init_kernel(int* __restrict__ pcount, uint32_t* __restrict__ hthr, int64_t n_lists, int* __restrict__ ovf,
+                                   uint32_t* __restrict__ gthr, int64_t nq, int* __restrict__ ovf_count, uint4* __restrict__ pad,
+                                   int64_t pad_vec) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (int64_t i = i0; i < n_lists; i += stride) {
+        pcount[i] = 0;
+        hthr[i] = 0x7f800000u;
+    }
+    for (int64_t i = i0; i < nq; i += stride) {
+        ovf[i] = 0;
+        gthr[i] = 0x7f800000u;
+    }
+    for (int64_t i = i0; i < pad_vec; i += stride) pad[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (i0 == 0) *ovf_count = 0;
+}
+
+// Exact answer for the queries the screen flagged (certified band wider than the candidate slots: mass duplicates; rows
+// the fp16 plane cannot represent), run ON THE DEVICE from the overflow list the finish kernel wrote -- the host never
+// reads the count, so a screened search needs no synchronisation.  Launched after every finalize; with an empty list
+// (the normal case) every block returns after one load.
+// Up to 4 flagged queries per block share one pass over the database: warps evaluate the fp32 difference form (same
+// per-lane summation order as diff_small_kernel: bit-identical distances to a small-batch search), keys below the
+// query's current k-th key are appended to a 1024-entry shared buffer that is sorted (block bitonic) whenever it fills.
+constexpr int OVF_CAP = 1024, OVF_GQ = 4, OVF_ROWS = 4;      // rows per warp per round
+
+__device__ __forceinline__ void block_sort_1024(uint64_t* keys) {
+    for (int size = 2; size <= OVF_CAP; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < OVF_CAP / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool asc = (lo & size) == 0;
+                const uint64_t a = keys[lo], b = keys[hi];
+                if ((a > b) == asc) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) ovf_exact_kernel(const int* __restrict__ ovf_count, const int* __restrict__ ovf_list,
+                                                        const float* __restrict__ xq, const float* __restrict__ xb, int64_t n, int d,
+                                                        int k, int64_t id_base, int ip, int gq, float* __restrict__ D,
+                                                        int64_t* __restrict__ I, unsigned long long* __restrict__ stat_fallback) {
+    const int total = *ovf_count;
+    if (total <= 0) return;
+    extern __shared__ __align__(16) uint8_t ovf_smem[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(ovf_smem);                         // [gq][OVF_CAP]
+    float* qrows = reinterpret_cast<float*>(ovf_smem + static_cast<size_t>(gq) * OVF_CAP * sizeof(uint64_t));   // [gq][d]
+    __shared__ int cnt[OVF_GQ], qid[OVF_GQ];
+    __shared__ uint64_t thr[OVF_GQ];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && stat_fallback) atomicAdd(stat_fallback, static_cast<unsigned long long>(total));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const bool vec = ((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15) == 0);
+    for (int base = blockIdx.x * gq; base < total; base += gridDim.x * gq) {
+        const int g = min(gq, total - base);
+        __syncthreads();
+        if (threadIdx.x < g) {
+            qid[threadIdx.x] = ovf_list[base + threadIdx.x];
+            cnt[threadIdx.x] = 0;
+            thr[threadIdx.x] = kEmptyKey;
+        }
+        __syncthreads();
+        for (int j = 0; j < g; ++j)
+            for (int c = threadIdx.x; c < d; c += blockDim.x) qrows[j * d + c] = xq[static_cast<int64_t>(qid[j]) * d + c];
+        __syncthreads();
+        auto compact = [&](int j, bool last) {      // block-uniform: sort list j, keep the best k, tighten its threshold
+            const int c = cnt[j];
+            __syncthreads();
+            for (int i = c + threadIdx.x; i < OVF_CAP; i += blockDim.x) keys[j * OVF_CAP + i] = kEmptyKey;
+            __syncthreads();
+            block_sort_1024(keys + j * OVF_CAP);
+            if (threadIdx.x == 0) {
+                cnt[j] = min(c, k);
+                if (c >= k) thr[j] = keys[j * OVF_CAP + k - 1];
+            }
+            __syncthreads();
+            (void)last;
+        };
+        for (int64_t r0 = 0; r0 < n; r0 += warps * OVF_ROWS) {
+#pragma unroll 1
+            for (int u = 0; u < OVF_ROWS; ++u) {
+                const int64_t r = r0 + warp * OVF_ROWS + u;
+                if (r >= n) break;
+                const float* row = xb + r * d;
+                float acc[OVF_GQ];
+#pragma unroll
+                for (int j = 0; j < OVF_GQ; ++j) acc[j] = 0.f;
+                if (vec) {
+                    for (int c = lane; c < (d >> 2); c += 32) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(row) + c);
+#pragma unroll
+                        for (int j = 0; j < OVF_GQ; ++j) {
+                            if (j < g) {
+                                const float4 a = reinterpret_cast<const float4*>(qrows + j * d)[c];
+                                if (ip) {
+                                    acc[j] = fmaf(a.x, v.x, acc[j]);
+                                    acc[j] = fmaf(a.y, v.y, acc[j]);
+                                    acc[j] = fmaf(a.z, v.z, acc[j]);
+                                    acc[j] = fmaf(a.w, v.w, acc[j]);
+                                } else {
+                                    float t;
+                                    t = a.x - v.x; acc[j] = fmaf(t, t, acc[j]);
+                                    t = a.y - v.y; acc[j] = fmaf(t, t, acc[j]);
+                                    t = a.z - v.z; acc[j] = fmaf(t, t, acc[j]);
+                                    t = a.w - v.w; acc[j] = fmaf(t, t, acc[j]);
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    for (int c = lane; c < d; c += 32) {
+                        const float v = __ldg(row + c);
+#pragma unroll
+                        for (int j = 0; j < OVF_GQ; ++j) {
+                            if (j < g) {
+                                const float a = qrows[j * d + c];
+                                const float t = ip ? a : a - v;
+                                acc[j] = fmaf(t, ip ? v : t, acc[j]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < OVF_GQ; ++j) {
+                    if (j < g) {
+                        float a = acc[j];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFull, a, o);
+                        if (lane == 0) {
+                            const uint64_t key = ip ? pack_key_signed(-a, static_cast<uint32_t>(r)) : pack_key(a, static_cast<uint32_t>(r));
+                            if (key < thr[j]) keys[j * OVF_CAP + atomicAdd(&cnt[j], 1)] = key;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // a round appends at most warps * OVF_ROWS keys per list: compact while that still fits
+            for (int j = 0; j < g; ++j)
+                if (cnt[j] > OVF_CAP - warps * OVF_ROWS) compact(j, false);
+        }
+        for (int j = 0; j < g; ++j) {
+            compact(j, true);
+            const int have = cnt[j];
+            const int64_t q = qid[j];
+            for (int i = threadIdx.x; i < k; i += blockDim.x) {
+                const bool empty = i >= have;
+                const uint64_t key = empty ? kEmptyKey : keys[j * OVF_CAP + i];
+                D[q * k + i] = ip ? (empty ? -3.4028234663852886e38f : -key_value_signed(key)) : (empty ? 3.4028234663852886e38f : key_dist(key));
+                I[q * k + i] = empty ? -1 : id_base + static_cast<int64_t>(key_idx(key));
+            }
+        }
+    }
+}
+
 __global__ void gather_rows_kernel(const float* __restrict__ x, const int* __restrict__ list, int n, int d, float* __restrict__ out) {
     const int r = blockIdx.x;
     if (r >= n) return;
@@ -544,6 +701,31 @@ cudaError_t launch_best_of_lists(const float* xq, const float* rows, int d, cons
                                  int64_t* best_pos, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
     best_of_lists_kernel<<<static_cast<unsigned>((nq + 3) / 4), 128, 0, st>>>(xq, rows, d, off, nq, best_d, best_pos);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_screen_init(int* pcount, uint32_t* hthr, int64_t n_lists, int* ovf, uint32_t* gthr, int64_t nq, int* ovf_count,
+                               void* pad, size_t pad_bytes, cudaStream_t st) {
+    const int64_t pad_vec = static_cast<int64_t>(pad_bytes / 16);      // plane rows are multiples of 128 bytes
+    const int64_t work = std::max<int64_t>({n_lists, nq, pad_vec, 1});
+    const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((work + 255) / 256, 2048));
+    screen_init_kernel<<<blocks, 256, 0, st>>>(pcount, hthr, n_lists, ovf, gthr, nq, ovf_count, static_cast<uint4*>(pad), pad_vec);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ovf_exact(const int* ovf_count, const int* ovf_list, const float* xq, const float* xb, int64_t n, int d, int k,
+                             int64_t id_base, int ip, float* D, int64_t* I, unsigned long long* stat_fallback, int num_sms,
+                             cudaStream_t st) {
+    if (k > OVF_CAP / 2) return cudaErrorInvalidValue;
+    // as many queries per block (<= 4) as fit next to their key buffers in shared memory
+    const size_t budget = 160 * 1024;
+    int gq = OVF_GQ;
+    while (gq > 1 && static_cast<size_t>(gq) * (OVF_CAP * sizeof(uint64_t) + static_cast<size_t>(d) * sizeof(float)) > budget) --gq;
+    const size_t smem = static_cast<size_t>(gq) * (OVF_CAP * sizeof(uint64_t) + static_cast<size_t>(d) * sizeof(float));
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;      // d > ~48k
+    cudaError_t e = cudaFuncSetAttribute(ovf_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    ovf_exact_kernel<<<num_sms, 256, smem, st>>>(ovf_count, ovf_list, xq, xb, n, d, k, id_base, ip, gq, D, I, stat_fallback);
     return cudaGetLastError();
 }
 

@@ -147,6 +147,13 @@ cudaError_t launch_best_of_lists(const float* xq, const float* rows, int d, cons
 cudaError_t launch_gather_rows(const float* x, const int* list, int n, int d, float* out, cudaStream_t st);
 cudaError_t launch_scatter_results(const float* Dt, const int64_t* It, const int* list, int n, int k, float* D, int64_t* I, cudaStream_t st);
 cudaError_t launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st);
+// one launch that resets the per-search state of the screen (list counters, bounds, overflow flags, query-plane padding)
+cudaError_t launch_screen_init(int* pcount, uint32_t* hthr, int64_t n_lists, int* ovf, uint32_t* gthr, int64_t nq, int* ovf_count,
+                               void* pad, size_t pad_bytes, cudaStream_t st);
+// device-side exact fallback over the overflow list written by the finish kernel (no host round trip)
+cudaError_t launch_ovf_exact(const int* ovf_count, const int* ovf_list, const float* xq, const float* xb, int64_t n, int d, int k,
+                             int64_t id_base, int ip, float* D, int64_t* I, unsigned long long* stat_fallback, int num_sms,
+                             cudaStream_t st);
 // fp64 radius neighbours (k_misc.cu:radius_kernel): fill = false -> counts[nq]; fill = true -> ids at the CSR offsets, ascending
 cudaError_t launch_radius(bool fill, const double* db, int64_t n, int dim, const double* q, int64_t nq, double r2, int64_t* counts,
                           const int64_t* offsets, int64_t* ids, cudaStream_t st);

@@ -223,6 +223,15 @@ class IndexFlatL2:
         return ms.value, n.value
 
 
+    PHASES = ("distance", "prep", "finish", "fallback")
+
+    def get_profile_phases(self, reset=True):
+        """{phase: (milliseconds, launches)} accumulated since the last reset (``agp_index_get_profile_phases``)."""
+        ms = (ctypes.c_double * 4)()
+        n = (ctypes.c_int64 * 4)()
+        _lib.check(self._lib.agp_index_get_profile_phases(self._h, ms, n, int(reset)), "agp_index_get_profile_phases")
+        return {name: (ms[i], n[i]) for i, name in enumerate(self.PHASES)}
+
     def set_knob(self, name: str, value: int):
         """Development switch of this index (A/B variants of the screen kernel; ``include/agpknn.h:agp_index_set_knob``)."""
         _lib.check(self._lib.agp_index_set_knob(self._h, name.encode(), int(value)), "agp_index_set_knob")

@@ -75,6 +75,7 @@ class ShardedIndexFlatL2:
         self._chunks = []          # (local_start, global_start, count) of this rank's rows, add order
         self._local_rows = 0
         self._result_device = result_device   # torch device for the exchange (None: cuda:<index device>)
+        self.phase_events = None              # bench.py: set to [] to collect (name, start_event, end_event) per search
 
     @property
     def ntotal(self):
@@ -123,6 +124,33 @@ class ShardedIndexFlatL2:
         self._ntotal = 0
 
     # ------------------------------------------------------------------ search
+    def _phase(self, name):
+        """Context manager recording a CUDA-event pair around one phase of search() when ``phase_events`` is a list."""
+        import contextlib
+        import torch
+        if self.phase_events is None or not torch.cuda.is_available():
+            return contextlib.nullcontext()
+
+        @contextlib.contextmanager
+        def cm():
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            yield
+            e1.record()
+            self.phase_events.append((name, e0, e1))
+        return cm()
+
+    def phase_ms(self, reset=True):
+        """{phase: total milliseconds} of the collected events (synchronises)."""
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.phase_events or []:
+            out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        if reset and self.phase_events is not None:
+            self.phase_events = []
+        return out
+
     def _engine_applies_base(self):
         """One contiguous chunk on this rank: the engine adds its global start itself (agp_index_set_id_base).  The base
         is re-derived from the chunk table before EVERY search and cleared otherwise, so no stale base survives an
@@ -164,7 +192,8 @@ class ShardedIndexFlatL2:
             xh = xs if _is_torch(xs) else torch.from_numpy(np.ascontiguousarray(xs, dtype=np.float32))
             xs = xh.to(torch.device("cuda", self.local.device), dtype=torch.float32, non_blocking=True)
         if xs.shape[0]:
-            D_loc, I_loc = self.local.search(xs, k)
+            with self._phase("local_search"):
+                D_loc, I_loc = self.local.search(xs, k)
         else:
             D_loc, I_loc = np.empty((0, k), np.float32), np.empty((0, k), np.int64)
         if not _is_torch(D_loc):
@@ -187,12 +216,14 @@ class ShardedIndexFlatL2:
             rows = nq
         d_bytes = (rows * k * 4 + 7) // 8 * 8
         i_bytes = rows * k * 8
-        send = torch.zeros(d_bytes + i_bytes, dtype=torch.uint8, device=dev)
-        n_loc = D_loc.shape[0] * k
-        send[: n_loc * 4].view(torch.float32).copy_(D_loc.reshape(-1))
-        send[d_bytes: d_bytes + n_loc * 8].view(torch.int64).copy_(I_loc.reshape(-1))
-        recv = torch.empty(self.world * (d_bytes + i_bytes), dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(recv, send, group=self.group)        # the single exchange step
+        with self._phase("pack"):
+            send = torch.zeros(d_bytes + i_bytes, dtype=torch.uint8, device=dev)
+            n_loc = D_loc.shape[0] * k
+            send[: n_loc * 4].view(torch.float32).copy_(D_loc.reshape(-1))
+            send[d_bytes: d_bytes + n_loc * 8].view(torch.int64).copy_(I_loc.reshape(-1))
+            recv = torch.empty(self.world * (d_bytes + i_bytes), dtype=torch.uint8, device=dev)
+        with self._phase("all_gather"):
+            dist.all_gather_into_tensor(recv, send, group=self.group)        # the single exchange step
         recv2 = recv.view(self.world, d_bytes + i_bytes)
 
         if self.shard == "query":
@@ -206,10 +237,11 @@ class ShardedIndexFlatL2:
             # int64 view must start 8-byte aligned: d_bytes is a multiple of 8
             I_lists = recv.view(torch.int64)[d_bytes // 8:]
             id_bound = self._ntotal
-            if self._metric == METRIC_L2:
-                Dg, Ig = self._merge(D_lists, stride // 4, I_lists, stride // 8, nq, k, self.world, id_bound)
-            else:
-                Dg, Ig = self._merge(D_lists, stride // 4, I_lists, stride // 8, nq, k, self.world, id_bound, self._metric)
+            with self._phase("merge"):
+                if self._metric == METRIC_L2:
+                    Dg, Ig = self._merge(D_lists, stride // 4, I_lists, stride // 8, nq, k, self.world, id_bound)
+                else:
+                    Dg, Ig = self._merge(D_lists, stride // 4, I_lists, stride // 8, nq, k, self.world, id_bound, self._metric)
 
         if D is not None:
             (D if _is_torch(D) else torch.from_numpy(D)).copy_(Dg)

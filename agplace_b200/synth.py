@@ -57,23 +57,36 @@ def _counter_scale(d):
     return np.float32(1.0 / (_IH_SIGMA * np.sqrt(float(d))))
 
 
-def counter_rows(row_ids, d, seed, chunk=16384):
-    """Rows ``row_ids`` (any int64 array) of the counter-based database ``seed``, on the CPU (numpy)."""
+def counter_rows(row_ids, d, seed, chunk=8192):
+    """Rows ``row_ids`` (any int64 array) of the counter-based database ``seed``, on the CPU (numpy; chunks run on a
+    small thread pool -- numpy releases the GIL inside the integer kernels)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
     row_ids = np.asarray(row_ids, dtype=np.int64).reshape(-1)
     out = np.empty((len(row_ids), d), dtype=np.float32)
     cols = np.arange(d, dtype=np.uint64)[None, :]
     base = np.uint64((seed * _SM_GOLDEN) & 0xFFFFFFFFFFFFFFFF)
     c = _counter_scale(d)
-    with np.errstate(over="ignore"):
-        for i0 in range(0, len(row_ids), chunk):
+    m = np.uint64(0xFFFF)
+
+    def fill(i0):
+        with np.errstate(over="ignore"):
             r = row_ids[i0:i0 + chunk].astype(np.uint64)[:, None]
             z = r * np.uint64(d) + cols + base
             z = (z ^ (z >> np.uint64(30))) * np.uint64(_SM_M1)
             z = (z ^ (z >> np.uint64(27))) * np.uint64(_SM_M2)
             z = z ^ (z >> np.uint64(31))
-            m = np.uint64(0xFFFF)
             a = ((z & m) + ((z >> np.uint64(16)) & m) + ((z >> np.uint64(32)) & m) + (z >> np.uint64(48))).astype(np.int64) - 131070
             out[i0:i0 + chunk] = a.astype(np.float32) * c
+
+    starts = range(0, len(row_ids), chunk)
+    workers = min(len(starts), max(1, (os.cpu_count() or 2) // 2), 16)
+    if workers <= 1:
+        for i0 in starts:
+            fill(i0)
+    else:
+        with ThreadPoolExecutor(workers) as ex:
+            list(ex.map(fill, starts))
     return out
 
 

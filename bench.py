@@ -1,17 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- exact L2 top-k queries/sec on BASELINE.json's configs (driver contract).
 
-    python bench.py --gpus 1 --steps K --warmup W                   # our CUDA engine, cfg2
-    torchrun ... bench.py --gpus N --steps K --warmup W             # N ranks, database row-sharded (strong scaling)
+    python bench.py --gpus 1 --steps K --warmup W                   # our CUDA engine, cfg4 on one GPU
+    torchrun ... bench.py --gpus N --steps K --warmup W             # N ranks: cfg4 row-sharded, all-gather + merge (strong scaling)
     python bench.py --impl reference ...                            # CPU restatement of faiss IndexFlatL2 (oracle port)
 
-A "step" is one pass of the hot path over one query batch: ``IndexFlatL2.search(xq, k)`` against a
-database that is already resident in HBM (``add()`` is one-time and reported separately).
-``value``  : whole-job queries/sec with the queries already on the device (CUDA events, max over ranks).
-``e2e``    : the same through the drop-in API with pinned HOST queries in and HOST (D, I) out every step.
+Default workload = cfg4 (BASELINE.json configs[3]: 10 M x 512 database, 100 k queries, top-100), the configuration the
+metric "queries/sec at 1/2/4/8 B200" and north_star's multi-GPU partition are quoted on; it fits one GPU (33 GB), so
+N = 1 runs the SAME config and N = 2/4/8 shard its rows (total work fixed: strong scaling).  The N = 1 line also
+carries a ``cfg2`` object (configs[1], the round-1 headline) measured in the same process.
+
+A "step" is one pass of the hot path over one query batch: ``IndexFlatL2.search(xq, k)`` against a database that is
+already resident in HBM (``add()`` is one-time and reported separately).
+``value``   : whole-job queries/sec with the queries already on the device (CUDA events, max over ranks).
+``e2e``     : the same through the drop-in call the reference makes -- pageable numpy queries in, numpy (D, I) out
+              (test.py:32) -- host<->device copies inside the timed region.
 ``roofline``: the fused tcgen05 screen kernel, algorithmic flops 2*nq*N*d per launch / its CUDA-event time.
+``phases``  : per-rank CUDA-event breakdown of a step (prep / screen / finish / exchange / merge).
+``verify``  : sampled parity inside warm-up: rows regenerated on the CPU (counter-based generator), oracle top-k.
 ``cpu_baseline``: oracle port (numpy/OpenBLAS sgemm + C heaps) timed here on the host cores, bounded sample.
-Only the cpu_baseline leg and ``--impl reference`` touch ``oracle/``; the product path never does.
+Only verify, the cpu_baseline leg and ``--impl reference`` touch ``oracle/``; the product path never does.
 """
 from __future__ import annotations
 
@@ -19,7 +27,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -38,6 +45,9 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "exact L2 top-k queries/sec"
 UNIT = "queries/s"
+DEVICE_GENERATED = 2e9          # databases above this many bytes are generated on the GPU (counter-based rows)
+PRECISION_DESC = "auto: certified single-pass fp16 tcgen05 screen (fp32 accumulate) + exact fp32 difference-form re-rank"
+KERNEL_DESC = "knn_screen_kernel (tcgen05 cta_group::2 fp16 single-pass distance tiles + fused certified top-k screen)"
 
 
 def load_peaks():
@@ -114,15 +124,30 @@ def workload(name):
     from agplace_b200 import synth
     c = dict(synth.CONFIGS[name])
     c["name"] = name
+    c["device_generated"] = c["n"] * c["d"] * 4 > DEVICE_GENERATED
     return c
 
 
-def make_host_data(c, rows=None):
+def host_queries(c, nq=None):
+    """The query batch of a config (host numpy, what the reference hands to search())."""
     from agplace_b200 import synth
-    n = c["n"] if rows is None else rows
-    xb = synth.descriptors(n, c["d"], c["seed"], "db")
-    xq = synth.descriptors(c["nq"], c["d"], c["seed"] + 7, "q")
-    return xb, xq
+    nq = c["nq"] if nq is None else nq
+    if c["device_generated"]:
+        return synth.counter_rows(np.arange(nq), c["d"], seed=c["seed"] + 7)
+    return synth.descriptors(nq, c["d"], c["seed"] + 7, "q")
+
+
+def host_rows(c, lo, hi):
+    """Database rows [lo, hi) of a config on the host (the whole database only for configs that fit host RAM)."""
+    from agplace_b200 import synth
+    if c["device_generated"]:
+        return synth.counter_rows(np.arange(lo, hi), c["d"], seed=c["seed"])
+    return synth.descriptors(c["n"], c["d"], c["seed"], "db")[lo:hi]
+
+
+GEN_DESC = {True: "counter-based rows generated on the owning GPU (splitmix64 of seed, row, col -> Irwin-Hall(4) -> one fp32 multiply; "
+                  "any row is regenerated bit-for-bit on the CPU for verification), |row| = 1 +- 0.06",
+            False: "host numpy default_rng (seeded), unit-norm rows"}
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -137,6 +162,14 @@ def cpu_search_rate(xb, xq_sample, k, repeats=1):
     return len(xq_sample) / best, best
 
 
+def cpu_sample_plan(c, seconds_per_pass, rate_hint=None):
+    """Bounded CPU sample of a workload: (database rows used, queries used).  The CPU cost of brute-force search is
+    linear in rows x queries, so a sample over R of N rows extrapolates as q/s(N) = q/s(R) * R / N."""
+    rows = min(c["n"], max(100_000, int(2e9 // (c["d"] * 4))))          # <= 2 GB of fp32 rows on the host
+    q = min(c["nq"], 4096)                                               # one faiss sgemm block
+    return rows, q
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -144,22 +177,19 @@ def run_reference(args):
     from oracle import flatl2_oracle as orc
     orc.build()
     c = workload(args.workload)
-    if c["n"] * c["d"] * 4 > 24e9:
-        emit(json.dumps({"impl": "reference", "unavailable": f"{c['name']} database does not fit this host's RAM budget for the CPU port"}))
-        return 0
-    xb, xq = make_host_data(c)
     cores = os.cpu_count() or 1
+    rows, _ = cpu_sample_plan(c, 2.0)
+    xb = host_rows(c, 0, rows)
+    xq = host_queries(c, min(c["nq"], 4096))
     # bounded sample: the CPU path is only efficient on large query blocks (faiss multiplies 4096 queries at a time), so
-    # the rate is probed on 1024 queries (after a throw-away call) and a step is sized for ~2 s of CPU work -- a whole
-    # --steps K run stays within ~2 minutes -- rather than on a sliver of the batch that would understate the CPU
-    cpu_search_rate(xb, xq[: min(256, c["nq"])], c["k"])
-    rate, _ = cpu_search_rate(xb, xq[: min(1024, c["nq"])], c["k"])
+    # the rate is probed on 1024 queries (after a throw-away call) and a step is sized so that the whole --steps K run
+    # stays within ~2.5 minutes
+    cpu_search_rate(xb, xq[:256], c["k"])
+    rate, _ = cpu_search_rate(xb, xq[: min(1024, len(xq))], c["k"])
     n_calls = max(args.steps + min(args.warmup, 2), 1)
-    per_step_s = min(2.0, 150.0 / n_calls)
-    sample_q = int(min(c["nq"], max(256, rate * per_step_s)))
-    # one full faiss query block (4096) whenever the whole run still fits ~2.5 minutes: smaller blocks run the sgemm
-    # below its efficient size (the 1024-query probe understates the full-block rate about 2x)
-    if sample_q < 4096 <= c["nq"] and 4096 / rate * n_calls <= 150.0:
+    per_step_s = min(4.0, 150.0 / n_calls)
+    sample_q = int(min(len(xq), max(256, rate * per_step_s)))
+    if sample_q < 4096 <= len(xq) and 4096 / rate * n_calls <= 150.0:
         sample_q = 4096
     sample = xq[:sample_q]
     for _ in range(max(1, min(args.warmup, 2))):
@@ -168,14 +198,17 @@ def run_reference(args):
     for _ in range(args.steps):
         orc.knn_fp32(sample, xb, c["k"])
     dt = time.perf_counter() - t0
-    value = sample_q * args.steps / dt
-    sample_desc = f"{sample_q} of {c['nq']} queries x full {c['n']}x{c['d']} database per step, k={c['k']}"
+    scale = rows / c["n"]                      # linear extrapolation from the row sample to the full database
+    value = sample_q * args.steps / dt * scale
+    sample_desc = (f"{sample_q} of {c['nq']} queries x {rows} of {c['n']} database rows x {c['d']}-d per step, k={c['k']}"
+                   + (f"; queries/s extrapolated linearly in rows (x {scale:.4g})" if scale != 1.0 else ""))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.workload in ("cfg4", "cfg5") else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{c['name']}: {c['desc']}", "n": c["n"], "nq": c["nq"], "d": c["d"], "k": c["k"],
-                   "note": "faiss-IndexFlatL2-equivalent CPU restatement (faiss not installable in this image); bounded query sample per step"},
+                   "note": "faiss-IndexFlatL2-equivalent CPU restatement (faiss not installable in this image); bounded sample per step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "threads": orc.num_threads(), "kind": "port", "sample": sample_desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -185,6 +218,148 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def fill_index(index, local, c, lo, hi, dev, world, shard_mode):
+    """Make rows [lo, hi) of the config's database resident on this rank."""
+    import torch
+    from agplace_b200 import synth
+    local.reserve(hi - lo)
+    if not c["device_generated"]:
+        xb = host_rows(c, 0, c["n"])
+        if world == 1 or shard_mode == "query":
+            index.add(xb)
+        else:
+            index.add_local(xb[lo:hi], lo, c["n"])
+        return xb
+    step_rows = max(8192, int((1 << 27) // c["d"]))        # 128 M elements per generated block
+    for a in range(lo, hi, step_rows):
+        b = min(hi, a + step_rows)
+        x = synth.counter_rows_device(a, b, c["d"], seed=c["seed"], device=dev)
+        if world == 1 or shard_mode == "query":
+            index.add(x)
+        else:
+            index.add_local(x, a, 0)
+        del x
+    if world > 1 and shard_mode == "db":
+        index._ntotal = c["n"]
+    torch.cuda.empty_cache()
+    return None
+
+
+def verify_sample(c, xq, D, I, n_queries=64, n_blocks=40, block=4096):
+    """Sampled parity of a search over a database the CPU cannot scan: for ``n_queries`` queries spread over the batch,
+    regenerate on the CPU (counter-based generator) every returned row plus ``n_blocks`` random blocks of ``block``
+    rows, run the oracle over that subset, and require the engine's (D, I) to be exactly the oracle's top-k of the
+    subset (any row of the subset closer than the engine's k-th would show up as a mismatch)."""
+    from oracle import flatl2_oracle as orc
+    t0 = time.perf_counter()
+    rng = np.random.default_rng(12345)
+    qs = np.unique(np.linspace(0, len(xq) - 1, n_queries).astype(np.int64))
+    k = D.shape[1]
+    blocks = rng.choice(max(1, c["n"] // block), size=min(n_blocks, max(1, c["n"] // block)), replace=False)
+    ids = np.unique(np.concatenate([(b * block + np.arange(block)) for b in blocks] + [I[qs].reshape(-1)]))
+    ids = ids[(ids >= 0) & (ids < c["n"])]
+    from agplace_b200 import synth
+    rows = synth.counter_rows(ids, c["d"], seed=c["seed"]) if c["device_generated"] else host_rows(c, 0, c["n"])[ids]
+    Dr, Ir = orc.knn_fp32(xq[qs], rows, k)
+    Ir = np.where(Ir >= 0, ids[np.maximum(Ir, 0)], -1)
+    # BASELINE.json tolerance: ids identical except ties within 1e-5 relative, distances within 1e-4 relative (the
+    # oracle evaluates the expansion form like faiss: + 8 ulp of |q|^2 + |x|^2 of cancellation error)
+    ok, msg = orc.compare_knn(D[qs], I[qs], Dr, Ir, xq=xq[qs], xb=rows, abs_floor_eps=8 * 2.0 ** -24)
+    rel = float(np.max(np.abs(D[qs] - Dr) / np.maximum(Dr, 1e-30)))
+    sorted_ok = bool(np.all(np.diff(D[qs], axis=1) >= 0))
+    return {"ok": bool(ok and sorted_ok), "queries": int(len(qs)), "rows_regenerated": int(len(ids)),
+            "of_rows": int(c["n"]), "max_rel_distance_error": rel, "ids_identical": bool(np.array_equal(I[qs], Ir)),
+            "detail": ("" if ok else msg)[:200], "seconds": round(time.perf_counter() - t0, 2),
+            "method": "oracle top-k over (returned rows + random row blocks) regenerated on the CPU == engine result"}
+
+
+def bench_single(agp, _lib, c, dev, local_rank, steps, warmup, peaks, clocks_on=True, verify=True):
+    """One GPU, one index: returns the measurement dict of a workload (used for the N = 1 line and the cfg2 extra)."""
+    import torch
+    n, nq, d, k = c["n"], c["nq"], c["d"], c["k"]
+    t0 = time.perf_counter()
+    index = agp.IndexFlatL2(d, device=local_rank)
+    xb = fill_index(index, index, c, 0, n, dev, 1, "single")
+    torch.cuda.synchronize()
+    add_s = time.perf_counter() - t0
+    xq = host_queries(c)
+    xq_dev = torch.from_numpy(xq).to(dev)
+
+    for _ in range(max(warmup, 3) - 1):
+        index.search(xq_dev, k)
+    Dw, Iw = index.search(xq_dev, k)
+    ver = None
+    if verify:
+        ver = verify_sample(c, xq, Dw.cpu().numpy(), Iw.cpu().numpy())
+    del Dw, Iw
+    index.set_profiling(True)
+    index.get_profile_phases(reset=True)
+    sampler = ClockSampler(local_rank) if clocks_on else None
+    launches0 = _lib.kernel_launches()
+    if sampler:
+        sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        index.search(xq_dev, k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    launches = _lib.kernel_launches() - launches0
+    phases = index.get_profile_phases(reset=True)
+    index.set_profiling(False)
+
+    # e2e: the reference's call -- pageable numpy in, numpy out
+    for _ in range(2):
+        index.search(xq, k)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        De, Ie = index.search(xq, k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    out = dict(index=index, xb=xb, xq=xq, ms=ms, ms_e2e=ms_e2e, clocks=clocks, launches=launches, phases=phases, add_s=add_s,
+               verify=ver, e2e_result_shapes=(tuple(De.shape), str(De.dtype), tuple(Ie.shape), str(Ie.dtype)))
+    return out
+
+
+def roofline_of(c, n_local, nq_local, steps, phases, ms, clocks, peaks):
+    kernel_ms, kernel_n = phases["distance"]
+    flops_per_launch = 2.0 * nq_local * n_local * c["d"] * (steps / max(kernel_n, 1))      # > 1 launch per step: 65536-query chunks
+    avg_kernel_ms = kernel_ms / max(kernel_n, 1)
+    achieved = flops_per_launch / (avg_kernel_ms * 1e-3) / 1e12 if avg_kernel_ms > 0 else 0.0
+    # burst peak when the clock record shows the kernel ran at full clock without a power cap, sustained otherwise
+    burst = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"]
+                 and "sw_power_cap" not in (clocks.get("reasons") or []))
+    peak = peaks["bf16"] if burst else peaks["bf16_sustained"]
+    traffic, traffic_src = None, None
+    tp = ROOT / "profiles" / "roofline_traffic.json"
+    if tp.exists():
+        try:
+            ent = json.loads(tp.read_text()).get(c["name"], {})
+            traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
+        except Exception:
+            pass
+    return {
+        "bound": "tensor", "kernel": KERNEL_DESC, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": ("dense bf16 BURST (SM clock at max, no power cap during the timed region)" if burst else
+                        "dense bf16 SUSTAINED (power-capped / long timed region)") + f", {peaks['source']}; burst {peaks['bf16']}, sustained {peaks['bf16_sustained']}",
+        "frac_of_burst": achieved / peaks["bf16"], "frac_of_sustained": achieved / peaks["bf16_sustained"],
+        "algorithmic_flops_per_launch": flops_per_launch, "avg_launch_ms": avg_kernel_ms, "launches_timed": kernel_n,
+        "kernel_share_of_step": (kernel_ms / ms) if ms else None,
+        "mode": "one fp16 tcgen05 MMA per algorithmic multiply-add (fp16 dense rate = bf16 dense rate); +16/d for the norm chunk",
+    }
+
+
+def phases_ms_per_step(phases, steps):
+    return {name: round(v[0] / steps, 4) for name, v in phases.items()}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -206,191 +381,175 @@ def run_ours(args):
     c = workload(args.workload)
     n, nq, d, k = c["n"], c["nq"], c["d"], c["k"]
     peaks = load_peaks()
-    nq_rank = nq                          # queries of the named config
+    steps = args.steps
 
-    # ---- sharding policy (north_star): row-shard the database only when it "exceeds one GPU"; a database that
-    # fits is replicated and the QUERIES are split across ranks (no redundant work, results concatenated by
-    # the same single all-gather).  --shard db|query overrides.
-    row_bytes = d * 4 + (((d + 63) // 64) * 64 + 64) * 2          # fp32 row + fp16 screen plane row
-    fits = n * row_bytes < 0.6 * torch.cuda.get_device_properties(dev).total_memory
-    shard_mode = args.shard if args.shard != "auto" else ("query" if fits else "db")
     if world == 1:
-        shard_mode = "single"
-    # Scaling mode.  weak (default; queries are independent units, so the path partitions with no data-path
-    # collective): every rank answers its own batch of the config's nq queries against the replicated database,
-    # i.e. the job is world x nq queries and per-GPU work is fixed.  strong: the config's nq queries in total.
-    weak = world > 1 and args.scaling == "weak" and shard_mode == "query"
+        r = bench_single(agp, _lib, c, dev, local_rank, steps, args.warmup, peaks, verify=not args.no_verify)
+        ms, ms_e2e = r["ms"], r["ms_e2e"]
+        line = {
+            "metric": METRIC, "value": nq * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong" if c["name"] in ("cfg4", "cfg5") else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{c['name']}: {c['desc']}", "n": n, "nq": nq, "d": d, "k": k, "precision": PRECISION_DESC,
+                       "sharding": "single GPU (the same config is row-sharded over N ranks at N > 1: strong scaling)",
+                       "l2": "inputs larger than L2 (fp32 rows %.0f MB + fp16 plane %.0f MB + queries %.0f MB vs 126 MB L2)" % (
+                           n * d * 4 / 1e6, n * (d + 64) * 2 / 1e6, nq * d * 4 / 1e6),
+                       "generator": GEN_DESC[c["device_generated"]], "add_seconds": r["add_s"]},
+            "e2e": {"value": nq * steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
+                    "h2d_bytes_per_step": int(nq * d * 4), "d2h_bytes_per_step": int(nq * k * 12),
+                    "call": "IndexFlatL2.search(pageable numpy fp32 [nq, d], k) -> numpy (D fp32, I int64): the reference's call (test.py:32); "
+                            "chunked H2D | compute | D2H pipeline inside agp_index_search",
+                    "result": r["e2e_result_shapes"]},
+            "gpu_launches": int(r["launches"]),
+            "roofline": roofline_of(c, n, nq, steps, r["phases"], ms, r["clocks"], peaks),
+            "phases_ms_per_step": phases_ms_per_step(r["phases"], steps),
+            "clocks": r["clocks"],
+        }
+        if r["verify"] is not None:
+            line["verify"] = r["verify"]
+        if not args.no_cpu_baseline:
+            from oracle import flatl2_oracle as orc
+            orc.build()
+            rows, q = cpu_sample_plan(c, args.cpu_seconds)
+            xb_s = r["xb"][:rows] if r["xb"] is not None else host_rows(c, 0, rows)
+            probe_rate, _ = cpu_search_rate(xb_s, r["xq"][:min(q, 1024)], k)
+            sample_q = int(min(nq, max(256, min(probe_rate * args.cpu_seconds, 4096 * 4))))
+            rate, dt = cpu_search_rate(xb_s, r["xq"][:sample_q], k)
+            scale = rows / n
+            line["cpu_baseline"] = {"value": rate * scale, "unit": UNIT, "cores": os.cpu_count(), "threads": orc.num_threads(), "kind": "port",
+                                    "sample": f"{sample_q} of {nq} queries x {rows} of {n} database rows x {d}-d, k={k}, one pass ({dt:.1f} s)"
+                                              + (f", queries/s extrapolated linearly in rows (x {scale:.4g})" if scale != 1.0 else "")
+                                              + "; faiss-IndexFlatL2-equivalent CPU restatement (numpy/OpenBLAS sgemm + C heaps)"}
+            del xb_s
+        # the round-1 headline config in the same process (configs[1]: 100k x 512, 20k queries, top-50)
+        if c["name"] != "cfg2" and not args.no_cfg2:
+            del r
+            torch.cuda.empty_cache()
+            c2 = workload("cfg2")
+            s2 = max(steps, 20)
+            r2 = bench_single(agp, _lib, c2, dev, local_rank, s2, args.warmup, peaks, verify=not args.no_verify)
+            line["cfg2"] = {
+                "workload": f"cfg2: {c2['desc']}", "value": c2["nq"] * s2 / (r2["ms"] * 1e-3), "unit": UNIT, "ms_per_step": r2["ms"] / s2, "steps": s2,
+                "e2e": {"value": c2["nq"] * s2 / (r2["ms_e2e"] * 1e-3), "unit": UNIT, "ms_per_step": r2["ms_e2e"] / s2,
+                        "h2d_bytes_per_step": int(c2["nq"] * c2["d"] * 4), "d2h_bytes_per_step": int(c2["nq"] * c2["k"] * 12)},
+                "roofline": roofline_of(c2, c2["n"], c2["nq"], s2, r2["phases"], r2["ms"], r2["clocks"], peaks),
+                "phases_ms_per_step": phases_ms_per_step(r2["phases"], s2), "clocks": r2["clocks"], "verify": r2["verify"],
+            }
+        emit(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ N > 1: one process per GPU
+    # north_star's partition: database row-sharded, queries replicated, per-shard top-k lists exchanged with ONE all-gather
+    # and merged.  (--shard query: the zero-exchange alternative for databases that fit one GPU -- queries split.)
+    shard_mode = args.shard if args.shard != "auto" else ("db" if c["name"] in ("cfg4", "cfg5") else "query")
+    weak = args.scaling == "weak" and shard_mode == "query"
+    nq_rank = nq
     if weak:
         nq = nq_rank * world
-    # ---- database: resident in HBM before anything is timed.  db-sharded: rank r owns rows shard_bounds(n)[r].
     lo, hi = shard_bounds(n, world)[rank] if shard_mode == "db" else (0, n)
     t_add0 = time.perf_counter()
-    if n * d * 4 <= 2e9:
-        xb, xq = make_host_data(dict(c, nq=nq))
-        xb_local = xb[lo:hi]
-        gen = "host numpy default_rng (seeded), unit-norm rows"
-    else:   # large configs: generate each shard on its own GPU (seeded per shard), never materialise on the host
-        g = torch.Generator(device=dev); g.manual_seed(c["seed"] * 1000 + (rank if shard_mode == "db" else 0))
-        xb_local = None
-        gen = "device torch.Generator per shard (seeded), unit-norm rows"
-        rng = np.random.default_rng(c["seed"] + 7)
-        xq = rng.standard_normal((nq, d), dtype=np.float32)
-        xq /= np.linalg.norm(xq, axis=1, keepdims=True)
-    if world == 1:
-        index = agp.IndexFlatL2(d, device=local_rank)
-        local = index
-    else:
-        index = ShardedIndexFlatL2(d, device=local_rank, shard=shard_mode)
-        local = index.local
-    local.reserve(hi - lo)
-    if xb_local is not None:
-        if world == 1 or shard_mode == "query":
-            index.add(xb_local)
-        else:
-            index.add_local(xb_local, lo, n)
-    else:
-        step_rows = 262144
-        for a in range(lo, hi, step_rows):
-            b = min(hi, a + step_rows)
-            x = torch.randn((b - a, d), generator=g, device=dev, dtype=torch.float32)
-            x /= x.norm(dim=1, keepdim=True)
-            if world == 1 or shard_mode == "query":
-                index.add(x)
-            else:
-                index.add_local(x, a, 0)
-        if world > 1 and shard_mode == "db":
-            index._ntotal = n
+    index = ShardedIndexFlatL2(d, device=local_rank, shard=shard_mode)
+    local = index.local
+    fill_index(index, local, c, lo, hi, dev, world, shard_mode)
     torch.cuda.synchronize()
     add_s = time.perf_counter() - t_add0
-
-    xq_pinned = torch.from_numpy(xq).pin_memory()
-    xq_dev = xq_pinned.to(dev)
-    D_host = torch.empty((nq, k), dtype=torch.float32).pin_memory()
-    I_host = torch.empty((nq, k), dtype=torch.int64).pin_memory()
-
-    no_gather = shard_mode == "query"      # query-split: results stay partitioned by query, like the inputs
+    xq = host_queries(c, nq)
+    xq_dev = torch.from_numpy(xq).to(dev)
+    no_gather = shard_mode == "query"
 
     def step_device():
-        if no_gather:
-            return index.search(xq_dev, k, gather=False)
-        return index.search(xq_dev, k)
+        return index.search(xq_dev, k, gather=False) if no_gather else index.search(xq_dev, k)
 
     def step_e2e():
-        if world == 1:
-            xd = xq_pinned.to(dev, non_blocking=True)
-            D, I = index.search(xd, k)
-        elif no_gather:   # the sharded index copies only this rank's slice of the queries and returns only its slice of (D, I)
-            D, I = index.search(xq_pinned, k, gather=False)
-        else:
-            D, I = index.search(xq_pinned, k)
-        D_host[: D.shape[0]].copy_(D, non_blocking=True)
-        I_host[: I.shape[0]].copy_(I, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller needs the results on the host
+        # every rank makes the reference's call: pageable numpy in, numpy out
+        return index.search(xq, k, gather=False) if no_gather else index.search(xq, k)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        dist.barrier()
         torch.cuda.synchronize()
 
     rank_spread = {}
 
-    def timed(fn, steps):
+    def timed(fn, nsteps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for _ in range(nsteps):
             fn()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms, -ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)      # slowest rank (the reported time) and fastest rank (diagnostic)
-            ms = float(t[0].item())
-            rank_spread["fastest_rank_ms_per_step"] = -float(t[1].item()) / steps
+        t = torch.tensor([ms, -ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)      # slowest rank (the reported time) and fastest rank (diagnostic)
+        rank_spread["fastest_rank_ms_per_step"] = -float(t[1].item()) / nsteps
         barrier()
-        return ms
+        return float(t[0].item())
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3) - 1):
         step_device()
+    Dw, Iw = step_device()
+    ver = None
+    if rank == 0 and not args.no_verify and not no_gather:
+        ver = verify_sample(c, xq, Dw.cpu().numpy(), Iw.cpu().numpy())
+    del Dw, Iw
     local.set_profiling(True)
-    local.get_profile(reset=True)
+    local.get_profile_phases(reset=True)
+    index.phase_events = []
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = _lib.kernel_launches()
     if sampler:
         sampler.start()
-    ms = timed(step_device, args.steps)
+    ms = timed(step_device, steps)
     spread_device = dict(rank_spread)
     clocks = sampler.stop() if sampler else None
     launches = _lib.kernel_launches() - launches0
-    kernel_ms, kernel_n = local.get_profile(reset=True)
+    phases = local.get_profile_phases(reset=True)
     local.set_profiling(False)
+    ex_phases = index.phase_ms()
+    index.phase_events = None
 
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, steps)
 
-    value = nq * args.steps / (ms * 1e-3)
-    e2e_value = nq * args.steps / (ms_e2e * 1e-3)
-
-    # ---- roofline of the dominant kernel (fused tcgen05 distance + top-k), this rank's shard
     n_local = hi - lo
     nq_local = nq if shard_mode != "query" else (shard_bounds(nq, world)[rank][1] - shard_bounds(nq, world)[rank][0])
-    flops_per_launch = 2.0 * nq_local * n_local * d * (args.steps / max(kernel_n, 1))   # launches per step may exceed 1 (query chunks)
-    avg_kernel_ms = kernel_ms / max(kernel_n, 1)
-    achieved = flops_per_launch / (avg_kernel_ms * 1e-3) / 1e12 if avg_kernel_ms > 0 else 0.0
-    peak = peaks["bf16_sustained"]
-    traffic = None
-    tp = ROOT / "profiles" / "roofline_traffic.json"
-    if tp.exists():
-        try:
-            traffic = json.loads(tp.read_text()).get(c["name"], {}).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {
-        "bound": "tensor", "kernel": "knn_screen_kernel (tcgen05 cta_group::2 fp16 single-pass distance tiles + fused certified top-k screen)",
-        "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak if peak else None, "traffic": traffic,
-        "peak_source": f"dense bf16 sustained (kernel timed inside a long step), {peaks['source']}; burst figure {peaks['bf16']}",
-        "algorithmic_flops_per_launch": flops_per_launch, "avg_launch_ms": avg_kernel_ms, "launches_timed": kernel_n,
-        "kernel_share_of_step": (kernel_ms / ms) if ms else None,
-        "mode": "one fp16 tcgen05 MMA per algorithmic multiply-add (fp16 dense rate = bf16 dense rate); +16/d for the norm chunk",
-    }
-
+    ph = phases_ms_per_step(phases, steps)
+    for name, v in ex_phases.items():
+        ph[name] = round(v / steps, 4)
+    # slowest rank per phase (the step is the max over ranks)
+    names = sorted(ph)
+    t = torch.tensor([ph[nm] for nm in names], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ph_max = {nm: round(float(v), 4) for nm, v in zip(names, t.tolist())}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None, "dtype": "f32",
+        "metric": METRIC, "value": nq * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{c['name']}: {c['desc']}", "n": n, "nq": nq, "d": d, "k": k, "precision": "auto: certified single-pass fp16 tcgen05 screen (fp32 accumulate) + exact fp32 difference-form re-rank",
-                   "sharding": ("single GPU" if world == 1 else
-                                f"database row-sharded over {world} ranks, queries replicated, one NCCL all-gather + merge" if shard_mode == "db" else
-                                f"database fits one GPU: replicated on {world} ranks, queries split across ranks, results stay partitioned by query (no data-path collective); "
+        "config": {"workload": f"{c['name']}: {c['desc']}", "n": n, "nq": nq, "d": d, "k": k, "precision": PRECISION_DESC,
+                   "sharding": (f"database row-sharded over {world} ranks ({n_local} rows on rank 0), queries replicated, per-shard top-k lists "
+                                f"exchanged with one NCCL all-gather per search + merge on every rank; strong scaling (total work fixed)"
+                                if shard_mode == "db" else
+                                f"database replicated on {world} ranks, queries split across ranks, results stay partitioned by query (no data-path collective); "
                                 + (f"weak scaling: {world} x {nq_rank} queries per step" if weak else f"strong scaling: {nq} queries per step in total")),
-                   "l2": "inputs larger than L2 (fp32 rows %.0f MB + fp16 plane %.0f MB + queries %.0f MB per rank vs 126 MB L2)" % (n_local * d * 4 / 1e6, n_local * (d + 64) * 2 / 1e6, nq * d * 4 / 1e6),
-                   "generator": gen, "add_seconds": add_s},
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(nq * d * 4 * (world if shard_mode == "db" else 1)),
-                "d2h_bytes_per_step": int(nq * k * 12 * (world if shard_mode == "db" else 1))},
+                   "comm_nranks": world, "collective_on_data_path": shard_mode == "db",
+                   "l2": "inputs larger than L2 (fp32 rows %.0f MB + fp16 plane %.0f MB + queries %.0f MB per rank vs 126 MB L2)" % (
+                       n_local * d * 4 / 1e6, n_local * (d + 64) * 2 / 1e6, nq * d * 4 / 1e6),
+                   "generator": GEN_DESC[c["device_generated"]], "add_seconds": add_s},
+        "e2e": {"value": nq * steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
+                "h2d_bytes_per_step": int(nq_local * d * 4 * world), "d2h_bytes_per_step": int(nq_local * k * 12 * world),
+                "call": "ShardedIndexFlatL2.search(pageable numpy, k) -> numpy on every rank"},
         "gpu_launches": int(launches * world),
-        "roofline": roofline,
+        "roofline": roofline_of(c, n_local, nq_local, steps, phases, ms, clocks, peaks),
+        "phases_ms_per_step": {"rank0": ph, "max_over_ranks": ph_max},
         "clocks": clocks,
+        "rank_spread": spread_device,
     }
-    if world > 1 and spread_device:     # ms_per_step is the SLOWEST rank's; the fastest rank shows how much of it is rank spread
-        line["rank_spread"] = spread_device
-
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and xb_local is not None:
-        from oracle import flatl2_oracle as orc
-        orc.build()
-        probe_rate, _ = cpu_search_rate(xb, xq[:min(nq, 2048)], k)      # >= half an sgemm block so the probe is representative
-        sample_q = int(min(nq, max(256, probe_rate * args.cpu_seconds)))
-        rate, dt = cpu_search_rate(xb, xq[:sample_q], k)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "threads": orc.num_threads(), "kind": "port",
-                                "sample": f"{sample_q} of {nq} queries x full {n}x{d} database, k={k}, one pass ({dt:.1f} s); "
-                                          "faiss-IndexFlatL2-equivalent CPU restatement (numpy/OpenBLAS sgemm + C heaps)"}
+    if ver is not None:
+        line["verify"] = ver
     if rank == 0:
         emit(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    dist.destroy_process_group()
     return 0
 
 
@@ -421,11 +580,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
-    ap.add_argument("--shard", default="auto", choices=["auto", "db", "query"], help="multi-GPU partitioning (auto: query-split if the database fits one GPU)")
+    ap.add_argument("--workload", default="cfg4", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--shard", default="auto", choices=["auto", "db", "query"],
+                    help="multi-GPU partitioning (auto: row-shard cfg4/cfg5 -- north_star's scheme; query-split the configs that fit one GPU)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = every rank answers its own batch of the config's queries (job = N x nq); strong = nq in total")
+                    help="query-split only: weak = every rank answers its own batch of the config's queries; strong = nq in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-cfg2", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":

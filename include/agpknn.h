@@ -12,8 +12,9 @@
  * sm_100 device every call fails with AGP_ENODEV.
  *
  * Threading: calls on different indexes are independent; one index must not be used from two
- * threads at once (same rule as faiss add()).  Host-output calls return after their stream has
- * been synchronised; device-output calls are asynchronous on the index's stream.
+ * threads at once (same rule as faiss add()).  Host-output calls return after their results have
+ * landed; device-in / device-out calls are asynchronous on the index's stream (no host synchronisation at all: the
+ * screen's overflow fallback runs on the device).
  */
 #ifndef AGPKNN_H
 #define AGPKNN_H
@@ -103,10 +104,20 @@ AGP_API int agp_index_set_stream(agp_index* idx, void* cuda_stream, int use_own_
  * multi-GPU index (one shard per rank). */
 AGP_API int agp_index_set_id_base(agp_index* idx, int64_t id_base);
 
-/* CUDA-event timing of the dominant distance/select kernel of each search (forces a stream
- * synchronise per search while enabled).  get returns accumulated milliseconds and launches. */
+/* CUDA-event timing of the dominant distance/select kernel of each search (event pairs recorded on the
+ * index's stream, read back -- with a synchronise -- only by get).  get returns accumulated milliseconds and launches. */
 AGP_API int agp_index_set_profiling(agp_index* idx, int enable);
 AGP_API int agp_index_get_profile(agp_index* idx, double* kernel_ms, int64_t* kernel_launches, int reset);
+
+/* Per-phase breakdown of the same timing (bench.py's phase table): ms[AGP_N_PHASES], launches[AGP_N_PHASES]. */
+enum agp_phase {
+    AGP_PHASE_DISTANCE = 0, /* the dominant kernel: fused tcgen05 distance tiles + top-k screen (or diff / SIMT / 3x kernels) */
+    AGP_PHASE_PREP = 1,     /* K1 on the queries: norms, fp16 plane, per-search state reset */
+    AGP_PHASE_FINISH = 2,   /* K4 + K6: candidate merge + exact fp32 re-rank of the certified band */
+    AGP_PHASE_FALLBACK = 3, /* device-side exact pass over flagged queries (normally empty) */
+    AGP_N_PHASES = 4
+};
+AGP_API int agp_index_get_profile_phases(agp_index* idx, double* ms, int64_t* launches, int reset);
 
 /* Counters of the single-pass screen: queries it answered, and how many of those had to be re-run
  * through the fp32 FMA path because their certified candidate band did not fit or a row was not

@@ -528,3 +528,75 @@ def test_native_library_was_used():
     search(np.random.default_rng(1).standard_normal((300, 32)).astype(np.float32),
            np.random.default_rng(2).standard_normal((40, 32)).astype(np.float32), 5)
     assert _lib.kernel_launches() > before
+
+
+def test_cuda_tensor_search_is_asynchronous():
+    """N1 contract (include/agpknn.h): a device-in / device-out search only enqueues work -- no host synchronisation
+    anywhere on the path (the screen's overflow fallback runs on the device).  The call must return while the GPU is
+    still busy, and an all-overflow batch (mass duplicates) must behave the same way."""
+    import time
+    import torch
+    import agplace_b200
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    xb = torch.randn((400_000, 256), generator=g, device=dev)
+    xq = torch.randn((40_000, 256), generator=g, device=dev)
+    ix = agplace_b200.IndexFlatL2(256, device=0); ix.add(xb)
+    ix.search(xq[:4096], 20)                     # builds the fp16 plane, sizes the scratch buffers
+    ix.search(xq, 20)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    D, I = ix.search(xq, 20)
+    t_call = time.perf_counter() - t0
+    busy_at_return = not torch.cuda.current_stream().query()
+    torch.cuda.synchronize()
+    t_total = time.perf_counter() - t0
+    assert busy_at_return, "the search call waited for the GPU"
+    assert t_call < 0.5 * t_total, f"call took {t_call * 1e3:.2f} ms of {t_total * 1e3:.2f} ms"
+    # all queries overflow (3 distinct rows x many copies): still no host round trip, still exact
+    xb2 = xb[torch.randint(0, 3, (60_000,), generator=g, device=dev)]
+    ix2 = agplace_b200.IndexFlatL2(256, device=0); ix2.add(xb2)
+    ix2.search(xq[:512], 25)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    D2, I2 = ix2.search(xq[:512], 25)
+    t_call = time.perf_counter() - t0
+    busy_at_return = not torch.cuda.current_stream().query()
+    torch.cuda.synchronize()
+    assert busy_at_return or t_call < 2e-3
+    assert ix2.get_stats()[1] == 1024
+    Dr, Ir = orc.knn_fp32(xq[:64].cpu().numpy(), xb2.cpu().numpy(), 25)
+    ok, msg = orc.compare_knn(D2[:64].cpu().numpy(), I2[:64].cpu().numpy(), Dr, Ir, xq=xq[:64].cpu().numpy(), xb=xb2.cpu().numpy(),
+                              abs_floor_eps=8 * 2.0 ** -24)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_pipeline_returns_the_device_path_bits(pinned):
+    """numpy in / numpy out goes through the chunked H2D | compute | D2H pipeline (agp_index_search with host buffers):
+    every chunk schedule returns exactly what one device-resident search returns."""
+    import torch
+    import agplace_b200
+    rng = np.random.default_rng(41)
+    n, nq, d, k = 60_000, 21_000, 256, 30          # 21.5 MB of queries: the automatic schedule cuts three chunks
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    xq = rng.standard_normal((nq, d)).astype(np.float32)
+    ix = agplace_b200.IndexFlatL2(d); ix.add(xb)
+    Dd, Id = ix.search(torch.from_numpy(xq).cuda(), k)
+    Dd, Id = Dd.cpu().numpy(), Id.cpu().numpy()
+    xin = torch.from_numpy(xq).pin_memory().numpy() if pinned else xq
+    for chunk in (0, 1000, 4096, 7777, 30_000):
+        ix.set_knob("pipe_chunk", chunk)
+        D, I = ix.search(xin, k)
+        np.testing.assert_array_equal(I, Id, err_msg=f"pipe_chunk={chunk}")
+        np.testing.assert_array_equal(D, Dd)
+        if pinned:
+            Dp = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+            Ip = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+            ix.search(xin, k, D=Dp.numpy(), I=Ip.numpy())
+            np.testing.assert_array_equal(Ip.numpy(), Id)
+            np.testing.assert_array_equal(Dp.numpy(), Dd)
+    sample = np.arange(0, nq, 211)
+    Dr, Ir = orc.knn_fp32(xq[sample], xb, k)
+    ok, msg = orc.compare_knn(Dd[sample], Id[sample], Dr, Ir, xq=xq[sample], xb=xb, abs_floor_eps=8 * 2.0 ** -24)
+    assert ok, msg
