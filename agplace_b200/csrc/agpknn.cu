@@ -18,12 +18,16 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
 #include <thread>
 #include <new>
 #include <unordered_map>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <vector>
 
 #include "launch.h"
@@ -155,6 +159,9 @@ namespace {
 constexpr size_t kStageChunk = 8u << 20;
 constexpr size_t kStageMin = 16u << 20;      // below two chunks there is nothing to overlap: the driver path is as fast
 
+// A transfer is cut into 256 KB parts that the pool's threads AND the caller claim with an atomic counter (dynamic load
+// balance: page-fault or NUMA stragglers do not hold the others up).  Workers spin for ~100 us after a job before they
+// go back to sleep, so the back-to-back jobs of one pipelined transfer never pay a futex wake-up.
 class CopyPool {
 public:
     static CopyPool& get() {
@@ -162,50 +169,123 @@ public:
         return *p;
     }
     // dst[0..bytes) = src[0..bytes) using the pool's threads plus the caller
-    void memcpy_parallel(void* dst, const void* src, size_t bytes) {
-        const size_t parts = std::min<size_t>(workers_.size() + 1, std::max<size_t>(1, bytes >> 20));
-        if (parts <= 1) { std::memcpy(dst, src, bytes); return; }
-        const size_t per = ((bytes / parts) + 4095) & ~static_cast<size_t>(4095);
-        std::unique_lock<std::mutex> lk(mu_);
-        pending_ = 0;
-        for (size_t i = 1; i < parts; ++i) {
-            const size_t off = i * per;
-            if (off >= bytes) break;
-            tasks_.push_back({static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, std::min(per, bytes - off)});
-            ++pending_;
+    // stream_dst: dst is pinned staging memory the CPU will not read again (non-temporal stores)
+    void memcpy_parallel(void* dst, const void* src, size_t bytes, bool stream_dst = false) {
+        if (workers_ == 0 || bytes < (size_t(1) << 20)) { copy_part(static_cast<char*>(dst), static_cast<const char*>(src), bytes, stream_dst && bytes >= 65536); return; }
+        Job j;
+        j.stream = stream_dst;
+        j.d = static_cast<char*>(dst);
+        j.s = static_cast<const char*>(src);
+        j.n = bytes;
+        j.n_parts = (bytes + kPart - 1) / kPart;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            job_ = &j;
+            epoch_.fetch_add(1, std::memory_order_release);
         }
-        lk.unlock();
         cv_.notify_all();
-        std::memcpy(dst, src, std::min(per, bytes));
-        lk.lock();
-        done_.wait(lk, [&] { return pending_ == 0; });
+        work(j);
+        while (j.done.load(std::memory_order_acquire) < j.n_parts) cpu_relax();
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            job_ = nullptr;
+        }
+        while (j.active.load(std::memory_order_acquire) != 0) cpu_relax();      // no worker still holds a pointer to j
     }
 
 private:
-    struct Task { char* d; const char* s; size_t n; };
+    static constexpr size_t kPart = size_t(256) << 10;
+    struct Job {
+        char* d = nullptr;
+        const char* s = nullptr;
+        size_t n = 0, n_parts = 0;
+        std::atomic<size_t> next{0}, done{0};
+        std::atomic<int> active{0};
+        bool stream = false;
+    };
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+    // Pinned staging memory is written once by the CPU and read once by the DMA engine: streaming (non-temporal) stores
+    // skip the read-for-ownership of every destination line and keep the copy out of the caches.
+#if defined(__x86_64__)
+    __attribute__((target("avx2"))) static void copy_stream_avx2(char* d, const char* s, size_t n) {
+        size_t head = (32 - (reinterpret_cast<uintptr_t>(d) & 31)) & 31;
+        if (head > n) head = n;
+        std::memcpy(d, s, head);
+        d += head; s += head; n -= head;
+        size_t i = 0;
+        for (; i + 128 <= n; i += 128) {
+            const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i));
+            const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i + 32));
+            const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i + 64));
+            const __m256i e = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i + 96));
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(d + i), a);
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(d + i + 32), b);
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(d + i + 64), c);
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(d + i + 96), e);
+        }
+        _mm_sfence();
+        std::memcpy(d + i, s + i, n - i);
+    }
+#endif
+    static void copy_part(char* d, const char* s, size_t n, bool stream) {
+#if defined(__x86_64__)
+        static const bool avx2 = __builtin_cpu_supports("avx2");
+        if (stream && avx2) { copy_stream_avx2(d, s, n); return; }
+#endif
+        (void)stream;
+        std::memcpy(d, s, n);
+    }
+    static void work(Job& j) {
+        for (;;) {
+            const size_t p = j.next.fetch_add(1, std::memory_order_relaxed);
+            if (p >= j.n_parts) return;
+            const size_t off = p * kPart;
+            copy_part(j.d + off, j.s + off, std::min(kPart, j.n - off), j.stream);
+            j.done.fetch_add(1, std::memory_order_release);
+        }
+    }
     CopyPool() {
         const unsigned hw = std::thread::hardware_concurrency();
-        const unsigned n = std::max(1u, std::min(7u, hw > 2 ? hw / 2 - 1 : 1u));
-        for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
-        for (auto& t : workers_) t.detach();
+        workers_ = std::max(1u, std::min(15u, hw > 2 ? hw - 2 : 1u));
+        for (unsigned i = 0; i < workers_; ++i) std::thread([this] { run(); }).detach();
     }
     void run() {
-        std::unique_lock<std::mutex> lk(mu_);
+        uint64_t seen = 0;
         for (;;) {
-            cv_.wait(lk, [&] { return !tasks_.empty(); });
-            Task t = tasks_.back();
-            tasks_.pop_back();
-            lk.unlock();
-            std::memcpy(t.d, t.s, t.n);
-            lk.lock();
-            if (--pending_ == 0) done_.notify_all();
+            // spin briefly for the next job of the same transfer, then sleep
+            const auto t0 = std::chrono::steady_clock::now();
+            while (epoch_.load(std::memory_order_acquire) == seen) {
+                cpu_relax();
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(100)) {
+                    std::unique_lock<std::mutex> lk(mu_);
+                    cv_.wait(lk, [&] { return epoch_.load(std::memory_order_acquire) != seen; });
+                    break;
+                }
+            }
+            Job* j = nullptr;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                seen = epoch_.load(std::memory_order_acquire);
+                j = job_;
+                if (j) j->active.fetch_add(1, std::memory_order_acq_rel);
+            }
+            if (j) {
+                work(*j);
+                j->active.fetch_sub(1, std::memory_order_acq_rel);
+            }
         }
     }
     std::mutex mu_;
-    std::condition_variable cv_, done_;
-    std::vector<Task> tasks_;
-    std::vector<std::thread> workers_;
-    size_t pending_ = 0;
+    std::condition_variable cv_;
+    Job* job_ = nullptr;
+    std::atomic<uint64_t> epoch_{0};
+    unsigned workers_ = 0;
 };
 std::mutex g_copy_mu;      // one staged transfer at a time drives the pool (transfers of different indexes serialise here)
 
@@ -270,6 +350,9 @@ struct agp_index {
     size_t out_slot_bytes = 0;
     std::vector<cudaEvent_t> pipe_ev;
     int pipe_chunk = 0;                              // knob: queries per pipeline chunk (0 = automatic)
+    int screen_chunk = 0;                            // knob: queries per screen launch (0 = automatic)
+    int screen_lockstep = -1;                        // knob: tiles between the meeting points of a full wave (0 = off, -1 = automatic)
+    Buf sync_ctr;
     int64_t stat_screened = 0;
     bool profile = false;
     cudaEvent_t ev_order = nullptr;
@@ -720,7 +803,11 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
     // whole 256-row tiles: rows between ntotal and the tile end are storage padding masked by yn = +inf
     CKR(make_plane_map(&m_b, ix->xs, static_cast<int64_t>(n_dbtiles) * TC_BN, ix->d_pad, TC_BM, 2, ld));
     const int clusters = ix->num_sms / 2;
-    const int64_t max_chunk = 65536;
+    // One wave of pair tiles per launch: every launch restarts all CTA pairs at database tile 0, so the pairs sweep the
+    // plane in step and each tile is fetched from HBM once for all of them.  In one long multi-wave launch the pairs
+    // drift apart (cfg4, power-capped: 917 ms per step with 65536-query launches, 834 ms with 18944-query launches).
+    const int64_t wave_q = static_cast<int64_t>(clusters) * 2 * TC_BM;
+    const int64_t max_chunk = ix->screen_chunk > 0 ? std::min<int64_t>(ix->screen_chunk, 65536) : (nq > wave_q + wave_q / 4 ? wave_q : 65536);
     for (int64_t q0 = 0; q0 < nq; q0 += max_chunk) {
         const int nqc = static_cast<int>(std::min<int64_t>(max_chunk, nq - q0));
         ScreenParams p;
@@ -766,6 +853,19 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         p.debug_skip_epilogue = ix->kn.skip_epi;
         p.dump = ix->probe_dump;
         p.dump_ld = ix->probe_ld;
+        p.lockstep = 0;
+        p.sync_ctr = nullptr;
+        // automatic: planes far larger than L2 (>= 2048 tiles = 0.6 GB at d = 512) are swept in step (cfg4: 845 -> 826 ms per
+        // step, and the power-capped clock rises 1477 -> 1560 MHz because fewer tiles are re-fetched from HBM); a short
+        // sweep loses more to the meeting points than it gains (cfg2, 391 tiles: kernel 1.73 -> 1.82 ms)
+        const int lockstep = ix->screen_lockstep >= 0 ? ix->screen_lockstep : (n_dbtiles >= 2048 ? 32 : 0);
+        if (lockstep > 0 && p.n_full_items > 0) {
+            p.lockstep = lockstep;
+            const size_t n_ctr = static_cast<size_t>(p.n_full_items / clusters) * ((n_dbtiles + p.lockstep - 1) / p.lockstep);
+            CKR(ensure(ix->sync_ctr, n_ctr * sizeof(unsigned int)));
+            CK(cudaMemsetAsync(ix->sync_ctr.p, 0, n_ctr * sizeof(unsigned int), ix->stream));
+            p.sync_ctr = static_cast<unsigned int*>(ix->sync_ctr.p);
+        }
         const int grid = 2 * std::min(p.n_items, clusters);
         const size_t n_lists_total = static_cast<size_t>(p.n_full_items) * 2 * TC_BM * 2 + static_cast<size_t>(rem_tiles) * 2 * TC_BM * 2 * p.rem_splits;
         CKR(ensure(ix->cand, n_lists_total * sizeof(int)));
@@ -874,7 +974,7 @@ static int copy_h2d(agp_index* ix, void* dst, const void* src, size_t bytes) {
         const int b = c & 1;
         const size_t len = std::min(kStageChunk, bytes - off);
         if (c >= 2) CK(cudaEventSynchronize(ix->stage_ev[b]));          // the DMA that last read this buffer is done
-        CopyPool::get().memcpy_parallel(ix->stage[b], static_cast<const char*>(src) + off, len);
+        CopyPool::get().memcpy_parallel(ix->stage[b], static_cast<const char*>(src) + off, len, true);
         CK(cudaMemcpyAsync(static_cast<char*>(dst) + off, ix->stage[b], len, cudaMemcpyHostToDevice, ix->stream));
         CK(cudaEventRecord(ix->stage_ev[b], ix->stream));
     }
@@ -1016,7 +1116,7 @@ void agp_index_free(agp_index* ix) {
     pool_free(ix->device, ix->dbstats, 8 * sizeof(uint32_t));
     free_buf(ix->sq);
     free_buf(ix->dq); free_buf(ix->hthr); free_buf(ix->mk_d); free_buf(ix->mk_i); free_buf(ix->mk_off); free_buf(ix->mk_ids);
-    free_buf(ix->ovf); free_buf(ix->ovf_list);
+    free_buf(ix->ovf); free_buf(ix->ovf_list); free_buf(ix->sync_ctr);
     free_buf(ix->q_raw); free_buf(ix->q_hi); free_buf(ix->q_lo); free_buf(ix->qn); free_buf(ix->cand);
     free_buf(ix->gthr); free_buf(ix->dbg); free_buf(ix->cand_d); free_buf(ix->cand_i); free_buf(ix->partial); free_buf(ix->panel);
     free_buf(ix->d_out); free_buf(ix->i_out);
@@ -1064,7 +1164,7 @@ int agp_index_set_knob(agp_index* ix, const char* name, int value) {
         {"screen_flags", &ix->kn.screen_flags}, {"screen_e", &ix->kn.screen_e}, {"screen_stages", &ix->kn.screen_stages},
         {"screen_sched", &ix->kn.screen_sched}, {"tc_e", &ix->kn.tc_e}, {"tc_rerank", &ix->kn.tc_rerank},
         {"tc_compact_sort", &ix->kn.tc_compact_sort}, {"tc_share_bound", &ix->kn.tc_share_bound}, {"cycle_counters", &ix->kn.cycle_counters},
-        {"pipe_chunk", &ix->pipe_chunk},
+        {"pipe_chunk", &ix->pipe_chunk}, {"screen_chunk", &ix->screen_chunk}, {"screen_lockstep", &ix->screen_lockstep},
 #ifdef AGP_DEBUG_KNOBS
         {"skip_epi", &ix->kn.skip_epi}, {"skip_mma", &ix->kn.skip_mma},
 #endif
@@ -1358,7 +1458,7 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
                     ring_pos = (ring_pos + 1) % 3;
                     if (ring_used >= 3) CK(cudaEventSynchronize(ix->in_ring_ev[b]));      // the DMA that last read this slot is done
                     else ++ring_used;
-                    CopyPool::get().memcpy_parallel(ix->in_ring[b], src + off, len);
+                    CopyPool::get().memcpy_parallel(ix->in_ring[b], src + off, len, true);
                     CK(cudaMemcpyAsync(dst + off, ix->in_ring[b], len, cudaMemcpyHostToDevice, ix->s_in));
                     CK(cudaEventRecord(ix->in_ring_ev[b], ix->s_in));
                 }

@@ -342,7 +342,22 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                         tma_load_2d_pair(q_region + kc * SC_CHUNK_BYTES, &tm_q, qfull_leader, kc * 64, qrow0);
                     qphase ^= 1;
                 }
+                // Lockstep (full waves only: every pair of the grid sweeps the whole plane): every `lockstep` tiles the
+                // producers meet at a global arrival counter, so no pair runs ahead of the slowest one by more than that
+                // and a database tile is fetched from HBM once for all pairs instead of once per straggler group.
+                const bool in_step = p.lockstep > 0 && item < p.n_full_items;
+                const int n_sync = in_step ? (p.n_dbtiles + p.lockstep - 1) / p.lockstep : 0;
+                unsigned int* ctr = in_step ? p.sync_ctr + static_cast<size_t>(item / n_clusters) * n_sync : nullptr;
                 for (int t = it.t0; t < it.t1; ++t) {
+                    if (in_step && t > 0 && t % p.lockstep == 0) {
+                        unsigned int* c = ctr + t / p.lockstep;
+                        if (rank == 0) atomicAdd(c, 1u);
+                        unsigned int seen;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(c) : "memory");
+                            if (seen < static_cast<unsigned>(n_clusters)) __nanosleep(100);
+                        } while (seen < static_cast<unsigned>(n_clusters));
+                    }
                     const int brow0 = t * TC_BN + static_cast<int>(rank) * (TC_BN / 2);
                     for (int kc = 0; kc < num_kc; ++kc) {
                         mbar_wait(&empty[stage], phase ^ 1);

@@ -69,6 +69,8 @@ struct ScreenParams {
     uint32_t* hthr;         // per list: upper bound of the ceil(k/2)-th best of that list (fp32 bits, +inf initially)
     int* ovf;               // [nq] set when a query's certified band did not fit its slots
     long long* dbg;
+    int lockstep;           // > 0: the pairs of a full wave meet every `lockstep` database tiles (sync_ctr), so they sweep the plane together
+    unsigned int* sync_ctr; // [full waves][ceil(n_dbtiles / lockstep)] arrival counters, zeroed before launch
     float* dump;            // instrumented build only (agp_index_screen_probe): dis~ of every (query, database row), [nq][dump_ld]
     int64_t dump_ld;
 };

@@ -40,6 +40,26 @@ def default_device() -> int:
     return 0
 
 
+_PINNED_RESULT_MIN = 1 << 20        # bytes: below this a plain numpy array is cheaper than a pinned block
+_PINNED_RESULT_MAX = 1 << 30
+
+
+def _result_array(shape, dtype):
+    """A fresh result array owned by the caller, like faiss returns.  Large results are numpy views of page-locked
+    blocks from torch's caching host allocator (the block goes back to that cache when the array is garbage
+    collected): the engine's D2H copy then lands directly in the array the caller receives -- no pinned staging copy,
+    no first-touch page faults on a fresh pageable allocation."""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    if _PINNED_RESULT_MIN <= nbytes <= _PINNED_RESULT_MAX:
+        try:
+            import torch
+            t = torch.empty(shape, dtype=torch.float32 if dtype == np.float32 else torch.int64, pin_memory=True)
+            return t.numpy()          # keeps the tensor (and its pinned block) alive through .base
+        except Exception:
+            pass
+    return np.empty(shape, dtype=dtype)
+
+
 class IndexFlatL2:
     """Exact brute-force squared-L2 index resident in one B200's HBM."""
 
@@ -126,12 +146,12 @@ class IndexFlatL2:
             x = x.detach().numpy()
         x = np.ascontiguousarray(x, dtype="float32")
         if D is None:
-            Dn = np.empty((n, k), dtype=np.float32)
+            Dn = _result_array((n, k), np.float32)
         else:
             Dn = D.numpy() if _is_torch(D) else D
             assert Dn.shape == (n, k)
         if I is None:
-            In = np.empty((n, k), dtype=np.int64)
+            In = _result_array((n, k), np.int64)
         else:
             In = I.numpy() if _is_torch(I) else I
             assert In.shape == (n, k)
