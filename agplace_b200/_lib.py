@@ -20,6 +20,8 @@ MAX_K = 512
 SIGNATURES = {
     "agp_index_create": (c_int, [c_int, c_int, c_int, POINTER(c_void_p)]),
     "agp_index_create_metric": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "agp_index_create_multi": (c_int, [c_int, c_int, POINTER(c_int), c_int, c_int, POINTER(c_void_p)]),
+    "agp_index_n_shards": (c_int, [c_void_p]),
     "agp_index_metric": (c_int, [c_void_p]),
     "agp_index_free": (None, [c_void_p]),
     "agp_index_add": (c_int, [c_void_p, c_int64, c_void_p, c_int]),

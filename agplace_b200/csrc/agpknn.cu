@@ -321,7 +321,18 @@ struct Knobs {
     int skip_epi = 0, skip_mma = 0;   // AGP_DEBUG_KNOBS builds only
 };
 
+struct ShardChunk { int64_t local_start, delta; };      // rows >= local_start of a shard (up to the next record): global id = local row + delta
+
 struct agp_index {
+    // Single-process multi-device index (agp_index_create_multi): the parent owns no rows; shards[g] is an ordinary
+    // index on device g holding a contiguous slice of every add() batch.  Empty for a one-device index.
+    std::vector<agp_index*> shards;
+    std::vector<std::vector<ShardChunk>> shard_chunks;      // per shard, add order
+    std::vector<Buf> shard_tab;                              // per shard: its chunk table on its device
+    std::vector<char> shard_tab_dirty;
+    std::vector<cudaEvent_t> shard_ev;
+    Buf gat_d, gat_i;                                        // home device: per-shard result lists of one query chunk
+    cudaEvent_t ev_home = nullptr;
     Knobs kn;
     float* probe_dump = nullptr;      // agp_index_screen_probe: device buffer [nq][probe_ld] for dis~
     int64_t probe_ld = 0;
@@ -1099,8 +1110,64 @@ int agp_index_create_metric(int d, int device, int precision_mode, int metric, a
     return 0;
 }
 
+int agp_index_create_multi(int d, int n_devices, const int* device_ids, int precision_mode, int metric, agp_index** out) {
+    if (!out) return set_err(AGP_EINVAL, "out is null");
+    *out = nullptr;
+    if (n_devices < 1 || n_devices > 64 || !device_ids) return set_err(AGP_EINVAL, "n_devices must be in 1..64 and device_ids non-null");
+    agp_index* parent = nullptr;
+    CKR(agp_index_create_metric(d, device_ids[0], precision_mode, metric, &parent));      // home device: merge + host transfers
+    if (n_devices == 1) {      // one device: an ordinary index
+        *out = parent;
+        return 0;
+    }
+    parent->shard_chunks.resize(n_devices);
+    parent->shard_tab.resize(n_devices);
+    parent->shard_tab_dirty.assign(n_devices, 0);
+    for (int g = 0; g < n_devices; ++g) {
+        agp_index* ch = nullptr;
+        int rc = agp_index_create_metric(d, device_ids[g], precision_mode, metric, &ch);
+        cudaEvent_t ev = nullptr;
+        if (rc == 0 && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) rc = set_err(AGP_ECUDA, "event creation failed");
+        if (rc != 0) {
+            if (ch) agp_index_free(ch);
+            agp_index_free(parent);
+            return rc;
+        }
+        parent->shards.push_back(ch);
+        parent->shard_ev.push_back(ev);
+    }
+    // peer access lets cudaMemcpyPeerAsync go over NVLink directly (it still works, staged, without it)
+    for (int g = 0; g < n_devices; ++g) {
+        for (int h = 0; h < n_devices; ++h) {
+            if (device_ids[g] == device_ids[h]) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, device_ids[g], device_ids[h]) == cudaSuccess && can) {
+                cudaSetDevice(device_ids[g]);
+                cudaError_t e = cudaDeviceEnablePeerAccess(device_ids[h], 0);
+                if (e != cudaSuccess) cudaGetLastError();      // already enabled (another index, torch): fine
+            }
+        }
+    }
+    cudaSetDevice(device_ids[0]);
+    *out = parent;
+    return 0;
+}
+
+int agp_index_n_shards(const agp_index* ix) { return ix ? std::max<int>(1, static_cast<int>(ix->shards.size())) : -1; }
+
 void agp_index_free(agp_index* ix) {
     if (!ix) return;
+    for (size_t g = 0; g < ix->shards.size(); ++g) {
+        agp_index* ch = ix->shards[g];
+        cudaSetDevice(ch->device);
+        cudaStreamSynchronize(ch->stream);
+        t_dev = ch->device;
+        t_stream = ch->stream;
+        free_buf(ix->shard_tab[g]);
+        if (ix->shard_ev[g]) cudaEventDestroy(ix->shard_ev[g]);
+        agp_index_free(ch);
+    }
+    ix->shards.clear();
     cudaSetDevice(ix->device);
     t_dev = ix->device;
     t_stream = ix->stream;
@@ -1116,7 +1183,8 @@ void agp_index_free(agp_index* ix) {
     pool_free(ix->device, ix->dbstats, 8 * sizeof(uint32_t));
     free_buf(ix->sq);
     free_buf(ix->dq); free_buf(ix->hthr); free_buf(ix->mk_d); free_buf(ix->mk_i); free_buf(ix->mk_off); free_buf(ix->mk_ids);
-    free_buf(ix->ovf); free_buf(ix->ovf_list); free_buf(ix->sync_ctr);
+    free_buf(ix->ovf); free_buf(ix->ovf_list); free_buf(ix->sync_ctr); free_buf(ix->gat_d); free_buf(ix->gat_i);
+    if (ix->ev_home) cudaEventDestroy(ix->ev_home);
     free_buf(ix->q_raw); free_buf(ix->q_hi); free_buf(ix->q_lo); free_buf(ix->qn); free_buf(ix->cand);
     free_buf(ix->gthr); free_buf(ix->dbg); free_buf(ix->cand_d); free_buf(ix->cand_i); free_buf(ix->partial); free_buf(ix->panel);
     free_buf(ix->d_out); free_buf(ix->i_out);
@@ -1170,13 +1238,18 @@ int agp_index_set_knob(agp_index* ix, const char* name, int value) {
 #endif
     };
     for (auto& t : table)
-        if (strcmp(t.n, name) == 0) { *t.v = value; return 0; }
+        if (strcmp(t.n, name) == 0) {
+            *t.v = value;
+            for (agp_index* ch : ix->shards) CKR(agp_index_set_knob(ch, name, value));
+            return 0;
+        }
     return set_err(AGP_EINVAL, "unknown knob '%s' (result-changing probes need an AGP_DEBUG_KNOBS build)", name);
 }
 
 int agp_index_screen_probe(agp_index* ix, int64_t nq, const float* x, float* dis, float* band) {
     if (!ix || !x || !dis || !band) return set_err(AGP_EINVAL, "null pointer");
-    if (!ix->screen || ix->ip) return set_err(AGP_EINVAL, "screen_probe needs an L2 index in precision auto or fp16_screen");
+    if (!ix->screen || ix->ip || !ix->shards.empty())
+        return set_err(AGP_EINVAL, "screen_probe needs a one-device L2 index in precision auto or fp16_screen");
     if (nq <= 0 || nq > 65536 || ix->ntotal <= 0) return set_err(AGP_EINVAL, "need 1 <= nq <= 65536 and a non-empty index");
     if (nq * ix->ntotal > (int64_t(1) << 28)) return set_err(AGP_EINVAL, "nq * ntotal too large for a probe");
     if (ix->num_sms & 1) return set_err(AGP_EINVAL, "the screen kernel needs an even SM count");
@@ -1224,6 +1297,7 @@ int agp_index_set_id_base(agp_index* ix, int64_t b) {
 
 int agp_index_set_profiling(agp_index* ix, int on) {
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    for (agp_index* ch : ix->shards) CKR(agp_index_set_profiling(ch, on));
     if (!on && ix->profile) prof_collect(ix);
     ix->profile = on != 0;
     return 0;
@@ -1231,6 +1305,7 @@ int agp_index_set_profiling(agp_index* ix, int on) {
 
 int agp_index_get_profile(agp_index* ix, double* ms, int64_t* launches, int reset) {
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    if (!ix->shards.empty()) return agp_index_get_profile(ix->shards[0], ms, launches, reset);      // shard 0 stands for all
     ENTER(ix);
     prof_collect(ix);
     if (ms) *ms = ix->prof_ms[AGP_PHASE_DISTANCE];
@@ -1242,6 +1317,7 @@ int agp_index_get_profile(agp_index* ix, double* ms, int64_t* launches, int rese
 
 int agp_index_get_profile_phases(agp_index* ix, double* ms, int64_t* launches, int reset) {
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    if (!ix->shards.empty()) return agp_index_get_profile_phases(ix->shards[0], ms, launches, reset);
     ENTER(ix);
     prof_collect(ix);
     for (int t = 0; t < AGP_N_PHASES; ++t) {
@@ -1254,12 +1330,26 @@ int agp_index_get_profile_phases(agp_index* ix, double* ms, int64_t* launches, i
 
 int agp_index_reserve(agp_index* ix, int64_t n) {
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    if (!ix->shards.empty()) {
+        const int64_t G = static_cast<int64_t>(ix->shards.size());
+        for (agp_index* ch : ix->shards) CKR(agp_index_reserve(ch, (n + G - 1) / G));
+        return 0;
+    }
     ENTER(ix);
     return grow(ix, n);
 }
 
 int agp_index_reset(agp_index* ix) {
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    if (!ix->shards.empty()) {
+        for (size_t g = 0; g < ix->shards.size(); ++g) {
+            CKR(agp_index_reset(ix->shards[g]));
+            ix->shard_chunks[g].clear();
+            ix->shard_tab_dirty[g] = 1;
+        }
+        ix->ntotal = 0;
+        return 0;
+    }
     ENTER(ix);
     if (ix->cap > 0) {
         LAUNCH(launch_fill_f32(ix->yn, ix->cap, HUGE_VALF, ix->stream));
@@ -1274,6 +1364,17 @@ int agp_index_reset(agp_index* ix) {
 
 int agp_index_get_stats(const agp_index* ix, int64_t* screened_queries, int64_t* fallback_queries) {
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    if (!ix->shards.empty()) {      // sums over the shards (every shard screens every query)
+        int64_t a = 0, b = 0;
+        for (const agp_index* ch : ix->shards) {
+            int64_t ca = 0, cb = 0;
+            CKR(agp_index_get_stats(ch, &ca, &cb));
+            a += ca; b += cb;
+        }
+        if (screened_queries) *screened_queries = a;
+        if (fallback_queries) *fallback_queries = b;
+        return 0;
+    }
     if (screened_queries) *screened_queries = ix->stat_screened;
     if (fallback_queries) {
         // the fallback runs on the device without telling the host: read its counter after the queued searches
@@ -1291,6 +1392,24 @@ int agp_index_add(agp_index* ix, int64_t n, const float* x, int mem_kind) {
     if (n < 0) return set_err(AGP_EINVAL, "n must be >= 0");
     if (n == 0) return 0;
     if (!x) return set_err(AGP_EINVAL, "x is null");
+    if (!ix->shards.empty()) {
+        // every add() batch is cut into G contiguous slices (shard g holds [g * ceil(n/G), ...)): global ids stay add-order
+        const int64_t G = static_cast<int64_t>(ix->shards.size()), per = (n + G - 1) / G;
+        for (int64_t g = 0; g < G; ++g) {
+            const int64_t lo = std::min(g * per, n), hi = std::min((g + 1) * per, n);
+            if (hi <= lo) continue;
+            agp_index* ch = ix->shards[g];
+            auto& tab = ix->shard_chunks[g];
+            const int64_t delta = ix->ntotal + lo - ch->ntotal;
+            if (tab.empty() || tab.back().delta != delta) {
+                tab.push_back({ch->ntotal, delta});
+                ix->shard_tab_dirty[g] = 1;
+            }
+            CKR(agp_index_add(ch, hi - lo, x + lo * ix->d, mem_kind));
+        }
+        ix->ntotal += n;
+        return 0;
+    }
     if (ix->ntotal + n > 0x7fffffffLL) return set_err(AGP_EINVAL, "a single shard holds at most 2^31-1 rows");
     ENTER(ix);
     CKR(grow(ix, ix->ntotal + n));
@@ -1348,14 +1467,70 @@ static int pipe_event(agp_index* ix, size_t i, cudaEvent_t* out) {
     return 0;
 }
 
+// One query chunk on a multi-device index: every shard searches the chunk on its own device and stream (nothing waits
+// on the host), maps its local rows to global ids, pushes its (D, I) lists to the home device over NVLink
+// (cudaMemcpyPeerAsync), and the home device merges the G lists with ties by global id -- the same K4 kernel the
+// NCCL path uses.  xq[g] = the chunk's queries on shard g's device.
+static int multi_compute_chunk(agp_index* ix, const std::vector<const float*>& xq, int64_t m, int k, float* D_home, int64_t* I_home) {
+    const int G = static_cast<int>(ix->shards.size());
+    const size_t list = static_cast<size_t>(m) * k;
+    ENTER(ix);
+    CKR(ensure(ix->gat_d, G * list * sizeof(float)));
+    CKR(ensure(ix->gat_i, G * list * sizeof(int64_t)));
+    if (!ix->ev_home) CK(cudaEventCreateWithFlags(&ix->ev_home, cudaEventDisableTiming));
+    CK(cudaEventRecord(ix->ev_home, ix->stream));      // the gather buffers are free once the previous chunk's merge has run
+    for (int g = 0; g < G; ++g) {
+        agp_index* ch = ix->shards[g];
+        ENTER(ch);
+        CK(cudaStreamWaitEvent(ch->stream, ix->ev_home, 0));
+        CKR(ensure(ch->d_out, list * sizeof(float)));
+        CKR(ensure(ch->i_out, list * sizeof(int64_t)));
+        const auto& tab = ix->shard_chunks[g];
+        const bool one = tab.size() <= 1;
+        ch->id_base = one ? (tab.empty() ? 0 : tab[0].delta) + ix->id_base : 0;
+        CKR(search_device(ch, xq[g], m, k, static_cast<float*>(ch->d_out.p), static_cast<int64_t*>(ch->i_out.p)));
+        if (!one) {
+            if (ix->shard_tab_dirty[g]) {
+                CKR(ensure(ix->shard_tab[g], tab.size() * sizeof(ShardChunk)));
+                CK(cudaMemcpyAsync(ix->shard_tab[g].p, tab.data(), tab.size() * sizeof(ShardChunk), cudaMemcpyHostToDevice, ch->stream));
+                CK(cudaStreamSynchronize(ch->stream));      // tab is host memory that a later add() may reallocate
+                ix->shard_tab_dirty[g] = 0;
+            }
+            LAUNCH(launch_remap_ids(static_cast<int64_t*>(ch->i_out.p), static_cast<int64_t>(list),
+                                    static_cast<const int64_t*>(ix->shard_tab[g].p), static_cast<int>(tab.size()), ix->id_base, ch->stream));
+        }
+        CK(cudaMemcpyPeerAsync(static_cast<float*>(ix->gat_d.p) + g * list, ix->device, ch->d_out.p, ch->device, list * sizeof(float), ch->stream));
+        CK(cudaMemcpyPeerAsync(static_cast<int64_t*>(ix->gat_i.p) + g * list, ix->device, ch->i_out.p, ch->device, list * sizeof(int64_t), ch->stream));
+        CK(cudaEventRecord(ix->shard_ev[g], ch->stream));
+    }
+    ENTER(ix);
+    for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(ix->stream, ix->shard_ev[g], 0));
+    const bool by_id = ix->ntotal + ix->id_base <= 0x100000000LL;
+    return DISPATCH_E32(k, launch_merge_lists, static_cast<const float*>(ix->gat_d.p), static_cast<int64_t>(list),
+                        static_cast<const int64_t*>(ix->gat_i.p), static_cast<int64_t>(list), by_id, m, G, k, D_home, I_home, ix->ip, ix->stream);
+}
+
+// Host-buffer search as a three-stage pipeline (what the reference's call hands over: numpy arrays in, numpy arrays
+// out -- test.py:32).  The query batch is cut into chunks; for chunk c
+//     host memcpy into a pinned ring + H2D   (copy-in stream of every device that holds a shard)
+//  -> prep / screen / finish / fallback      (the compute stream(s), after the chunk's H2D event; multi-device: + gather + merge)
+//  -> D2H of (D, I) into the caller's pinned arrays or a pinned slot (stream s_out, after the chunk's compute event)
+// run concurrently for chunks c + 1, c and c - 1.  No stage needs a host synchronisation of the compute stream (the
+// screen's overflow fallback is device-side), so the host thread only ever blocks on a staging slot or a finished chunk.
+// Chunks are whole waves of pair tiles (74 x 256 queries on B200) when the batch is large; a mid-sized batch is cut
+// unevenly (small first chunk: the GPU starts early; large later chunks: the kernel stays efficient).
+// Also serves device-resident queries of a multi-device index (peer copies instead of H2D).
 static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, int k, float* D, int64_t* I, int out_mem_kind) {
     const bool x_host = x_mem_kind != AGP_MEM_DEVICE, out_host = out_mem_kind != AGP_MEM_DEVICE;
+    const bool multi = !ix->shards.empty();
+    const int G = multi ? static_cast<int>(ix->shards.size()) : 1;
+    auto worker = [&](int g) { return multi ? ix->shards[g] : ix; };
     const size_t row_in = static_cast<size_t>(ix->d) * sizeof(float);
     const size_t row_d = static_cast<size_t>(k) * sizeof(float), row_i = static_cast<size_t>(k) * sizeof(int64_t);
     // ---- chunk schedule
     std::vector<int64_t> cuts;       // chunk c = [cuts[c], cuts[c + 1])
     cuts.push_back(0);
-    const int64_t wave = static_cast<int64_t>(ix->num_sms / 2) * 2 * TC_BM;      // queries one wave of pair tiles covers
+    const int64_t wave = static_cast<int64_t>(worker(0)->num_sms / 2) * 2 * TC_BM;      // queries one wave of pair tiles covers
     const size_t moved = (x_host ? nq * row_in : 0) + (out_host ? nq * (row_d + row_i) : 0);
     const bool batched_path = ix->ntotal > 0 && nq >= kMaxSmallNq;
     if (ix->pipe_chunk > 0) {
@@ -1372,11 +1547,23 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
     cuts.push_back(nq);
     const int n_chunks = static_cast<int>(cuts.size()) - 1;
 
-    const float* xq_dev = x;
-    if (x_host) {
-        CKR(ensure(ix->q_raw, static_cast<size_t>(nq) * row_in));
-        xq_dev = static_cast<const float*>(ix->q_raw.p);
+    // ---- where the queries live on every device that computes
+    int x_dev = -1;
+    if (!x_host && multi) {
+        cudaPointerAttributes at;
+        CK(cudaPointerGetAttributes(&at, x));
+        x_dev = at.device;
     }
+    std::vector<const float*> xq_dev(G, x);
+    for (int g = 0; g < G; ++g) {
+        agp_index* w = worker(g);
+        if (x_host || (multi && w->device != x_dev)) {
+            ENTER(w);
+            CKR(ensure(w->q_raw, static_cast<size_t>(nq) * row_in));
+            xq_dev[g] = static_cast<const float*>(w->q_raw.p);
+        }
+    }
+    ENTER(ix);
     float* D_dev = D;
     int64_t* I_dev = I;
     if (out_host) {
@@ -1385,10 +1572,16 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
         D_dev = static_cast<float*>(ix->d_out.p);
         I_dev = static_cast<int64_t*>(ix->i_out.p);
     }
-    if (n_chunks == 1 && !(x_host && nq * row_in >= kStageMin)) {
+    auto compute = [&](int64_t a, int64_t m) -> int {
+        if (!multi) return search_device(ix, xq_dev[0] + a * ix->d, m, k, D_dev + a * k, I_dev + a * k);
+        std::vector<const float*> xc(G);
+        for (int g = 0; g < G; ++g) xc[g] = xq_dev[g] + a * ix->d;
+        return multi_compute_chunk(ix, xc, m, k, D_dev + a * k, I_dev + a * k);
+    };
+    if (!multi && n_chunks == 1 && !(x_host && nq * row_in >= kStageMin)) {
         // small call (the mining shapes): one copy in, one launch sequence, one copy out, one synchronisation
         if (x_host) CK(cudaMemcpyAsync(ix->q_raw.p, x, static_cast<size_t>(nq) * row_in, cudaMemcpyHostToDevice, ix->stream));
-        CKR(search_device(ix, xq_dev, nq, k, D_dev, I_dev));
+        CKR(compute(0, nq));
         if (out_host) {
             CK(cudaMemcpyAsync(D, D_dev, static_cast<size_t>(nq) * row_d, cudaMemcpyDeviceToHost, ix->stream));
             CK(cudaMemcpyAsync(I, I_dev, static_cast<size_t>(nq) * row_i, cudaMemcpyDeviceToHost, ix->stream));
@@ -1397,15 +1590,20 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
         return 0;
     }
 
-    if (!ix->s_in) CK(pool_stream(ix->device, &ix->s_in));
     if (!ix->s_out) CK(pool_stream(ix->device, &ix->s_out));
-    const bool stage_in = x_host && is_pageable(x);
+    for (int g = 0; g < G; ++g) {
+        agp_index* w = worker(g);
+        CK(cudaSetDevice(w->device));
+        if (!w->s_in) CK(pool_stream(w->device, &w->s_in));
+        for (int b = 0; b < 3; ++b)
+            if (!w->in_ring_ev[b]) CK(cudaEventCreateWithFlags(&w->in_ring_ev[b], cudaEventDisableTiming));
+    }
+    CK(cudaSetDevice(ix->device));
+    const bool stage_in = x_host && is_pageable(x) && nq * row_in >= 65536;
     const bool stage_out = out_host && (is_pageable(D) || is_pageable(I));
     if (stage_in)
-        for (int b = 0; b < 3; ++b) {
-            if (!ix->in_ring[b]) CK(cudaHostAlloc(reinterpret_cast<void**>(&ix->in_ring[b]), kStageChunk, cudaHostAllocDefault));
-            if (!ix->in_ring_ev[b]) CK(cudaEventCreateWithFlags(&ix->in_ring_ev[b], cudaEventDisableTiming));
-        }
+        for (int b = 0; b < 3; ++b)
+            if (!ix->in_ring[b]) CK(cudaHostAlloc(reinterpret_cast<void**>(&ix->in_ring[b]), kStageChunk, cudaHostAllocPortable));
     int64_t max_chunk = 0;
     for (int c = 0; c < n_chunks; ++c) max_chunk = std::max(max_chunk, cuts[c + 1] - cuts[c]);
     const size_t slot_bytes = static_cast<size_t>(max_chunk) * (row_d + row_i);
@@ -1418,12 +1616,21 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
         }
         ix->out_slot_bytes = slot_bytes;
     }
-    // the copy streams start after everything already queued on the compute stream (earlier calls own the scratch buffers)
+    // the copy streams start after everything already queued on the compute stream(s) (earlier calls own the scratch buffers)
     cudaEvent_t ev_start;
     CKR(pipe_event(ix, 0, &ev_start));
     CK(cudaEventRecord(ev_start, ix->stream));
-    CK(cudaStreamWaitEvent(ix->s_in, ev_start, 0));
     CK(cudaStreamWaitEvent(ix->s_out, ev_start, 0));
+    for (int g = 0; g < G; ++g) {
+        agp_index* w = worker(g);
+        CK(cudaSetDevice(w->device));
+        if (multi) CK(cudaStreamWaitEvent(w->stream, ev_start, 0));
+        cudaEvent_t e;
+        CKR(pipe_event(w, 0, &e));
+        CK(cudaEventRecord(e, w->stream));
+        CK(cudaStreamWaitEvent(w->s_in, e, 0));
+    }
+    CK(cudaSetDevice(ix->device));
 
     std::lock_guard<std::mutex> lk(g_copy_mu);      // one pipelined transfer at a time drives the copy workers
     int ring_pos = 0, ring_used = 0;
@@ -1441,32 +1648,53 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
     };
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t a = cuts[c], m = cuts[c + 1] - cuts[c];
-        cudaEvent_t ev_in, ev_done, ev_out;
-        CKR(pipe_event(ix, 3 * c + 1, &ev_in));
+        cudaEvent_t ev_done, ev_out;
         CKR(pipe_event(ix, 3 * c + 2, &ev_done));
         CKR(pipe_event(ix, 3 * c + 3, &ev_out));
+        const size_t bytes = static_cast<size_t>(m) * row_in, off0 = static_cast<size_t>(a) * row_in;
         if (x_host) {
-            const char* src = reinterpret_cast<const char*>(x) + static_cast<size_t>(a) * row_in;
-            char* dst = static_cast<char*>(ix->q_raw.p) + static_cast<size_t>(a) * row_in;
-            const size_t bytes = static_cast<size_t>(m) * row_in;
-            if (!stage_in) {
-                CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ix->s_in));
-            } else {
-                for (size_t off = 0; off < bytes; off += kStageChunk) {
-                    const size_t len = std::min(kStageChunk, bytes - off);
-                    const int b = ring_pos;
+            const char* src = reinterpret_cast<const char*>(x) + off0;
+            for (size_t off = 0; off < bytes; off += (stage_in ? kStageChunk : bytes)) {
+                const size_t len = stage_in ? std::min(kStageChunk, bytes - off) : bytes;
+                const void* from = src + off;
+                int b = 0;
+                if (stage_in) {
+                    b = ring_pos;
                     ring_pos = (ring_pos + 1) % 3;
-                    if (ring_used >= 3) CK(cudaEventSynchronize(ix->in_ring_ev[b]));      // the DMA that last read this slot is done
-                    else ++ring_used;
+                    if (ring_used >= 3) {      // the DMAs that last read this slot (one per device) are done
+                        for (int g = 0; g < G; ++g) CK(cudaEventSynchronize(worker(g)->in_ring_ev[b]));
+                    } else {
+                        ++ring_used;
+                    }
                     CopyPool::get().memcpy_parallel(ix->in_ring[b], src + off, len, true);
-                    CK(cudaMemcpyAsync(dst + off, ix->in_ring[b], len, cudaMemcpyHostToDevice, ix->s_in));
-                    CK(cudaEventRecord(ix->in_ring_ev[b], ix->s_in));
+                    from = ix->in_ring[b];
+                }
+                for (int g = 0; g < G; ++g) {
+                    agp_index* w = worker(g);
+                    if (multi) CK(cudaSetDevice(w->device));
+                    CK(cudaMemcpyAsync(static_cast<char*>(w->q_raw.p) + off0 + off, from, len, cudaMemcpyHostToDevice, w->s_in));
+                    if (stage_in) CK(cudaEventRecord(w->in_ring_ev[b], w->s_in));
                 }
             }
-            CK(cudaEventRecord(ev_in, ix->s_in));
-            CK(cudaStreamWaitEvent(ix->stream, ev_in, 0));
+        } else {      // multi-device index, device-resident queries: peer copies to the shards on other devices
+            for (int g = 0; g < G; ++g) {
+                agp_index* w = worker(g);
+                if (w->device == x_dev) continue;
+                CK(cudaSetDevice(w->device));
+                CK(cudaMemcpyPeerAsync(static_cast<char*>(w->q_raw.p) + off0, w->device, reinterpret_cast<const char*>(x) + off0, x_dev, bytes, w->s_in));
+            }
         }
-        CKR(search_device(ix, xq_dev + a * ix->d, m, k, D_dev + a * k, I_dev + a * k));
+        for (int g = 0; g < G; ++g) {
+            agp_index* w = worker(g);
+            if (!x_host && (!multi || w->device == x_dev)) continue;
+            if (multi) CK(cudaSetDevice(w->device));
+            cudaEvent_t ev_in;
+            CKR(pipe_event(w, 3 * c + 1, &ev_in));
+            CK(cudaEventRecord(ev_in, w->s_in));
+            CK(cudaStreamWaitEvent(w->stream, ev_in, 0));
+        }
+        if (multi) CK(cudaSetDevice(ix->device));
+        CKR(compute(a, m));
         if (out_host) {
             CK(cudaEventRecord(ev_done, ix->stream));
             if (stage_out && c >= 2) CKR(drain(c - 2));      // frees the pinned slot this chunk's results go to
@@ -1485,12 +1713,12 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
     }
     if (out_host) {
         for (int c = std::max(0, n_chunks - 2); c < n_chunks; ++c) CKR(drain(c));
-        // later work on the compute stream must not overwrite d_out / i_out under a pending D2H: all of them are done here
-    } else {
+    } else if (x_host) {
         CK(cudaStreamSynchronize(ix->stream));      // host queries: the caller may reuse x once we return
     }
     if (stage_in)
-        for (int b = 0; b < std::min(ring_used, 3); ++b) CK(cudaEventSynchronize(ix->in_ring_ev[b]));
+        for (int b = 0; b < std::min(ring_used, 3); ++b)
+            for (int g = 0; g < G; ++g) CK(cudaEventSynchronize(worker(g)->in_ring_ev[b]));
     return 0;
 }
 
@@ -1503,7 +1731,7 @@ int agp_index_search(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, 
     if (!x || !D || !I) return set_err(AGP_EINVAL, "x, D and I must be non-null");
     if (nq > 0x7fffffffLL) return set_err(AGP_EINVAL, "nq too large");
     ENTER(ix);
-    if (x_mem_kind == AGP_MEM_DEVICE && out_mem_kind == AGP_MEM_DEVICE)
+    if (ix->shards.empty() && x_mem_kind == AGP_MEM_DEVICE && out_mem_kind == AGP_MEM_DEVICE)
         return search_device(ix, x, nq, k, D, I);      // asynchronous on the index's stream: nothing here waits for the GPU
     return search_host_pipelined(ix, nq, x, x_mem_kind, k, D, I, out_mem_kind);
 }
@@ -1515,7 +1743,7 @@ int agp_index_search_masked(agp_index* ix, int64_t nq, const float* x, int x_mem
     if (k <= 0) return set_err(AGP_EINVAL, "k must be positive, got %d", k);
     if (nq == 0) return 0;
     if (!x || !D || !I || !excl_offsets) return set_err(AGP_EINVAL, "x, D, I and excl_offsets must be non-null");
-    if (ix->ip) return set_err(AGP_EINVAL, "search_masked is defined for L2 indexes only");
+    if (ix->ip || !ix->shards.empty()) return set_err(AGP_EINVAL, "search_masked is defined for one-device L2 indexes only");
     int64_t max_ex = 0;
     for (int64_t q = 0; q < nq; ++q) {
         const int64_t c = excl_offsets[q + 1] - excl_offsets[q];
@@ -1590,7 +1818,7 @@ int agp_index_search_subset(agp_index* ix, int64_t nq, const float* x, int x_mem
     if (k > AGP_MAX_K) return set_err(AGP_EINVAL, "k=%d exceeds AGP_MAX_K=%d", k, AGP_MAX_K);
     if (nq == 0) return 0;
     if (!x || !D || !I || !cand_offsets) return set_err(AGP_EINVAL, "x, D, I and cand_offsets must be non-null");
-    if (ix->ip) return set_err(AGP_EINVAL, "search_subset is defined for L2 indexes only");
+    if (ix->ip || !ix->shards.empty()) return set_err(AGP_EINVAL, "search_subset is defined for one-device L2 indexes only");
     if (nq > 0x7fffffffLL) return set_err(AGP_EINVAL, "nq too large");
     if (cand_offsets[0] != 0) return set_err(AGP_EINVAL, "cand_offsets[0] must be 0");
     if (static_cast<size_t>(ix->d) * sizeof(float) > 48 * 1024) return set_err(AGP_EINVAL, "search_subset supports d <= 12288");

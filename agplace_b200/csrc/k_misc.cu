@@ -549,6 +549,21 @@ __global__ void __launch_bounds__(256) ovf_exact_kernel(const int* __restrict__ 
     }
 }
 
+// Multi-device index: local row of a shard -> global id.  tab = (local_start, delta) records in add order; a row belongs to
+// the last record whose local_start is <= it.  Padding (-1) stays.
+__global__ void remap_ids_kernel(int64_t* __restrict__ I, int64_t count, const int64_t* __restrict__ tab, int n_chunks, int64_t extra) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int64_t id = I[i];
+    if (id < 0) return;
+    int lo = 0, hi = n_chunks;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (tab[2 * mid] <= id) lo = mid; else hi = mid;
+    }
+    I[i] = id + tab[2 * lo + 1] + extra;
+}
+
 __global__ void gather_rows_kernel(const float* __restrict__ x, const int* __restrict__ list, int n, int d, float* __restrict__ out) {
     const int r = blockIdx.x;
     if (r >= n) return;
@@ -726,6 +741,12 @@ cudaError_t launch_ovf_exact(const int* ovf_count, const int* ovf_list, const fl
     cudaError_t e = cudaFuncSetAttribute(ovf_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     ovf_exact_kernel<<<num_sms, 256, smem, st>>>(ovf_count, ovf_list, xq, xb, n, d, k, id_base, ip, gq, D, I, stat_fallback);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_remap_ids(int64_t* I, int64_t count, const int64_t* tab, int n_chunks, int64_t extra, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    remap_ids_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, st>>>(I, count, tab, n_chunks, extra);
     return cudaGetLastError();
 }
 

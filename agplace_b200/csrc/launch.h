@@ -149,6 +149,8 @@ cudaError_t launch_best_of_lists(const float* xq, const float* rows, int d, cons
 cudaError_t launch_gather_rows(const float* x, const int* list, int n, int d, float* out, cudaStream_t st);
 cudaError_t launch_scatter_results(const float* Dt, const int64_t* It, const int* list, int n, int k, float* D, int64_t* I, cudaStream_t st);
 cudaError_t launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st);
+// multi-device index: shard-local rows -> global ids through the shard's (local_start, delta) table
+cudaError_t launch_remap_ids(int64_t* I, int64_t count, const int64_t* tab, int n_chunks, int64_t extra, cudaStream_t st);
 // one launch that resets the per-search state of the screen (list counters, bounds, overflow flags, query-plane padding)
 cudaError_t launch_screen_init(int* pcount, uint32_t* hthr, int64_t n_lists, int* ovf, uint32_t* gthr, int64_t nq, int* ovf_count,
                                void* pad, size_t pad_bytes, cudaStream_t st);

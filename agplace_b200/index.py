@@ -65,19 +65,33 @@ class IndexFlatL2:
 
     _metric = METRIC_L2
 
-    def __init__(self, d, device=None, precision=None):
+    def __init__(self, d, device=None, precision=None, devices=None):
+        """``devices=[0, 1, ...]`` (or ``AGP_DEVICES=0,1,...`` in the environment, read here, not in the library) builds ONE
+        index over several GPUs of the box from this single process: rows are split across the devices, every search
+        runs on all of them and is merged on ``devices[0]`` -- same results as a one-device index, same surface, so the
+        reference's ``faiss.IndexFlatL2(d)`` call sites use the whole box unmodified."""
         self.d = int(d)
         self.is_trained = True
         self.metric_type = self._metric
-        self.device = default_device() if device is None else int(device)
+        if devices is None and device is None and os.environ.get("AGP_DEVICES", "") != "":
+            devices = [int(v) for v in os.environ["AGP_DEVICES"].split(",") if v.strip() != ""]
+        self.devices = [int(v) for v in devices] if devices is not None and len(devices) > 1 else None
+        if devices is not None and len(devices) == 1 and device is None:
+            device = int(devices[0])
+        self.device = self.devices[0] if self.devices else (default_device() if device is None else int(device))
         precision = precision or os.environ.get("AGP_PRECISION", "auto")
         if precision not in _lib.PRECISION:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISION)}, got {precision!r}")
         self.precision = precision
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
-        _lib.check(self._lib.agp_index_create_metric(self.d, self.device, _lib.PRECISION[precision], self._metric,
-                                                     ctypes.byref(self._h)), "agp_index_create_metric")
+        if self.devices:
+            ids = (ctypes.c_int * len(self.devices))(*self.devices)
+            _lib.check(self._lib.agp_index_create_multi(self.d, len(self.devices), ids, _lib.PRECISION[precision], self._metric,
+                                                        ctypes.byref(self._h)), "agp_index_create_multi")
+        else:
+            _lib.check(self._lib.agp_index_create_metric(self.d, self.device, _lib.PRECISION[precision], self._metric,
+                                                         ctypes.byref(self._h)), "agp_index_create_metric")
 
     # ------------------------------------------------------------------ faiss attributes
     @property

@@ -187,6 +187,9 @@ class ShardedIndexFlatL2:
         base_applied = self._engine_applies_base()
         if hasattr(self.local, "set_id_base"):
             self.local.set_id_base(self._chunks[0][1] if base_applied else 0)
+        if (self.shard == "db" and as_numpy and isinstance(self.local, IndexFlatL2) and D is None and I is None
+                and nq * d * 4 >= self.PIPELINE_MIN_BYTES and torch.cuda.is_available()):
+            return self._search_host_pipelined(np.ascontiguousarray(x, dtype=np.float32), k, base_applied)
         if isinstance(self.local, IndexFlatL2) and not (_is_torch(xs) and xs.is_cuda) and xs.shape[0]:
             # host queries: one H2D copy, then everything (search, exchange, merge) stays on the GPU
             xh = xs if _is_torch(xs) else torch.from_numpy(np.ascontiguousarray(xs, dtype=np.float32))
@@ -254,6 +257,81 @@ class ShardedIndexFlatL2:
         if as_numpy and I is None:
             Ig = Ig.cpu().numpy()
         return Dg, Ig
+
+
+    # ------------------------------------------------------------------ host-buffer pipeline (row-sharded)
+    PIPELINE_MIN_BYTES = 16 << 20
+    PIPELINE_CHUNK = 18944           # queries per chunk: one wave of 256-query pair tiles on a 148-SM B200
+
+    def _exchange_and_merge(self, D_loc, I_loc, nq, k):
+        """The one exchange step: pack this shard's lists, all-gather, K4 merge (ties by global id)."""
+        import torch
+        import torch.distributed as dist
+        dev = D_loc.device
+        d_bytes = (nq * k * 4 + 7) // 8 * 8
+        i_bytes = nq * k * 8
+        with self._phase("pack"):
+            send = torch.empty(d_bytes + i_bytes, dtype=torch.uint8, device=dev)
+            send[: nq * k * 4].view(torch.float32).copy_(D_loc.reshape(-1))
+            send[d_bytes:].view(torch.int64).copy_(I_loc.reshape(-1))
+            recv = torch.empty(self.world * (d_bytes + i_bytes), dtype=torch.uint8, device=dev)
+        with self._phase("all_gather"):
+            dist.all_gather_into_tensor(recv, send, group=self.group)
+        stride = d_bytes + i_bytes
+        with self._phase("merge"):
+            args = (recv.view(torch.float32), stride // 4, recv.view(torch.int64)[d_bytes // 8:], stride // 8, nq, k, self.world, self._ntotal)
+            return self._merge(*args) if self._metric == METRIC_L2 else self._merge(*args, self._metric)
+
+    def _search_host_pipelined(self, x, k, base_applied):
+        """numpy in / numpy out on every rank, as a pipeline over query chunks: host copy into a pinned buffer + H2D
+        (copy stream) | local search + all-gather + merge (compute stream; nothing in it synchronises the host) | D2H
+        into the pinned result arrays (copy-out stream).  Every rank issues the same sequence of collectives."""
+        import torch
+        from .index import _result_array
+        nq = x.shape[0]
+        dev = torch.device("cuda", self.local.device)
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_s_in"):
+            self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self._stage = [None, None]
+        chunk = self.PIPELINE_CHUNK
+        cuts = list(range(0, nq, chunk)) + [nq]
+        D = _result_array((nq, k), np.float32)
+        I = _result_array((nq, k), np.int64)
+        Dt, It = torch.from_numpy(D), torch.from_numpy(I)
+        pinned_out = Dt.is_pinned() and It.is_pinned()
+        xt = torch.from_numpy(x)
+        xq_dev = torch.empty((nq, self.d), dtype=torch.float32, device=dev)
+        stage_ev = [None, None]
+        pending = []
+        self._s_in.wait_stream(main)                        # xq_dev's block may still be in use by work queued on main
+        for c in range(len(cuts) - 1):
+            a, b = cuts[c], cuts[c + 1]
+            st = self._stage[c & 1]
+            if st is None or st.shape[0] < b - a:
+                st = self._stage[c & 1] = torch.empty((max(chunk, b - a), self.d), dtype=torch.float32, pin_memory=True)
+            if stage_ev[c & 1] is not None:
+                stage_ev[c & 1].synchronize()              # the DMA that last read this pinned buffer is done
+            st[: b - a].copy_(xt[a:b])                      # host memcpy: overlaps the GPU work of the previous chunks
+            with torch.cuda.stream(self._s_in):
+                xq_dev[a:b].copy_(st[: b - a], non_blocking=True)
+                ev_in = torch.cuda.Event(); ev_in.record()
+            stage_ev[c & 1] = ev_in
+            main.wait_event(ev_in)
+            with self._phase("local_search"):
+                D_loc, I_loc = self.local.search(xq_dev[a:b], k)
+            I_loc = self._to_global(I_loc, base_applied)
+            Dg, Ig = self._exchange_and_merge(D_loc, I_loc, b - a, k)
+            ev_done = torch.cuda.Event(); ev_done.record(main)
+            with torch.cuda.stream(self._s_out):
+                self._s_out.wait_event(ev_done)
+                Dt[a:b].copy_(Dg, non_blocking=pinned_out)
+                It[a:b].copy_(Ig, non_blocking=pinned_out)
+            Dg.record_stream(self._s_out); Ig.record_stream(self._s_out)
+            pending.append((Dg, Ig))
+        self._s_out.synchronize()
+        xq_dev.record_stream(self._s_in)
+        return D, I
 
 
 class ShardedIndexFlatIP(ShardedIndexFlatL2):

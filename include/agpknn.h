@@ -71,6 +71,17 @@ AGP_API int agp_index_create(int d, int device, int precision_mode, agp_index** 
 AGP_API int agp_index_create_metric(int d, int device, int precision_mode, int metric, agp_index** out);
 AGP_API int agp_index_metric(const agp_index* idx);
 
+/* The same index over SEVERAL GPUs of one box, driven by ONE process: the reference's call site is a
+ * single process (test.py:27-32, called from train.py:360), so this is what lets the unmodified reference use the whole
+ * box.  device_ids[0] is the home device (merge, host transfers).  Every add() batch is cut into n_devices contiguous
+ * slices; search() sends the queries to every device (one pinned staging copy, one H2D per device; peer copies for
+ * device-resident queries), each device searches its slice on its own stream, pushes its per-shard top-k lists to the
+ * home device over NVLink (cudaMemcpyPeerAsync) and the home device merges them with ties by global id -- bit-identical to
+ * a one-device index.  All other entry points take the returned handle unchanged (search_masked / search_subset /
+ * screen_probe: one-device indexes only).  A device may be listed more than once (virtual shards). */
+AGP_API int agp_index_create_multi(int d, int n_devices, const int* device_ids, int precision_mode, int metric, agp_index** out);
+AGP_API int agp_index_n_shards(const agp_index* idx);
+
 /* Index destructor (SWIG __del__).  Frees every device allocation, stream and event. */
 AGP_API void agp_index_free(agp_index* idx);
 

@@ -35,6 +35,10 @@ def _worker(rank, world, port, shard, out_dir, metric="l2"):
         D, I = ix.search(xq, 40)                                   # numpy in -> numpy out
         Dt, It = ix.search(torch.from_numpy(xq).cuda(), 100)       # CUDA in -> CUDA out
         extra = {}
+        if shard == "db":                                          # the chunked host pipeline (H2D | search + all-gather + merge | D2H)
+            ix.PIPELINE_MIN_BYTES, ix.PIPELINE_CHUNK = 0, 300
+            D3, I3 = ix.search(xq, 40)
+            assert np.array_equal(D3, D) and np.array_equal(I3, I)
         if shard == "query":                                       # results left partitioned by query: this rank's slice only
             Dl, Il = ix.search(xq, 40, gather=False)
             extra = dict(Dl=Dl, Il=Il)
