@@ -1395,6 +1395,12 @@ int agp_index_add(agp_index* ix, int64_t n, const float* x, int mem_kind) {
     if (!ix->shards.empty()) {
         // every add() batch is cut into G contiguous slices (shard g holds [g * ceil(n/G), ...)): global ids stay add-order
         const int64_t G = static_cast<int64_t>(ix->shards.size()), per = (n + G - 1) / G;
+        const bool dev_rows = mem_kind == AGP_MEM_DEVICE;
+        if (dev_rows) {      // device-resident rows were produced on the parent's stream: the shards' copies must come after
+            ENTER(ix);
+            if (!ix->ev_home) CK(cudaEventCreateWithFlags(&ix->ev_home, cudaEventDisableTiming));
+            CK(cudaEventRecord(ix->ev_home, ix->stream));
+        }
         for (int64_t g = 0; g < G; ++g) {
             const int64_t lo = std::min(g * per, n), hi = std::min((g + 1) * per, n);
             if (hi <= lo) continue;
@@ -1405,7 +1411,17 @@ int agp_index_add(agp_index* ix, int64_t n, const float* x, int mem_kind) {
                 tab.push_back({ch->ntotal, delta});
                 ix->shard_tab_dirty[g] = 1;
             }
+            if (dev_rows) {
+                CK(cudaSetDevice(ch->device));
+                CK(cudaStreamWaitEvent(ch->stream, ix->ev_home, 0));
+            }
             CKR(agp_index_add(ch, hi - lo, x + lo * ix->d, mem_kind));
+            if (dev_rows) CK(cudaEventRecord(ix->shard_ev[g], ch->stream));
+        }
+        if (dev_rows) {      // ... and the caller's stream may reuse x only after every shard has copied its slice
+            ENTER(ix);
+            for (int64_t g = 0; g < G; ++g)
+                if (std::min((g + 1) * per, n) > std::min(g * per, n)) CK(cudaStreamWaitEvent(ix->stream, ix->shard_ev[g], 0));
         }
         ix->ntotal += n;
         return 0;

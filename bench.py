@@ -311,9 +311,10 @@ def bench_single(agp, _lib, c, dev, local_rank, steps, warmup, peaks, clocks_on=
     phases = index.get_profile_phases(reset=True)
     index.set_profiling(False)
 
-    # e2e: the reference's call -- pageable numpy in, numpy out
-    for _ in range(2):
-        index.search(xq, k)
+    # e2e: the reference's call -- pageable numpy in, numpy out (warm-up holds the results like the timed loop does, so the
+    # pinned result blocks of two generations exist before the clock starts)
+    for _ in range(3):
+        De, Ie = index.search(xq, k)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e0.record()
@@ -508,9 +509,11 @@ def run_ours(args):
     ex_phases = index.phase_ms()
     index.phase_events = None
 
-    for _ in range(2):
-        step_e2e()
+    keep = None
+    for _ in range(3):
+        keep = step_e2e()
     ms_e2e = timed(step_e2e, steps)
+    del keep
 
     n_local = hi - lo
     nq_local = nq if shard_mode != "query" else (shard_bounds(nq, world)[rank][1] - shard_bounds(nq, world)[rank][0])

@@ -7,10 +7,24 @@ import torch
 import agplace_b200 as agp
 import bench
 
-n_dev = int(sys.argv[1]) if len(sys.argv) > 1 else torch.cuda.device_count()
+arg = sys.argv[1] if len(sys.argv) > 1 else str(torch.cuda.device_count())
+devices = [int(v) for v in arg.split(",")] if "," in arg else list(range(int(arg)))
+n_dev = len(devices)
 c = bench.workload(sys.argv[2] if len(sys.argv) > 2 else "cfg4")
-devices = list(range(n_dev))
+if len(sys.argv) > 3:
+    c["n"] = int(sys.argv[3])
+T0 = time.perf_counter()
+import faulthandler
+faulthandler.dump_traceback_later(150, repeat=False, file=sys.stderr)
+
+
+def log(msg):
+    print(f"[{time.perf_counter() - T0:7.2f}s] {msg}", file=sys.stderr, flush=True)
+
+
 ix = agp.IndexFlatL2(c["d"], devices=devices) if n_dev > 1 else agp.IndexFlatL2(c["d"], device=0)
+ix.reserve(c["n"])
+log("index created")
 t0 = time.perf_counter()
 step_rows = 1 << 18
 from agplace_b200 import synth
@@ -19,10 +33,13 @@ for a in range(0, c["n"], step_rows):
     ix.add(synth.counter_rows_device(a, b, c["d"], c["seed"], torch.device("cuda", 0)))
 torch.cuda.synchronize()
 add_s = time.perf_counter() - t0
+log(f"added {ix.ntotal} rows")
 xq = bench.host_queries(c)
 xq_d = torch.from_numpy(xq).to("cuda:0")
 k = c["k"]
 D, I = ix.search(xq_d, k)
+torch.cuda.synchronize()
+log("first search done")
 ver = bench.verify_sample(c, xq, D.cpu().numpy(), I.cpu().numpy())
 for _ in range(2):
     ix.search(xq_d, k)
@@ -33,12 +50,28 @@ for _ in range(reps):
     ix.search(xq_d, k)
 torch.cuda.synchronize()
 dev_ms = (time.perf_counter() - t0) / reps * 1e3
+log(f"device steps {dev_ms:.1f} ms")
 ix.search(xq, k)
+log("first numpy search done")
 t0 = time.perf_counter()
 for _ in range(reps):
     De, Ie = ix.search(xq, k)
 e2e_ms = (time.perf_counter() - t0) / reps * 1e3
 same = bool(np.array_equal(Ie, I.cpu().numpy()))
+xp = torch.from_numpy(xq).pin_memory().numpy()
+Dp = torch.empty((c["nq"], k), dtype=torch.float32).pin_memory().numpy()
+Ip = torch.empty((c["nq"], k), dtype=torch.int64).pin_memory().numpy()
+for name, fn, chunk in [("pinned_in_pinned_out", lambda: ix.search(xp, k, D=Dp, I=Ip), 0), ("pageable_in_pinned_out", lambda: ix.search(xq, k, D=Dp, I=Ip), 0),
+                        ("pageable_in_fresh_out", lambda: ix.search(xq, k), 0), ("pageable_one_chunk", lambda: ix.search(xq, k), 1 << 20),
+                        ("pageable_half_wave_chunks", lambda: ix.search(xq, k), 9472)]:
+    ix.set_knob("pipe_chunk", chunk)
+    fn(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    log(f"{name}: {(time.perf_counter() - t0) / reps * 1e3:.1f} ms")
+ix.set_knob("pipe_chunk", 0)
 print(json.dumps(dict(workload=c["name"], devices=devices, single_process=True, add_s=round(add_s, 1), device_step_ms=round(dev_ms, 2),
                       device_qps=round(c["nq"] / dev_ms * 1e3), numpy_e2e_ms=round(e2e_ms, 2), e2e_qps=round(c["nq"] / e2e_ms * 1e3),
                       numpy_equals_device=same, verify=ver)))
