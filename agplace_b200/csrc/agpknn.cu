@@ -135,6 +135,47 @@ cudaError_t pool_stream(int dev, cudaStream_t* s) {
     return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
 }
 
+// Page-locked host blocks (power-of-two classes, <= 8 MB, at most 256 MB cached): the host mirror and the query / result
+// bounce buffers of small indexes -- the mining loop builds and drops thousands of them (cudaHostAlloc costs ~100 us).
+struct HostPool {
+    std::mutex mu;
+    std::unordered_map<size_t, std::vector<void*>> blocks;
+    size_t cached = 0;
+};
+HostPool g_host_pool;
+size_t host_class(size_t bytes) {
+    size_t c = 4096;
+    while (c < bytes) c <<= 1;
+    return c;
+}
+cudaError_t host_pool_alloc(void** p, size_t bytes) {
+    const size_t c = host_class(bytes);
+    {
+        std::lock_guard<std::mutex> lk(g_host_pool.mu);
+        auto it = g_host_pool.blocks.find(c);
+        if (it != g_host_pool.blocks.end() && !it->second.empty()) {
+            *p = it->second.back();
+            it->second.pop_back();
+            g_host_pool.cached -= c;
+            return cudaSuccess;
+        }
+    }
+    return cudaHostAlloc(p, c, cudaHostAllocPortable | cudaHostAllocMapped);
+}
+void host_pool_free(void* p, size_t bytes) {       // precondition: no queued work reads or writes the block
+    if (!p) return;
+    const size_t c = host_class(bytes);
+    {
+        std::lock_guard<std::mutex> lk(g_host_pool.mu);
+        if (c <= (size_t(8) << 20) && g_host_pool.cached + c <= (size_t(256) << 20)) {
+            g_host_pool.blocks[c].push_back(p);
+            g_host_pool.cached += c;
+            return;
+        }
+    }
+    cudaFreeHost(p);
+}
+
 void pool_stream_release(int dev, cudaStream_t s) {       // precondition: synchronised
     if (!s) return;
     if (dev >= 0 && dev < 16) {
@@ -360,6 +401,16 @@ struct agp_index {
     uint8_t* out_slot[2] = {nullptr, nullptr};
     size_t out_slot_bytes = 0;
     std::vector<cudaEvent_t> pipe_ev;
+    // Small host-fed indexes (the reference's per-query mining indexes: <= 1000 x 256 rows, one search, dropped): add()
+    // only copies the rows into a pinned host mirror; the first search uploads them asynchronously and answers with one
+    // fused kernel.  lazy = the mirror holds rows the device does not have yet.
+    bool lazy = true;
+    uint8_t* h_rows = nullptr;                       // pinned mirror of rows [0, ntotal) while lazy
+    size_t h_rows_bytes = 0;
+    uint8_t* h_io = nullptr;                         // pinned bounce: queries in, (D, I) out of a small search
+    size_t h_io_bytes = 0;
+    int64_t norm_rows = 0;                           // rows [0, norm_rows) have their squared norm in yn (computed on demand)
+    int64_t dev_rows = 0;                            // rows [0, dev_rows) are resident in xb (< ntotal only while lazy)
     int pipe_chunk = 0;                              // knob: queries per pipeline chunk (0 = automatic)
     int screen_chunk = 0;                            // knob: queries per screen launch (0 = automatic)
     int screen_lockstep = -1;                        // knob: tiles between the meeting points of a full wave (0 = off, -1 = automatic)
@@ -457,14 +508,14 @@ static int grow(agp_index* ix, int64_t need) {
             LAUNCH(launch_fill_f32(nwx, ncap, 0.f, ix->stream));
         }
     }
-    LAUNCH(launch_fill_f32(nyn, ncap, HUGE_VALF, ix->stream));
-    if (ix->ntotal > 0) {
-        CK(cudaMemcpyAsync(nxb, ix->xb, static_cast<size_t>(ix->ntotal) * ix->d * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
-        CK(cudaMemcpyAsync(nyn, ix->yn, static_cast<size_t>(ix->ntotal) * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+    if (ix->planes) LAUNCH(launch_fill_f32(nyn, ncap, HUGE_VALF, ix->stream));      // +inf beyond ntotal masks the 3x kernels' zero-filled tail rows
+    if (ix->dev_rows > 0) {
+        CK(cudaMemcpyAsync(nxb, ix->xb, static_cast<size_t>(ix->dev_rows) * ix->d * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+        CK(cudaMemcpyAsync(nyn, ix->yn, static_cast<size_t>(ix->dev_rows) * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
         if (ix->planes) {
-            CK(cudaMemcpyAsync(nhi, ix->xb_hi, static_cast<size_t>(ix->ntotal) * plane_row, cudaMemcpyDeviceToDevice, ix->stream));
-            CK(cudaMemcpyAsync(nlo, ix->xb_lo, static_cast<size_t>(ix->ntotal) * plane_row, cudaMemcpyDeviceToDevice, ix->stream));
-            if (nwx) CK(cudaMemcpyAsync(nwx, ix->wx, static_cast<size_t>(ix->ntotal) * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+            CK(cudaMemcpyAsync(nhi, ix->xb_hi, static_cast<size_t>(ix->dev_rows) * plane_row, cudaMemcpyDeviceToDevice, ix->stream));
+            CK(cudaMemcpyAsync(nlo, ix->xb_lo, static_cast<size_t>(ix->dev_rows) * plane_row, cudaMemcpyDeviceToDevice, ix->stream));
+            if (nwx) CK(cudaMemcpyAsync(nwx, ix->wx, static_cast<size_t>(ix->dev_rows) * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
         }
     }
     if (ix->cap > 0) {
@@ -607,6 +658,28 @@ static int choose_splits(int n_qtiles, int n_dbtiles, int num_sms) {
 // ------------------------------------------------------------------------------------------ search paths
 // every path writes D/I (device) for queries [q0, q0+nqc)
 
+constexpr size_t kLazyMaxBytes = size_t(4) << 20;
+
+// rows that so far only live in the pinned host mirror go to the device (asynchronous: the mirror is page-locked and stays
+// allocated until the index is reset or freed)
+static int flush_lazy(agp_index* ix) {
+    if (!ix->lazy || ix->ntotal == 0 || !ix->h_rows) return 0;
+    CKR(grow(ix, ix->ntotal));
+    CK(cudaMemcpyAsync(ix->xb, ix->h_rows, static_cast<size_t>(ix->ntotal) * ix->d * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+    ix->dev_rows = ix->ntotal;
+    ix->lazy = false;
+    return 0;
+}
+
+// squared norms of the rows that do not have one yet (fp32 tile path only)
+static int ensure_norms(agp_index* ix) {
+    if (ix->norm_rows >= ix->ntotal) return 0;
+    const int64_t a = ix->norm_rows, n = ix->ntotal - a;
+    LAUNCH(launch_prep_rows(false, ix->xb + a * ix->d, n, ix->d, ix->d_pad, ix->yn + a, nullptr, nullptr, ix->num_sms * 32, ix->stream));
+    ix->norm_rows = ix->ntotal;
+    return 0;
+}
+
 static int search_empty(agp_index* ix, int64_t nq, int k, float* D, int64_t* I) {
     // no database rows: emit padding through the merge kernel with zero lists
     return DISPATCH_E32(k, launch_merge_keys, static_cast<const uint64_t*>(nullptr), nq, 0, k, ix->id_base, D, I, ix->ip, ix->stream);
@@ -630,6 +703,12 @@ static int search_diff(agp_index* ix, const float* xq_dev, int64_t nq, int k, fl
     for (int64_t q0 = 0; q0 < nq; q0 += max_group) {
         const int g = static_cast<int>(std::min<int64_t>(max_group, nq - q0));
         ProfScope prof(ix);
+        if (n <= kFusedSmallMaxRows) {      // small database: distances and selection in one launch
+            LAUNCH(launch_diff_small_fused(xq_dev + q0 * ix->d, g, ix->xb, n, ix->d, static_cast<float*>(ix->panel.p), ld, ix->num_sms, ix->ip,
+                                           ix->dbstats + 6, k, ix->id_base, D + q0 * k, I + q0 * k, ix->stream));
+            prof.stop();
+            continue;
+        }
         LAUNCH(launch_diff_small(xq_dev + q0 * ix->d, g, ix->xb, n, ix->d, static_cast<float*>(ix->panel.p), ld, ix->num_sms, ix->ip, ix->stream));
         prof.stop();
         CKR(select_and_merge(ix, static_cast<const float*>(ix->panel.p), ld, g, k, D + q0 * k, I + q0 * k));
@@ -642,6 +721,7 @@ static int search_simt(agp_index* ix, const float* xq_dev, int64_t nq, int k, fl
     const int64_t ld = round_up(n, 32);
     // select_rows / merge_keys put the query on grid.y (<= 65535)
     const int64_t max_rows = std::max<int64_t>(1, std::min<int64_t>({nq, (static_cast<int64_t>(128) << 20) / ld, int64_t(65535)}));
+    CKR(ensure_norms(ix));
     CKR(ensure(ix->panel, static_cast<size_t>(max_rows) * ld * sizeof(float)));
     CKR(ensure(ix->qn, static_cast<size_t>(nq) * sizeof(float)));
     LAUNCH(launch_prep_rows(false, xq_dev, nq, ix->d, ix->d_pad, static_cast<float*>(ix->qn.p), nullptr, nullptr, ix->num_sms * 32, ix->stream));
@@ -1192,6 +1272,8 @@ void agp_index_free(agp_index* ix) {
         if (ix->stage[b]) cudaFreeHost(ix->stage[b]);
         if (ix->stage_ev[b]) cudaEventDestroy(ix->stage_ev[b]);
     }
+    host_pool_free(ix->h_rows, ix->h_rows_bytes);
+    host_pool_free(ix->h_io, ix->h_io_bytes);
     for (int b = 0; b < 3; ++b) {
         if (ix->in_ring[b]) cudaFreeHost(ix->in_ring[b]);
         if (ix->in_ring_ev[b]) cudaEventDestroy(ix->in_ring_ev[b]);
@@ -1254,6 +1336,7 @@ int agp_index_screen_probe(agp_index* ix, int64_t nq, const float* x, float* dis
     if (nq * ix->ntotal > (int64_t(1) << 28)) return set_err(AGP_EINVAL, "nq * ntotal too large for a probe");
     if (ix->num_sms & 1) return set_err(AGP_EINVAL, "the screen kernel needs an even SM count");
     ENTER(ix);
+    CKR(flush_lazy(ix));
     const int64_t n = ix->ntotal, ld = round_up(n, TC_BN);
     const int k = static_cast<int>(std::min<int64_t>(10, n));
     Buf dump;
@@ -1351,6 +1434,10 @@ int agp_index_reset(agp_index* ix) {
         return 0;
     }
     ENTER(ix);
+    if (ix->h_rows) CK(cudaStreamSynchronize(ix->stream));      // a queued upload may still read the mirror
+    ix->lazy = true;
+    ix->norm_rows = 0;
+    ix->dev_rows = 0;
     if (ix->cap > 0) {
         LAUNCH(launch_fill_f32(ix->yn, ix->cap, HUGE_VALF, ix->stream));
     }
@@ -1427,7 +1514,26 @@ int agp_index_add(agp_index* ix, int64_t n, const float* x, int mem_kind) {
         return 0;
     }
     if (ix->ntotal + n > 0x7fffffffLL) return set_err(AGP_EINVAL, "a single shard holds at most 2^31-1 rows");
+    const size_t row_bytes = static_cast<size_t>(ix->d) * sizeof(float);
+    if (ix->lazy && !ix->planes && mem_kind != AGP_MEM_DEVICE && static_cast<size_t>(ix->ntotal + n) * row_bytes <= kLazyMaxBytes) {
+        // small host-fed index: keep the rows in the pinned mirror, touch no device state (no allocation, launch or sync)
+        const size_t need = static_cast<size_t>(ix->ntotal + n) * row_bytes;
+        if (need > ix->h_rows_bytes) {
+            void* nb = nullptr;
+            CK(cudaSetDevice(ix->device));
+            CK(host_pool_alloc(&nb, need + need / 2));
+            if (ix->ntotal > 0) std::memcpy(nb, ix->h_rows, static_cast<size_t>(ix->ntotal) * row_bytes);
+            host_pool_free(ix->h_rows, ix->h_rows_bytes);
+            ix->h_rows = static_cast<uint8_t*>(nb);
+            ix->h_rows_bytes = host_class(need + need / 2);
+        }
+        std::memcpy(ix->h_rows + static_cast<size_t>(ix->ntotal) * row_bytes, x, static_cast<size_t>(n) * row_bytes);
+        ix->ntotal += n;
+        return 0;
+    }
     ENTER(ix);
+    CKR(flush_lazy(ix));
+    ix->lazy = false;
     CKR(grow(ix, ix->ntotal + n));
     float* dst = ix->xb + ix->ntotal * ix->d;
     if (mem_kind == AGP_MEM_DEVICE) {
@@ -1442,10 +1548,11 @@ int agp_index_add(agp_index* ix, int64_t n, const float* x, int mem_kind) {
     } else if (ix->planes) {
         LAUNCH(launch_prep_rows(true, dst, n, ix->d, ix->d_pad, ix->yn + ix->ntotal, reinterpret_cast<float*>(ix->xb_hi + plane_off),
                                 reinterpret_cast<float*>(ix->xb_lo + plane_off), ix->num_sms * 32, ix->stream));
-    } else {
-        LAUNCH(launch_prep_rows(false, dst, n, ix->d, ix->d_pad, ix->yn + ix->ntotal, nullptr, nullptr, ix->num_sms * 32, ix->stream));
     }
+    // (no planes: the squared norms are only needed by the fp32 tile path and are computed on demand -- ensure_norms)
+    if (ix->planes) ix->norm_rows = ix->ntotal + n;
     ix->ntotal += n;
+    ix->dev_rows = ix->ntotal;
     if (mem_kind != AGP_MEM_DEVICE) CK(cudaStreamSynchronize(ix->stream));   // caller may reuse x immediately
     return 0;
 }
@@ -1453,6 +1560,7 @@ int agp_index_add(agp_index* ix, int64_t n, const float* x, int mem_kind) {
 // device queries -> device results for [0, nq) on the index's stream (asynchronous)
 static int search_device(agp_index* ix, const float* xq_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
     if (ix->ntotal == 0) return search_empty(ix, nq, k, D_dev, I_dev);
+    CKR(flush_lazy(ix));
     switch (ix->mode) {
         case AGP_PRECISION_AUTO:
             return (nq < kMaxSmallNq) ? search_diff(ix, xq_dev, nq, k, D_dev, I_dev) : search_screen(ix, xq_dev, nq, k, D_dev, I_dev);
@@ -1749,6 +1857,43 @@ int agp_index_search(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, 
     ENTER(ix);
     if (ix->shards.empty() && x_mem_kind == AGP_MEM_DEVICE && out_mem_kind == AGP_MEM_DEVICE)
         return search_device(ix, x, nq, k, D, I);      // asynchronous on the index's stream: nothing here waits for the GPU
+    if (ix->shards.empty() && x_mem_kind != AGP_MEM_DEVICE && out_mem_kind != AGP_MEM_DEVICE && nq < kMaxSmallNq && ix->ntotal > 0 &&
+        ix->ntotal <= kFusedSmallMaxRows && (ix->mode == AGP_PRECISION_AUTO || ix->mode == AGP_PRECISION_EXACT_DIFF) &&
+        static_cast<size_t>(nq) * ix->d * sizeof(float) <= 96 * 1024) {
+        // The reference's mining call (one query against <= 1000 rows, kitti360:981,990): queries and results bounce through
+        // one pinned block, the rows go up asynchronously from the pinned mirror, ONE fused kernel writes (D, I) straight
+        // into the pinned block over PCIe, one synchronisation.
+        const size_t q_bytes = static_cast<size_t>(nq) * ix->d * sizeof(float);
+        const size_t d_bytes = (static_cast<size_t>(nq) * k * sizeof(float) + 15) & ~size_t(15), i_bytes = static_cast<size_t>(nq) * k * sizeof(int64_t);
+        const size_t q_off = d_bytes + i_bytes;
+        if (q_off + q_bytes > ix->h_io_bytes) {
+            CK(cudaStreamSynchronize(ix->stream));
+            host_pool_free(ix->h_io, ix->h_io_bytes);
+            ix->h_io = nullptr;
+            ix->h_io_bytes = 0;
+            void* nb = nullptr;
+            CK(host_pool_alloc(&nb, q_off + q_bytes));
+            ix->h_io = static_cast<uint8_t*>(nb);
+            ix->h_io_bytes = host_class(q_off + q_bytes);
+        }
+        CKR(flush_lazy(ix));
+        std::memcpy(ix->h_io + q_off, x, q_bytes);
+        CKR(ensure(ix->q_raw, q_bytes));
+        CK(cudaMemcpyAsync(ix->q_raw.p, ix->h_io + q_off, q_bytes, cudaMemcpyHostToDevice, ix->stream));
+        const int64_t n = ix->ntotal, ld = round_up(n, 32);
+        CKR(ensure(ix->panel, static_cast<size_t>(nq) * ld * sizeof(float)));
+        {
+            ProfScope prof(ix);
+            LAUNCH(launch_diff_small_fused(static_cast<const float*>(ix->q_raw.p), static_cast<int>(nq), ix->xb, n, ix->d, static_cast<float*>(ix->panel.p),
+                                           ld, ix->num_sms, ix->ip, ix->dbstats + 6, k, ix->id_base, reinterpret_cast<float*>(ix->h_io),
+                                           reinterpret_cast<int64_t*>(ix->h_io + d_bytes), ix->stream));
+            prof.stop();
+        }
+        CK(cudaStreamSynchronize(ix->stream));
+        std::memcpy(D, ix->h_io, static_cast<size_t>(nq) * k * sizeof(float));
+        std::memcpy(I, ix->h_io + d_bytes, i_bytes);
+        return 0;
+    }
     return search_host_pipelined(ix, nq, x, x_mem_kind, k, D, I, out_mem_kind);
 }
 
@@ -1773,6 +1918,7 @@ int agp_index_search_masked(agp_index* ix, int64_t nq, const float* x, int x_mem
     if (kp64 > AGP_MAX_K) return set_err(AGP_EINVAL, "k + longest exclusion list = %lld exceeds AGP_MAX_K=%d", static_cast<long long>(k + max_ex), AGP_MAX_K);
     const int kp = static_cast<int>(kp64);
     ENTER(ix);
+    CKR(flush_lazy(ix));
     CKR(ensure(ix->mk_d, static_cast<size_t>(nq) * kp * sizeof(float)));
     CKR(ensure(ix->mk_i, static_cast<size_t>(nq) * kp * sizeof(int64_t)));
     CKR(ensure(ix->mk_off, static_cast<size_t>(nq + 1) * sizeof(int64_t)));
@@ -1850,6 +1996,7 @@ int agp_index_search_subset(agp_index* ix, int64_t nq, const float* x, int x_mem
             return set_err(AGP_EINVAL, "cand_ids[%lld] = %lld is not a row of this index (ntotal = %lld)", static_cast<long long>(e),
                            static_cast<long long>(cand_ids[e]), static_cast<long long>(ix->ntotal));
     ENTER(ix);
+    CKR(flush_lazy(ix));
     const float* xq_dev = x;
     if (x_mem_kind != AGP_MEM_DEVICE) {
         CKR(ensure(ix->q_raw, static_cast<size_t>(nq) * ix->d * sizeof(float)));

@@ -249,11 +249,33 @@ __global__ void fill_f32_kernel(float* __restrict__ p, int64_t n, float v) {
     if (i < n) p[i] = v;
 }
 
+constexpr int OVF_CAP = 1024, OVF_GQ = 4, OVF_ROWS = 4;      // rows per warp per round
+
+__device__ __forceinline__ void block_sort_1024(uint64_t* keys) {
+    for (int size = 2; size <= OVF_CAP; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < OVF_CAP / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool asc = (lo & size) == 0;
+                const uint64_t a = keys[lo], b = keys[hi];
+                if ((a > b) == asc) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // dist[q * ld + r] = sum_c (xq[q,c] - xb[r,c])^2
 // ip != 0: dist[q * ld + r] = -<xq[q], xb[r]>  (IndexFlatIP: the smallest negated products are the best matches)
+// Fused tail (ticket != nullptr; small databases -- the reference's mining calls search <= 1000 rows with one query):
+// the block that finishes last (atomicInc ticket, which wraps back to 0 by itself) selects the k best of every query from
+// the distance rows with a block-wide bitonic sort and writes the final (D, I) -- one launch instead of distance kernel +
+// row select + merge.
 __global__ void __launch_bounds__(256) diff_small_kernel(const float* __restrict__ xq, int nq, const float* __restrict__ xb,
-                                                         int64_t n, int d, float* __restrict__ dist, int64_t ld, int ip) {
-    extern __shared__ float sq[];   // [nq][d]
+                                                         int64_t n, int d, float* __restrict__ dist, int64_t ld, int ip,
+                                                         unsigned int* __restrict__ ticket, int k, int64_t id_base,
+                                                         float* __restrict__ D, int64_t* __restrict__ I) {
+    extern __shared__ __align__(16) float sq[];   // [nq][d]; reused as the 1024-key sort buffer by the fused tail
     for (int i = threadIdx.x; i < nq * d; i += blockDim.x) sq[i] = xq[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -306,6 +328,45 @@ __global__ void __launch_bounds__(256) diff_small_kernel(const float* __restrict
                 for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFull, a, o);
                 if (lane == 0) dist[q * ld + r] = ip ? -a : a;
             }
+        }
+    }
+    if (ticket == nullptr) return;
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sq);       // OVF_CAP keys (the launcher sizes the dynamic window for it)
+    for (int q = 0; q < nq; ++q) {
+        const float* row = dist + static_cast<int64_t>(q) * ld;
+        int have = 0;                                       // best keys kept so far, sorted, at keys[0 .. have)
+        int64_t base = 0;
+        do {
+            __syncthreads();
+            const int room = OVF_CAP - have;
+            for (int i = threadIdx.x; i < room; i += blockDim.x) {
+                const int64_t c = base + i;
+                uint64_t key = kEmptyKey;
+                if (c < n) {
+                    const float v = __ldcg(row + c);
+                    key = ip ? pack_key_signed(v, static_cast<uint32_t>(c)) : pack_key(v, static_cast<uint32_t>(c));
+                }
+                keys[have + i] = key;
+            }
+            __syncthreads();
+            block_sort_1024(keys);
+            base += room;
+            const int64_t seen = base < n ? base : n;
+            have = static_cast<int>(seen < k ? seen : k);
+        } while (base < n);
+        __syncthreads();
+        for (int i = threadIdx.x; i < k; i += blockDim.x) {
+            const bool empty = i >= have || keys[i] == kEmptyKey;
+            const uint64_t key = keys[i];
+            D[static_cast<int64_t>(q) * k + i] = ip ? (empty ? -3.4028234663852886e38f : -key_value_signed(key)) : (empty ? 3.4028234663852886e38f : key_dist(key));
+            I[static_cast<int64_t>(q) * k + i] = empty ? -1 : id_base + static_cast<int64_t>(key_idx(key));
         }
     }
 }
@@ -418,22 +479,6 @@ __global__ void screen_init_kernel(int* __restrict__ pcount, uint32_t* __restric
 // Up to 4 flagged queries per block share one pass over the database: warps evaluate the fp32 difference form (same
 // per-lane summation order as diff_small_kernel: bit-identical distances to a small-batch search), keys below the
 // query's current k-th key are appended to a 1024-entry shared buffer that is sorted (block bitonic) whenever it fills.
-constexpr int OVF_CAP = 1024, OVF_GQ = 4, OVF_ROWS = 4;      // rows per warp per round
-
-__device__ __forceinline__ void block_sort_1024(uint64_t* keys) {
-    for (int size = 2; size <= OVF_CAP; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = threadIdx.x; i < OVF_CAP / 2; i += blockDim.x) {
-                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
-                const bool asc = (lo & size) == 0;
-                const uint64_t a = keys[lo], b = keys[hi];
-                if ((a > b) == asc) { keys[lo] = b; keys[hi] = a; }
-            }
-            __syncthreads();
-        }
-    }
-}
-
 __global__ void __launch_bounds__(256) ovf_exact_kernel(const int* __restrict__ ovf_count, const int* __restrict__ ovf_list,
                                                         const float* __restrict__ xq, const float* __restrict__ xb, int64_t n, int d,
                                                         int k, int64_t id_base, int ip, int gq, float* __restrict__ D,
@@ -811,13 +856,35 @@ cudaError_t launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+static cudaError_t diff_small_attr() {
+    static bool done = false;      // (one device family per process: the attribute is per function, set once per device in practice)
+    static int last_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (done && dev == last_dev) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(diff_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e == cudaSuccess) { done = true; last_dev = dev; }
+    return e;
+}
+
 cudaError_t launch_diff_small(const float* xq, int nq, const float* xb, int64_t n, int d, float* dist, int64_t ld, int num_sms,
                               int ip, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(nq) * d * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(diff_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = diff_small_attr();
     if (e != cudaSuccess) return e;
     const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(num_sms) * 8)));
-    diff_small_kernel<<<blocks, 256, smem, st>>>(xq, nq, xb, n, d, dist, ld, ip);
+    diff_small_kernel<<<blocks, 256, smem, st>>>(xq, nq, xb, n, d, dist, ld, ip, nullptr, 0, 0, nullptr, nullptr);
+    return cudaGetLastError();
+}
+
+// distances + top-k of a small database in ONE launch (n <= kFusedSmallMaxRows, k <= 512)
+cudaError_t launch_diff_small_fused(const float* xq, int nq, const float* xb, int64_t n, int d, float* dist, int64_t ld, int num_sms,
+                                    int ip, unsigned int* ticket, int k, int64_t id_base, float* D, int64_t* I, cudaStream_t st) {
+    const size_t smem = std::max(static_cast<size_t>(nq) * d * sizeof(float), static_cast<size_t>(OVF_CAP) * sizeof(uint64_t));
+    cudaError_t e = diff_small_attr();
+    if (e != cudaSuccess) return e;
+    const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(num_sms) * 8)));
+    diff_small_kernel<<<blocks, 256, smem, st>>>(xq, nq, xb, n, d, dist, ld, ip, ticket, k, id_base, D, I);
     return cudaGetLastError();
 }
 

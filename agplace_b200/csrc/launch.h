@@ -163,6 +163,9 @@ cudaError_t launch_radius(bool fill, const double* db, int64_t n, int dim, const
                           const int64_t* offsets, int64_t* ids, cudaStream_t st);
 cudaError_t launch_diff_small(const float* xq, int nq, const float* xb, int64_t n, int d, float* dist, int64_t ld, int num_sms,
                               int ip, cudaStream_t st);
+constexpr int kFusedSmallMaxRows = 4096;      // databases up to this size: distances + selection fused in one launch
+cudaError_t launch_diff_small_fused(const float* xq, int nq, const float* xb, int64_t n, int d, float* dist, int64_t ld, int num_sms,
+                                    int ip, unsigned int* ticket, int k, int64_t id_base, float* D, int64_t* I, cudaStream_t st);
 cudaError_t launch_dist_simt(const float* xq, const float* qn, int nq, const float* xb, const float* yn, int64_t n, int d, float* dist,
                              int64_t ld, int ip, cudaStream_t st);
 cudaError_t launch_recall(const int64_t* I, int64_t nq, int k, const int64_t* pos_off, const int64_t* pos_ids, const int* ns, int n_ns,

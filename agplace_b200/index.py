@@ -49,7 +49,7 @@ def _result_array(shape, dtype):
     blocks from torch's caching host allocator (the block goes back to that cache when the array is garbage
     collected): the engine's D2H copy then lands directly in the array the caller receives -- no pinned staging copy,
     no first-touch page faults on a fresh pageable allocation."""
-    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    nbytes = shape[0] * shape[1] * (4 if dtype is np.float32 else 8)
     if _PINNED_RESULT_MIN <= nbytes <= _PINNED_RESULT_MAX:
         try:
             import torch
@@ -85,6 +85,7 @@ class IndexFlatL2:
         self.precision = precision
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
+        self._foreign_stream = False
         if self.devices:
             ids = (ctypes.c_int * len(self.devices))(*self.devices)
             _lib.check(self._lib.agp_index_create_multi(self.d, len(self.devices), ids, _lib.PRECISION[precision], self._metric,
@@ -114,9 +115,12 @@ class IndexFlatL2:
             raise ValueError(f"tensor is on cuda:{tensor.device.index} but the index lives on cuda:{self.device}")
         stream = torch.cuda.current_stream(tensor.device).cuda_stream
         _lib.check(self._lib.agp_index_set_stream(self._h, ctypes.c_void_p(stream), 0), "agp_index_set_stream")
+        self._foreign_stream = True
 
     def _use_own_stream(self):
-        _lib.check(self._lib.agp_index_set_stream(self._h, None, 1), "agp_index_set_stream")
+        if self._foreign_stream:      # (a fresh index is already on its own stream: the mining loop never pays this call)
+            _lib.check(self._lib.agp_index_set_stream(self._h, None, 1), "agp_index_set_stream")
+            self._foreign_stream = False
 
     # ------------------------------------------------------------------ add / reset
     def add(self, x):

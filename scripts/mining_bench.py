@@ -22,5 +22,18 @@ for name, kw, meth in (("loop_gpu_engine", {}, "compute_triplets_partial"), ("lo
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     res[name] = dict(seconds=round(best, 4), us_per_query=round(best / R * 1e6, 1), checksum=int(t.sum()))
+# one index lifecycle of the reference's two mining calls: IndexFlatL2(d); add(rows); search(1 query, k); drop
+import agplace_b200 as agp
+rng = np.random.default_rng(0)
+for name, rows, k in (("lifecycle_1000x256_k10", 1000, 10), ("lifecycle_3x256_k1", 3, 1)):
+    xb = rng.standard_normal((rows, 256)).astype(np.float32)
+    q = rng.standard_normal((1, 256)).astype(np.float32)
+    for cls, tag in ((agp.IndexFlatL2, "gpu_engine"), (orc.IndexFlatL2, "cpu_oracle")):
+        for _ in range(50):
+            ix = cls(256); ix.add(xb); ix.search(q, k)
+        t0 = time.perf_counter()
+        for _ in range(500):
+            ix = cls(256); ix.add(xb); ix.search(q, k)
+        res[f"{name}_{tag}_us"] = round((time.perf_counter() - t0) / 500 * 1e6, 1)
 res["identical"] = len({v["checksum"] for v in res.values() if isinstance(v, dict)}) == 1
 print(json.dumps(res))
