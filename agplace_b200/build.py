@@ -21,12 +21,16 @@ LIB = PKG / "libagpknn.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+if os.environ.get("AGP_BUILD_DEBUG", "") not in ("", "0"):
+    # development build: AGP_SCREEN_* / AGP_TC_* environment seeding of the per-index knobs and the result-changing
+    # bandwidth probes (skip_epi, skip_mma).  The product build has none of it.
+    CFLAGS.append("-DAGP_DEBUG_KNOBS")
 
 # (source, define value or None, object name)
 UNITS = (
     [("agpknn.cu", None, "agpknn.o"), ("k_misc.cu", None, "k_misc.o")]
     + [("k_tc.cu", e, f"k_tc_{e}.o") for e in (2, 4, 8, 16)]
-    + [("k_screen.cu", e, f"k_screen_{e}.o") for e in (8, 16)]
+    + [("k_screen.cu", e, f"k_screen_{e}.o") for e in (8, 16, 32)]
     + [("k_select.cu", e, f"k_select_{e}.o") for e in (2, 4, 8, 16, 32)]
 )
 

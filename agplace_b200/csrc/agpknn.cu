@@ -353,7 +353,7 @@ struct Knobs {
     int screen_flags = 0;     // ScreenParams::flags (bit 0 branchy scan, bit 2 no pair exchange, bit 3 no first-tile bootstrap)
     int screen_e = 0;         // candidate slots per list / 32 (8 or 16), 0 = automatic
     int screen_stages = 0;    // operand ring depth, 0 = as many as fit
-    int screen_sched = 8;     // compaction schedule multiplier in quarters (8 = doubling)
+    int screen_sched = 0;     // compaction schedule multiplier in quarters (8 = doubling, 12 = x3), 0 = automatic
     int tc_e = 0;             // 3xTF32 / 3xFP16 kernel: register budget override
     int tc_rerank = 1;        // 3xTF32 / 3xFP16: exact re-rank of k + margin candidates
     int tc_compact_sort = 0;  // 3xTF32 / 3xFP16: exact warp sort instead of the pivot compaction
@@ -412,6 +412,7 @@ struct agp_index {
     int64_t norm_rows = 0;                           // rows [0, norm_rows) have their squared norm in yn (computed on demand)
     int64_t dev_rows = 0;                            // rows [0, dev_rows) are resident in xb (< ntotal only while lazy)
     int pipe_chunk = 0;                              // knob: queries per pipeline chunk (0 = automatic)
+    int pipe_first = 0;                              // knob: two chunks, the first with this many queries (0 = automatic)
     int screen_chunk = 0;                            // knob: queries per screen launch (0 = automatic)
     int screen_lockstep = -1;                        // knob: tiles between the meeting points of a full wave (0 = off, -1 = automatic)
     Buf sync_ctr;
@@ -857,10 +858,12 @@ static int screen_regs_for_k(int k, int override_e) {
     const int kc_est = k + std::max(16, k / 4);
     if (override_e) {
         const int e = override_e;
-        if ((e == 8 || e == 16) && 32 * e - 128 >= kc_est + 16) return e;
+        if ((e == 8 || e == 16 || e == 32) && 32 * e - 128 >= kc_est + 16) return e;
     }
-    // a list must hold k + band next to one whole tile (128 columns) of new admissions
-    return (32 * 8 - 128 >= kc_est + 32) ? 8 : 16;
+    // a list must hold k + band next to one whole tile (128 columns) of new admissions: 256 slots up to k = 76, 512 up to
+    // k = 256, 1024 up to AGP_MAX_K = 512
+    if (32 * 8 - 128 >= kc_est + 32) return 8;
+    return k <= 256 ? 16 : 32;
 }
 
 #define DISPATCH_EV(e, fn, ...)                                                                  \
@@ -868,6 +871,7 @@ static int screen_regs_for_k(int k, int override_e) {
         switch (e) {                                                                             \
             case 8: LAUNCH(fn<8>(__VA_ARGS__)); return 0;                                        \
             case 16: LAUNCH(fn<16>(__VA_ARGS__)); return 0;                                      \
+            case 32: LAUNCH(fn<32>(__VA_ARGS__)); return 0;                                      \
             default: return set_err(AGP_EINVAL, "unsupported register budget %d", e);            \
         }                                                                                        \
     }()
@@ -875,7 +879,7 @@ static int screen_regs_for_k(int k, int override_e) {
 // Single-pass certified screen on CTA pairs (knn_screen.cuh), exact finish, fp32 SIMT fallback for flagged queries.
 static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, float* D, int64_t* I) {
     const int64_t n = ix->ntotal;
-    if (k > 256 || !ix->screen || (ix->num_sms & 1)) return search_simt(ix, xq_dev, nq, k, D, I);
+    if (k > AGP_MAX_K || !ix->screen || (ix->num_sms & 1)) return search_simt(ix, xq_dev, nq, k, D, I);
     CKR(ensure_screen_plane(ix));
     const int E = screen_regs_for_k(k, ix->kn.screen_e);
     const int slots = 32 * E;
@@ -938,7 +942,11 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         p.n_items = p.n_full_items + rem_tiles * p.rem_splits;
         p.q_resident = resident;
         p.n_stages = n_stages;
-        p.sched_mul = ix->kn.screen_sched >= 5 ? ix->kn.screen_sched : 8;      // quarters: 8 = x2, 6 = x1.5
+        // compaction rounds after tiles 1, m, m^2, ... (quarters: 8 = x2, 12 = x3).  Long sweeps: doubling (a tighter bound
+        // admits less); sweeps of <= 64 tiles (small databases, heavily split remainders): x3 -- a round costs as much as
+        // ~3-5 tiles there (cfg1 0.054 -> 0.048 ms, cfg3 0.132 -> 0.127 ms; cfg2 is 10 % slower with x3)
+        const int tiles_per_item = p.n_full_items > 0 ? n_dbtiles : (n_dbtiles + p.rem_splits - 1) / p.rem_splits;
+        p.sched_mul = ix->kn.screen_sched >= 5 ? ix->kn.screen_sched : (tiles_per_item <= 64 ? 12 : 8);
         p.flags = ix->kn.screen_flags;
         p.ip = ix->ip;
         p.debug_skip_epilogue = ix->kn.skip_epi;
@@ -1314,7 +1322,7 @@ int agp_index_set_knob(agp_index* ix, const char* name, int value) {
         {"screen_flags", &ix->kn.screen_flags}, {"screen_e", &ix->kn.screen_e}, {"screen_stages", &ix->kn.screen_stages},
         {"screen_sched", &ix->kn.screen_sched}, {"tc_e", &ix->kn.tc_e}, {"tc_rerank", &ix->kn.tc_rerank},
         {"tc_compact_sort", &ix->kn.tc_compact_sort}, {"tc_share_bound", &ix->kn.tc_share_bound}, {"cycle_counters", &ix->kn.cycle_counters},
-        {"pipe_chunk", &ix->pipe_chunk}, {"screen_chunk", &ix->screen_chunk}, {"screen_lockstep", &ix->screen_lockstep},
+        {"pipe_chunk", &ix->pipe_chunk}, {"pipe_first", &ix->pipe_first}, {"screen_chunk", &ix->screen_chunk}, {"screen_lockstep", &ix->screen_lockstep},
 #ifdef AGP_DEBUG_KNOBS
         {"skip_epi", &ix->kn.skip_epi}, {"skip_mma", &ix->kn.skip_mma},
 #endif
@@ -1657,7 +1665,9 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
     const int64_t wave = static_cast<int64_t>(worker(0)->num_sms / 2) * 2 * TC_BM;      // queries one wave of pair tiles covers
     const size_t moved = (x_host ? nq * row_in : 0) + (out_host ? nq * (row_d + row_i) : 0);
     const bool batched_path = ix->ntotal > 0 && nq >= kMaxSmallNq;
-    if (ix->pipe_chunk > 0) {
+    if (ix->pipe_first > 0) {
+        if (ix->pipe_first < nq) cuts.push_back(ix->pipe_first);
+    } else if (ix->pipe_chunk > 0) {
         for (int64_t a = ix->pipe_chunk; a < nq; a += ix->pipe_chunk) cuts.push_back(a);
     } else if (batched_path && moved >= (size_t(4) << 20)) {
         if (nq >= 3 * wave) {
@@ -1928,30 +1938,9 @@ int agp_index_search_masked(agp_index* ix, int64_t nq, const float* x, int x_mem
     // Ids in this call are POSITIONS in the index (the exclusion lists are): the shard base is not applied.
     const int64_t saved_base = ix->id_base;
     ix->id_base = 0;
-    int rc_search;
-    if (kp > 256 && nq >= kMaxSmallNq && ix->ntotal > 0) {
-        // Beyond the tensor-core screen's 256 results the batch is answered by the fp32 FMA tiles in the EXPANSION form
-        // (|q|^2 + |y|^2 - 2 q.y), whose distances -- and therefore near-tie order -- differ from the difference form every
-        // other path of this call returns.  Fetch a margin of extra candidates and re-rank all of them in the exact fp32
-        // difference form (merge.cuh:rerank), so D and the (distance, id) order are path-independent.
-        const int kc = static_cast<int>(std::min<int64_t>({static_cast<int64_t>(kp) + 16, int64_t(AGP_MAX_K), std::max<int64_t>(ix->ntotal, kp)}));
-        const float* xq_dev = x;
-        rc_search = 0;
-        if (x_mem_kind != AGP_MEM_DEVICE) {
-            rc_search = ensure(ix->q_raw, static_cast<size_t>(nq) * ix->d * sizeof(float));
-            if (rc_search == 0) rc_search = copy_h2d(ix, ix->q_raw.p, x, static_cast<size_t>(nq) * ix->d * sizeof(float));
-            xq_dev = static_cast<const float*>(ix->q_raw.p);
-        }
-        if (rc_search == 0) rc_search = ensure(ix->cand_d, static_cast<size_t>(nq) * kc * sizeof(float));
-        if (rc_search == 0) rc_search = ensure(ix->cand_i, static_cast<size_t>(nq) * kc * sizeof(int64_t));
-        if (rc_search == 0)
-            rc_search = search_simt(ix, xq_dev, nq, kc, static_cast<float*>(ix->cand_d.p), static_cast<int64_t*>(ix->cand_i.p));
-        if (rc_search == 0)
-            rc_search = DISPATCH_E32(kc, launch_rerank, xq_dev, ix->xb, ix->d, static_cast<const int64_t*>(ix->cand_i.p), kc, nq, kp,
-                                     static_cast<int64_t>(0), static_cast<float*>(ix->mk_d.p), static_cast<int64_t*>(ix->mk_i.p), ix->stream);
-    } else {
-        rc_search = agp_index_search(ix, nq, x, x_mem_kind, kp, static_cast<float*>(ix->mk_d.p), static_cast<int64_t*>(ix->mk_i.p), AGP_MEM_DEVICE);
-    }
+    // (every k + |exclusions| <= 512 is answered by the same path as a plain search: tensor-core screen + exact fp32
+    // difference-form finish for batches, difference form for nq < 20 -- D and the tie order do not depend on the list lengths)
+    const int rc_search = agp_index_search(ix, nq, x, x_mem_kind, kp, static_cast<float*>(ix->mk_d.p), static_cast<int64_t*>(ix->mk_i.p), AGP_MEM_DEVICE);
     ix->id_base = saved_base;
     CKR(rc_search);
     float* D_dev = D;

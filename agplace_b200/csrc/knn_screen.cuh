@@ -906,6 +906,10 @@ cudaError_t launch_screen_finalize(const uint64_t* partial, const int* pcount, i
     constexpr int warps = 4;
     if (2 * rem_splits > kMaxRaggedLists) return cudaErrorInvalidValue;
     const size_t smem = warps * 32 * E * (sizeof(uint64_t) + sizeof(float)) + warps * (kMaxRaggedLists + 1) * sizeof(int);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(screen_finalize_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+    }
     screen_finalize_kernel<E><<<static_cast<unsigned>((nq + warps - 1) / warps), warps * 32, smem, st>>>(
         partial, pcount, slot_stride, nq, n_full_items, rem_splits, k, xq, xb, d, d_pad, qn, dq, dbstats, ovf_in, ovf_count, ovf_list, id_base, D, I, ip);
     return cudaGetLastError();

@@ -17,7 +17,7 @@ import agplace_b200 as agp
 from agplace_b200 import synth
 
 
-def probe(name, counters, pipe, reps):
+def probe(name, counters, pipe, reps, sched=(), first_cuts=()):
     c = dict(synth.CONFIGS[name])
     n, nq, d, k = c["n"], c["nq"], c["d"], c["k"]
     xb = synth.descriptors(n, d, c["seed"], "db")
@@ -47,6 +47,21 @@ def probe(name, counters, pipe, reps):
     kms = ph["distance"][0] / max(ph["distance"][1], 1) * (ph["distance"][1] / reps)
     out = dict(cfg=name, step_ms=round(step, 4), kernel_ms=round(kms, 4), tflops=round(2.0 * nq * n * d / (kms * 1e-3) / 1e12, 1),
                phases_ms={p: round(v[0] / reps, 4) for p, v in ph.items()}, kernel_share=round(kms / step, 3))
+    if sched:
+        sw = {}
+        for m in sched:
+            ix.set_knob("screen_sched", m)
+            for _ in range(3):
+                ix.search(xq_d, k)
+            torch.cuda.synchronize()
+            ix.set_profiling(True); ix.get_profile_phases(reset=True)
+            for _ in range(reps):
+                ix.search(xq_d, k)
+            torch.cuda.synchronize()
+            p2 = ix.get_profile_phases(reset=True); ix.set_profiling(False)
+            sw[str(m)] = round(p2["distance"][0] / reps, 4)
+        ix.set_knob("screen_sched", 0)
+        out["kernel_ms_by_sched_quarters"] = sw
     e2e = {}
     for chunk in pipe:
         ix.set_knob("pipe_chunk", chunk)
@@ -60,6 +75,20 @@ def probe(name, counters, pipe, reps):
         e2e[str(chunk)] = round((time.perf_counter() - t0) / reps * 1e3, 4)
     ix.set_knob("pipe_chunk", 0)
     out["numpy_e2e_ms_by_pipe_chunk"] = e2e
+    e2f = {}
+    for first in first_cuts:
+        ix.set_knob("pipe_first", first)
+        for _ in range(3):
+            ix.search(xq, k)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ix.search(xq, k)
+        torch.cuda.synchronize()
+        e2f[str(first)] = round((time.perf_counter() - t0) / reps * 1e3, 4)
+    ix.set_knob("pipe_first", 0)
+    if e2f:
+        out["numpy_e2e_ms_by_first_chunk"] = e2f
     # where the host path spends its time: pinned in / pinned preallocated out (pure pipeline), pageable in + reused
     # pageable out (no page faults on the results), and the default call (fresh numpy results)
     xp = torch.from_numpy(xq).pin_memory().numpy()
@@ -96,6 +125,8 @@ if __name__ == "__main__":
     ap.add_argument("--counters", action="store_true")
     ap.add_argument("--pipe", default="0")
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--sched", default="")
+    ap.add_argument("--first", default="")
     a = ap.parse_args()
     for name in a.cfgs:
-        probe(name, a.counters, [int(x) for x in a.pipe.split(",")], a.reps)
+        probe(name, a.counters, [int(x) for x in a.pipe.split(",")], a.reps, [int(x) for x in a.sched.split(",") if x], [int(x) for x in a.first.split(",") if x])

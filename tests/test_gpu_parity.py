@@ -50,6 +50,7 @@ SHAPES = [  # nq, n, d, k
     (1, 1, 1, 1), (1, 1000, 256, 10), (1, 37, 256, 1), (3, 5, 3, 8), (19, 999, 64, 20), (20, 999, 64, 20),
     (127, 255, 8, 5), (128, 256, 32, 32), (129, 257, 33, 33), (300, 5000, 255, 50), (257, 4097, 512, 100),
     (64, 1500, 100, 256), (50, 3000, 16, 257), (40, 700, 24, 512), (1000, 130, 48, 20), (21, 70000, 32, 10),
+    (300, 20000, 64, 400), (257, 9000, 128, 512),      # 256 < k <= 512: the 1024-slot instantiation of the screen kernel
 ]
 
 
