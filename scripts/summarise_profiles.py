@@ -18,7 +18,7 @@ if src.exists():
         if r["Metric Name"] == "gpu__time_duration.sum":
             agg[r["Kernel Name"]].append(float(r["Metric Value"]) / 1e3)
     total = sum(sum(v) for v in agg.values())
-    text = [f"ncu --metrics gpu__time_duration.sum --clock-control none -c 600, python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-verify "
+    text = [f"ncu --metrics gpu__time_duration.sum --clock-control none -k regex:<the library's kernels> -c 400, python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-verify "
             f"(cfg4 then cfg2 in one process, 1 GPU); per-launch times are cold-cache and serialised: compare SHARES. {len(rows)} launches, {total / 1e3:.1f} ms"]
     for name, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         text.append(f"{name[:110]:110s} n={len(v):4d} mean={sum(v) / len(v):12.1f} us share={100 * sum(v) / total:5.1f}%")
