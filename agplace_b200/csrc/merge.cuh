@@ -68,18 +68,63 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
                                                           const int64_t* __restrict__ Iin, int64_t i_stride, bool by_id,
                                                           int64_t nq, int n_lists, int k, float* __restrict__ D,
                                                           int64_t* __restrict__ I, int ip) {
-    const int lane = threadIdx.x & 31;
-    const int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    constexpr int CAP = 32 * E;
+    extern __shared__ uint64_t mstage[];      // [warps][CAP]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
     if (q >= nq) return;
-    uint64_t key[E];
-    warp_select_stream<E>(key, lane, k, static_cast<int64_t>(n_lists) * k, [&](int64_t i) {
+    uint64_t* buf = mstage + warp * CAP;
+    auto fetch = [&](int64_t i) -> uint64_t {
         const int64_t g = i / k, r = i - g * k;
         const int64_t id = Iin[g * i_stride + q * k + r];
         if (id < 0) return kEmptyKey;
         // inner-product lists hold products, best = largest: order by -<q, y> through the sign-aware key
         const uint32_t payload = by_id ? static_cast<uint32_t>(id) : static_cast<uint32_t>(i);
         return ip ? pack_key_signed(-Din[g * d_stride + q * k + r], payload) : pack_key(Din[g * d_stride + q * k + r], payload);
-    });
+    };
+    const int64_t total = static_cast<int64_t>(n_lists) * k;
+    uint64_t key[E];
+    bool done = false;
+    // Every list is sorted, so the entry at rank ceil(k / G) - 1 of each list bounds the merged k-th entry from above:
+    // if every list holds that many entries at or below T = max over lists of that entry, the union holds >= k.  Only
+    // entries <= T can appear in the result: on shards of similar content that is ~k (not G k) keys -- one sort instead of
+    // ceil(G k / (CAP - k)) of them.  (A list padded before that rank, or more survivors than slots: the general path.)
+    if (n_lists > 1 && total > CAP) {
+        const int kk = (k + n_lists - 1) / n_lists;
+        uint64_t t = 0;
+        for (int g = lane; g < n_lists; g += 32) {
+            const uint64_t e = fetch(static_cast<int64_t>(g) * k + kk - 1);
+            t = e > t ? e : t;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint64_t v = __shfl_xor_sync(kFull, t, o);
+            t = v > t ? v : t;
+        }
+        if (t != kEmptyKey) {
+            const uint64_t bound = t | 0xffffffffull;      // every payload of that distance survives
+            int fill = 0;
+            bool fits = true;
+            for (int64_t base = 0; base < total; base += 32) {
+                const int64_t i = base + lane;
+                const uint64_t e = i < total ? fetch(i) : kEmptyKey;
+                const bool keep = e <= bound && e != kEmptyKey;
+                const unsigned m = __ballot_sync(kFull, keep);
+                const int pos = fill + __popc(m & ((1u << lane) - 1u));
+                if (keep && pos < CAP) buf[pos] = e;
+                fill += __popc(m);
+                if (fill > CAP) { fits = false; break; }
+            }
+            if (fits) {
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < E; ++j) key[j] = (j * 32 + lane < fill) ? buf[j * 32 + lane] : kEmptyKey;
+                warp_bitonic_sort<E>(key, lane);
+                done = true;
+            }
+        }
+    }
+    if (!done) warp_select_stream<E>(key, lane, k, total, fetch);
 #pragma unroll
     for (int j = 0; j < E; ++j) {
         const int i = j * 32 + lane;
@@ -108,8 +153,13 @@ template <int E>
 cudaError_t launch_merge_lists(const float* Din, int64_t d_stride, const int64_t* Iin, int64_t i_stride, bool by_id, int64_t nq,
                                int n_lists, int k, float* D, int64_t* I, int ip, cudaStream_t st) {
     constexpr int warps = 4;
-    merge_lists_kernel<E><<<static_cast<unsigned>((nq + warps - 1) / warps), warps * 32, 0, st>>>(Din, d_stride, Iin, i_stride, by_id, nq,
-                                                                                                  n_lists, k, D, I, ip);
+    const size_t smem = static_cast<size_t>(warps) * 32 * E * sizeof(uint64_t);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(merge_lists_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+    }
+    merge_lists_kernel<E><<<static_cast<unsigned>((nq + warps - 1) / warps), warps * 32, smem, st>>>(Din, d_stride, Iin, i_stride, by_id, nq,
+                                                                                                     n_lists, k, D, I, ip);
     return cudaGetLastError();
 }
 

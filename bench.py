@@ -193,7 +193,12 @@ def run_reference(args):
         sample_q = 4096
     sample = xq[:sample_q]
     for _ in range(max(1, min(args.warmup, 2))):
+        t0 = time.perf_counter()
         orc.knn_fp32(sample, xb, c["k"])
+        t_warm = time.perf_counter() - t0
+        if t_warm > 1.25 * per_step_s and sample_q > 256:      # the probe overstated the rate: shrink the sample to the budget
+            sample_q = max(256, int(sample_q * per_step_s / t_warm))
+            sample = xq[:sample_q]
     t0 = time.perf_counter()
     for _ in range(args.steps):
         orc.knn_fp32(sample, xb, c["k"])
