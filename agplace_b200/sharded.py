@@ -24,15 +24,18 @@ from . import _lib
 from .index import METRIC_INNER_PRODUCT, METRIC_L2, IndexFlatIP, IndexFlatL2, _is_torch
 
 
-def _cuda_merge(D_lists, d_stride, I_lists, i_stride, nq, k, n_lists, id_bound, metric=METRIC_L2):
+def _cuda_merge(D_lists, d_stride, I_lists, i_stride, nq, k, n_lists, id_bound, metric=METRIC_L2, out=None):
     """K4 across shards on the GPU through the C ABI (device tensors in, device tensors out)."""
     import torch
     if not D_lists.is_cuda:
         raise RuntimeError("agplace_b200 has no CPU merge: per-shard lists must be CUDA tensors "
                            "(tests inject a merge_fn for the gloo/CPU host-logic checks)")
     dev = D_lists.device
-    D = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    I = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    if out is not None:
+        D, I = out
+    else:
+        D = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        I = torch.empty((nq, k), dtype=torch.int64, device=dev)
     lib = _lib.load()
     stream = torch.cuda.current_stream(dev).cuda_stream
     _lib.check(lib.agp_merge_topk_metric(dev.index, ctypes.c_void_p(stream), nq, k, n_lists, ctypes.c_void_p(D_lists.data_ptr()),
@@ -45,6 +48,51 @@ def shard_bounds(n, world):
     """Contiguous row ranges: shard g holds [g*ceil(n/G), min((g+1)*ceil(n/G), n))."""
     per = -(-n // world) if n else 0
     return [(min(g * per, n), min((g + 1) * per, n)) for g in range(world)]
+
+
+class _PeerExchange:
+    """The exchange step over NVLink peer memory instead of an NCCL kernel: every rank owns a symmetric buffer
+    ``[2 slots][world][list bytes]`` (torch symmetric memory: the same allocation mapped into every rank's address
+    space); a rank PUSHES its packed per-shard lists into slot ``s``, row ``rank`` of every peer's buffer with plain
+    device-to-device copies (copy engines: no SMs, so the pushes of query chunk c run while the persistent screen kernel
+    of chunk c + 1 owns every SM), then a signal barrier makes the arrivals visible and the local K4 kernel merges the
+    ``world`` lists.  Two slots and one barrier per chunk are enough: a peer can only overwrite slot ``s`` after it has
+    passed the barrier of the chunk in between, which this rank enters after its merge of slot ``s``."""
+
+    def __init__(self, group, device, list_bytes):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.list_bytes = int(list_bytes)
+        g = group if group is not None else dist.group.WORLD
+        try:
+            symm_mem.enable_symm_mem_for_group(g.group_name)      # needed by older torch releases, a no-op / deprecated later
+        except Exception:                                          # noqa: BLE001
+            pass
+        self.buf = symm_mem.empty(2 * self.world * self.list_bytes, dtype=torch.uint8, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, g.group_name)
+        self.peers = [self.hdl.get_buffer(p, (2, self.world, self.list_bytes), torch.uint8) for p in range(self.world)]
+        self.n = 0
+
+    def exchange(self, D_loc, I_loc):
+        """Push (D fp32 [m, k] | I int64 [m, k]) to every rank; returns (slot view [world, list_bytes], d_bytes)."""
+        import torch
+        m_k = D_loc.numel()
+        d_bytes = (m_k * 4 + 7) // 8 * 8
+        assert d_bytes + m_k * 8 <= self.list_bytes
+        s = self.n & 1
+        self.n += 1
+        Db = D_loc.reshape(-1).view(torch.uint8)
+        Ib = I_loc.reshape(-1).view(torch.uint8)
+        for off in range(self.world):                      # start with myself, then the ring: spreads the link load
+            p = (self.rank + off) % self.world
+            row = self.peers[p][s, self.rank]
+            row[: m_k * 4].copy_(Db, non_blocking=True)
+            row[d_bytes: d_bytes + m_k * 8].copy_(Ib, non_blocking=True)
+        self.hdl.barrier(channel=s)
+        return self.peers[self.rank][s], d_bytes
 
 
 class ShardedIndexFlatL2:
@@ -187,9 +235,11 @@ class ShardedIndexFlatL2:
         base_applied = self._engine_applies_base()
         if hasattr(self.local, "set_id_base"):
             self.local.set_id_base(self._chunks[0][1] if base_applied else 0)
-        if (self.shard == "db" and as_numpy and isinstance(self.local, IndexFlatL2) and D is None and I is None
-                and nq * d * 4 >= self.PIPELINE_MIN_BYTES and torch.cuda.is_available()):
+        native = self.shard == "db" and isinstance(self.local, IndexFlatL2) and self._merge is _cuda_merge and torch.cuda.is_available()
+        if native and as_numpy and D is None and I is None and nq * d * 4 >= self.PIPELINE_MIN_BYTES:
             return self._search_host_pipelined(np.ascontiguousarray(x, dtype=np.float32), k, base_applied)
+        if native and _is_torch(x) and x.is_cuda and D is None and I is None and nq > self.PIPELINE_CHUNK + self.PIPELINE_CHUNK // 4:
+            return self._search_device_chunked(x, k, base_applied)
         if isinstance(self.local, IndexFlatL2) and not (_is_torch(xs) and xs.is_cuda) and xs.shape[0]:
             # host queries: one H2D copy, then everything (search, exchange, merge) stays on the GPU
             xh = xs if _is_torch(xs) else torch.from_numpy(np.ascontiguousarray(xs, dtype=np.float32))
@@ -263,11 +313,46 @@ class ShardedIndexFlatL2:
     PIPELINE_MIN_BYTES = 16 << 20
     PIPELINE_CHUNK = 18944           # queries per chunk: one wave of 256-query pair tiles on a 148-SM B200
 
-    def _exchange_and_merge(self, D_loc, I_loc, nq, k):
-        """The one exchange step: pack this shard's lists, all-gather, K4 merge (ties by global id)."""
+    USE_PEER_MEMORY = True           # exchange through symmetric peer memory (copy engines); False / unavailable: NCCL all-gather
+
+    def _peer_exchange(self, dev, list_bytes):
+        """The symmetric-memory exchange object, (re)built collectively when a larger list size is needed; None if this
+        torch build / topology cannot provide it (every rank takes the same decision: allocation is all-or-nothing)."""
+        import torch
+        import torch.distributed as dist
+        if not self.USE_PEER_MEMORY:
+            return None
+        ex = getattr(self, "_peer", None)
+        if ex is not None and ex is not False and ex.list_bytes >= list_bytes:
+            return ex
+        if ex is False:
+            return None
+        ok = torch.ones(1, device=dev)
+        try:
+            new = _PeerExchange(self.group, dev, list_bytes)
+        except Exception:                                   # noqa: BLE001 -- any failure means "not available here"
+            new = None
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if ok.item() < 1:
+            self._peer = False
+            return None
+        self._peer = new
+        return new
+
+    def _exchange_and_merge(self, D_loc, I_loc, nq, k, out=None):
+        """The one exchange step: this shard's lists go to every rank, K4 merge (ties by global id)."""
         import torch
         import torch.distributed as dist
         dev = D_loc.device
+        ex = self._peer_exchange(dev, getattr(self, "_peer_list_bytes", 0) or ((nq * k * 4 + 7) // 8 * 8 + nq * k * 8))
+        if ex is not None:
+            with self._phase("exchange_peer_memory"):
+                slot, d_bytes = ex.exchange(D_loc, I_loc)
+            with self._phase("merge"):
+                stride = ex.list_bytes
+                args = (slot.view(torch.float32), stride // 4, slot.view(torch.int64)[d_bytes // 8:], stride // 8, nq, k, self.world, self._ntotal)
+                return _cuda_merge(*args, self._metric, out=out)
         d_bytes = (nq * k * 4 + 7) // 8 * 8
         i_bytes = nq * k * 8
         with self._phase("pack"):
@@ -280,7 +365,40 @@ class ShardedIndexFlatL2:
         stride = d_bytes + i_bytes
         with self._phase("merge"):
             args = (recv.view(torch.float32), stride // 4, recv.view(torch.int64)[d_bytes // 8:], stride // 8, nq, k, self.world, self._ntotal)
+            if out is not None and self._merge is _cuda_merge:
+                return _cuda_merge(*args, self._metric, out=out)
             return self._merge(*args) if self._metric == METRIC_L2 else self._merge(*args, self._metric)
+
+    def _search_device_chunked(self, x, k, base_applied):
+        """CUDA queries in, CUDA results out, one wave of query tiles at a time: while the (persistent, SM-filling) screen
+        kernel of chunk c + 1 runs on the main stream, the lists of chunk c travel through peer memory on a second
+        stream; only the last chunk's exchange + merge is exposed."""
+        import torch
+        nq = x.shape[0]
+        dev = x.device
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_s_comm"):
+            self._s_comm = torch.cuda.Stream(dev)
+        comm = self._s_comm
+        x = x.detach().to(torch.float32).contiguous()
+        D = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        I = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        chunk = self.PIPELINE_CHUNK
+        self._peer_list_bytes = (chunk * k * 4 + 7) // 8 * 8 + chunk * k * 8      # one buffer size for every chunk
+        comm.wait_stream(main)
+        for a in range(0, nq, chunk):
+            b = min(nq, a + chunk)
+            with self._phase("local_search"):
+                D_loc, I_loc = self.local.search(x[a:b], k)
+            I_loc = self._to_global(I_loc, base_applied)
+            ev = torch.cuda.Event(); ev.record(main)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev)
+                self._exchange_and_merge(D_loc, I_loc, b - a, k, out=(D[a:b], I[a:b]))
+            D_loc.record_stream(comm); I_loc.record_stream(comm)
+        main.wait_stream(comm)
+        self._peer_list_bytes = 0
+        return D, I
 
     def _search_host_pipelined(self, x, k, base_applied):
         """numpy in / numpy out on every rank, as a pipeline over query chunks: host copy into a pinned buffer + H2D
@@ -304,6 +422,8 @@ class ShardedIndexFlatL2:
         xq_dev = torch.empty((nq, self.d), dtype=torch.float32, device=dev)
         stage_ev = [None, None]
         pending = []
+        self._peer_list_bytes = (chunk * k * 4 + 7) // 8 * 8 + chunk * k * 8
+        self._s_out.wait_stream(main)
         self._s_in.wait_stream(main)                        # xq_dev's block may still be in use by work queued on main
         for c in range(len(cuts) - 1):
             a, b = cuts[c], cuts[c + 1]
@@ -321,15 +441,16 @@ class ShardedIndexFlatL2:
             with self._phase("local_search"):
                 D_loc, I_loc = self.local.search(xq_dev[a:b], k)
             I_loc = self._to_global(I_loc, base_applied)
-            Dg, Ig = self._exchange_and_merge(D_loc, I_loc, b - a, k)
-            ev_done = torch.cuda.Event(); ev_done.record(main)
-            with torch.cuda.stream(self._s_out):
-                self._s_out.wait_event(ev_done)
+            ev = torch.cuda.Event(); ev.record(main)
+            with torch.cuda.stream(self._s_out):        # exchange (peer copies) + merge + D2H run beside the next chunk's search
+                self._s_out.wait_event(ev)
+                Dg, Ig = self._exchange_and_merge(D_loc, I_loc, b - a, k)
                 Dt[a:b].copy_(Dg, non_blocking=pinned_out)
                 It[a:b].copy_(Ig, non_blocking=pinned_out)
-            Dg.record_stream(self._s_out); Ig.record_stream(self._s_out)
+            D_loc.record_stream(self._s_out); I_loc.record_stream(self._s_out)
             pending.append((Dg, Ig))
         self._s_out.synchronize()
+        self._peer_list_bytes = 0
         xq_dev.record_stream(self._s_in)
         return D, I
 

@@ -39,6 +39,9 @@ def _worker(rank, world, port, shard, out_dir, metric="l2"):
             ix.PIPELINE_MIN_BYTES, ix.PIPELINE_CHUNK = 0, 300
             D3, I3 = ix.search(xq, 40)
             assert np.array_equal(D3, D) and np.array_equal(I3, I)
+            D4, I4 = ix.search(torch.from_numpy(xq).cuda(), 40)   # CUDA in, chunked: exchange through peer memory on a second stream
+            assert np.array_equal(D4.cpu().numpy(), D) and np.array_equal(I4.cpu().numpy(), I)
+            extra["peer_memory"] = np.array([0 if getattr(ix, "_peer", None) in (None, False) else 1])
         if shard == "query":                                       # results left partitioned by query: this rank's slice only
             Dl, Il = ix.search(xq, 40, gather=False)
             extra = dict(Dl=Dl, Il=Il)
@@ -69,6 +72,8 @@ def test_nccl_sharded_equals_single(tmp_path, shard):
         np.testing.assert_array_equal(got["D"], Ds)
         np.testing.assert_array_equal(got["I2"], Is2)
         np.testing.assert_array_equal(got["D2"], Ds2)
+        if shard == "db" and "peer_memory" in got.files:
+            print("peer-memory exchange used on rank", r, ":", bool(got["peer_memory"][0]))
         if shard == "query":
             from agplace_b200.sharded import shard_bounds
             a, b = shard_bounds(len(xq), world)[r]
