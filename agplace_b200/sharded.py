@@ -65,7 +65,7 @@ class _PeerExchange:
         import torch.distributed._symmetric_memory as symm_mem
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.list_bytes = int(list_bytes)
+        self.list_bytes = (int(list_bytes) + 15) // 16 * 16
         g = group if group is not None else dist.group.WORLD
         try:
             symm_mem.enable_symm_mem_for_group(g.group_name)      # needed by older torch releases, a no-op / deprecated later
@@ -92,7 +92,7 @@ class _PeerExchange:
             row[: m_k * 4].copy_(Db, non_blocking=True)
             row[d_bytes: d_bytes + m_k * 8].copy_(Ib, non_blocking=True)
         self.hdl.barrier(channel=s)
-        return self.peers[self.rank][s], d_bytes
+        return self.buf.view(2, self.world, self.list_bytes)[s], d_bytes
 
 
 class ShardedIndexFlatL2:
@@ -351,7 +351,8 @@ class ShardedIndexFlatL2:
                 slot, d_bytes = ex.exchange(D_loc, I_loc)
             with self._phase("merge"):
                 stride = ex.list_bytes
-                args = (slot.view(torch.float32), stride // 4, slot.view(torch.int64)[d_bytes // 8:], stride // 8, nq, k, self.world, self._ntotal)
+                flat = slot.reshape(-1)                   # [world * list_bytes]: list g starts at g * stride bytes
+                args = (flat.view(torch.float32), stride // 4, flat.view(torch.int64)[d_bytes // 8:], stride // 8, nq, k, self.world, self._ntotal)
                 return _cuda_merge(*args, self._metric, out=out)
         d_bytes = (nq * k * 4 + 7) // 8 * 8
         i_bytes = nq * k * 8
