@@ -67,10 +67,6 @@ class _PeerExchange:
         self.rank = dist.get_rank(group)
         self.list_bytes = (int(list_bytes) + 15) // 16 * 16
         g = group if group is not None else dist.group.WORLD
-        try:
-            symm_mem.enable_symm_mem_for_group(g.group_name)      # needed by older torch releases, a no-op / deprecated later
-        except Exception:                                          # noqa: BLE001
-            pass
         self.buf = symm_mem.empty(2 * self.world * self.list_bytes, dtype=torch.uint8, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, g.group_name)
         self.peers = [self.hdl.get_buffer(p, (2, self.world, self.list_bytes), torch.uint8) for p in range(self.world)]

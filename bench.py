@@ -536,7 +536,8 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": f"{c['name']}: {c['desc']}", "n": n, "nq": nq, "d": d, "k": k, "precision": PRECISION_DESC,
                    "sharding": (f"database row-sharded over {world} ranks ({n_local} rows on rank 0), queries replicated, per-shard top-k lists "
-                                f"exchanged with one NCCL all-gather per search + merge on every rank; strong scaling (total work fixed)"
+                                f"exchanged once per query chunk (one wave of query tiles) through symmetric peer memory over NVLink -- copy-engine pushes + signal barrier on a second stream, "
+                                f"overlapped with the next chunk's search; NCCL all-gather is the fallback -- + K4 merge on every rank; strong scaling (total work fixed)"
                                 if shard_mode == "db" else
                                 f"database replicated on {world} ranks, queries split across ranks, results stay partitioned by query (no data-path collective); "
                                 + (f"weak scaling: {world} x {nq_rank} queries per step" if weak else f"strong scaling: {nq} queries per step in total")),
@@ -549,7 +550,11 @@ def run_ours(args):
                 "call": "ShardedIndexFlatL2.search(pageable numpy, k) -> numpy on every rank"},
         "gpu_launches": int(launches * world),
         "roofline": roofline_of(c, n_local, nq_local, steps, phases, ms, clocks, peaks),
-        "phases_ms_per_step": {"rank0": ph, "max_over_ranks": ph_max},
+        "phases_ms_per_step": {"rank0": ph, "max_over_ranks": ph_max,
+                               "note": "distance / prep / finish / fallback: CUDA events around the kernels of the local search; exchange_peer_memory / merge: "
+                                       "spans on the SECOND stream (copy-engine pushes into the peers' symmetric buffers + signal barrier, then the K4 merge kernel) -- "
+                                       "they run beside the next query chunk's search and include the time they wait for it, so they do not add up to the step; "
+                                       "step - local_search = the exposed part"},
         "clocks": clocks,
         "rank_spread": spread_device,
     }
