@@ -427,7 +427,8 @@ class ShardedIndexFlatL2:
             self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
             self._stage = [None, None]
         chunk = self.PIPELINE_CHUNK
-        cuts = list(range(0, nq, chunk)) + [nq]
+        first = max(256, chunk // 4)                    # a short first chunk: the GPU starts after a quarter-wave of host copy
+        cuts = [0] + list(range(first, nq, chunk)) + [nq] if nq > first + chunk // 2 else [0, nq]
         D = _result_array((nq, k), np.float32)
         I = _result_array((nq, k), np.int64)
         Dt, It = torch.from_numpy(D), torch.from_numpy(I)
