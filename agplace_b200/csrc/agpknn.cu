@@ -1580,15 +1580,7 @@ static int search_device(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
     }
 }
 
-// Host-buffer search as a three-stage pipeline (what the reference's call hands over: numpy arrays in, numpy arrays
-// out -- test.py:32).  The query batch is cut into chunks; for chunk c
-//     host memcpy into a pinned ring + H2D   (stream s_in)
-//  -> prep / screen / finish / fallback      (the index's stream, after the chunk's H2D event)
-//  -> D2H of (D, I) into a pinned slot       (stream s_out, after the chunk's compute event) + host memcpy out
-// run concurrently for chunks c + 1, c and c - 1.  No stage needs a host synchronisation of the compute stream (the
-// screen's overflow fallback is device-side), so the host thread only ever blocks on a staging slot or a finished chunk.
-// Chunks are whole waves of pair tiles (74 x 256 queries on B200) when the batch is large; a mid-sized batch is cut
-// unevenly (small first chunk: the GPU starts early; large later chunks: the kernel stays efficient).
+// lazily created, reusable events of one index's pipeline (index i of the call's event schedule)
 static int pipe_event(agp_index* ix, size_t i, cudaEvent_t* out) {
     while (ix->pipe_ev.size() <= i) {
         cudaEvent_t e = nullptr;
@@ -1599,22 +1591,19 @@ static int pipe_event(agp_index* ix, size_t i, cudaEvent_t* out) {
     return 0;
 }
 
-// One query chunk on a multi-device index: every shard searches the chunk on its own device and stream (nothing waits
-// on the host), maps its local rows to global ids, pushes its (D, I) lists to the home device over NVLink
-// (cudaMemcpyPeerAsync), and the home device merges the G lists with ties by global id -- the same K4 kernel the
-// NCCL path uses.  xq[g] = the chunk's queries on shard g's device.
-static int multi_compute_chunk(agp_index* ix, const std::vector<const float*>& xq, int64_t m, int k, float* D_home, int64_t* I_home) {
+// Multi-device index, one query chunk [a, a + m) of a batch of nq: every shard searches the chunk on its own device and
+// stream (nothing waits on the host), maps its local rows to global ids and pushes its (D, I) rows into ITS list of the home
+// device's gather buffer ([G][nq k], rows a.. of list g) over NVLink with cudaMemcpyPeerAsync -- copy engines, so the
+// transfer of chunk c runs beside the screen kernel of chunk c + 1.  multi_merge() then merges the G lists of the whole
+// batch with ONE launch of the K4 kernel (ties by global id).  (A merge per chunk was measured slower on the NCCL path:
+// a kernel queued between two screen launches delays the next launch's CTA pairs.)  xq[g] = the chunk's queries on
+// shard g's device.
+static int multi_search_chunk(agp_index* ix, const std::vector<const float*>& xq, int64_t nq, int64_t a, int64_t m, int k) {
     const int G = static_cast<int>(ix->shards.size());
-    const size_t list = static_cast<size_t>(m) * k;
-    ENTER(ix);
-    CKR(ensure(ix->gat_d, G * list * sizeof(float)));
-    CKR(ensure(ix->gat_i, G * list * sizeof(int64_t)));
-    if (!ix->ev_home) CK(cudaEventCreateWithFlags(&ix->ev_home, cudaEventDisableTiming));
-    CK(cudaEventRecord(ix->ev_home, ix->stream));      // the gather buffers are free once the previous chunk's merge has run
+    const size_t list = static_cast<size_t>(m) * k, whole = static_cast<size_t>(nq) * k;
     for (int g = 0; g < G; ++g) {
         agp_index* ch = ix->shards[g];
         ENTER(ch);
-        CK(cudaStreamWaitEvent(ch->stream, ix->ev_home, 0));
         CKR(ensure(ch->d_out, list * sizeof(float)));
         CKR(ensure(ch->i_out, list * sizeof(int64_t)));
         const auto& tab = ix->shard_chunks[g];
@@ -1631,15 +1620,22 @@ static int multi_compute_chunk(agp_index* ix, const std::vector<const float*>& x
             LAUNCH(launch_remap_ids(static_cast<int64_t*>(ch->i_out.p), static_cast<int64_t>(list),
                                     static_cast<const int64_t*>(ix->shard_tab[g].p), static_cast<int>(tab.size()), ix->id_base, ch->stream));
         }
-        CK(cudaMemcpyPeerAsync(static_cast<float*>(ix->gat_d.p) + g * list, ix->device, ch->d_out.p, ch->device, list * sizeof(float), ch->stream));
-        CK(cudaMemcpyPeerAsync(static_cast<int64_t*>(ix->gat_i.p) + g * list, ix->device, ch->i_out.p, ch->device, list * sizeof(int64_t), ch->stream));
+        CK(cudaMemcpyPeerAsync(static_cast<float*>(ix->gat_d.p) + g * whole + a * k, ix->device, ch->d_out.p, ch->device, list * sizeof(float), ch->stream));
+        CK(cudaMemcpyPeerAsync(static_cast<int64_t*>(ix->gat_i.p) + g * whole + a * k, ix->device, ch->i_out.p, ch->device, list * sizeof(int64_t), ch->stream));
         CK(cudaEventRecord(ix->shard_ev[g], ch->stream));
     }
     ENTER(ix);
-    for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(ix->stream, ix->shard_ev[g], 0));
+    return 0;
+}
+
+static int multi_merge(agp_index* ix, int64_t nq, int k, float* D_home, int64_t* I_home) {
+    const int G = static_cast<int>(ix->shards.size());
+    const size_t whole = static_cast<size_t>(nq) * k;
+    ENTER(ix);
+    for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(ix->stream, ix->shard_ev[g], 0));      // recorded after each shard's LAST chunk
     const bool by_id = ix->ntotal + ix->id_base <= 0x100000000LL;
-    return DISPATCH_E32(k, launch_merge_lists, static_cast<const float*>(ix->gat_d.p), static_cast<int64_t>(list),
-                        static_cast<const int64_t*>(ix->gat_i.p), static_cast<int64_t>(list), by_id, m, G, k, D_home, I_home, ix->ip, ix->stream);
+    return DISPATCH_E32(k, launch_merge_lists, static_cast<const float*>(ix->gat_d.p), static_cast<int64_t>(whole),
+                        static_cast<const int64_t*>(ix->gat_i.p), static_cast<int64_t>(whole), by_id, nq, G, k, D_home, I_home, ix->ip, ix->stream);
 }
 
 // Host-buffer search as a three-stage pipeline (what the reference's call hands over: numpy arrays in, numpy arrays
@@ -1669,7 +1665,7 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
         if (ix->pipe_first < nq) cuts.push_back(ix->pipe_first);
     } else if (ix->pipe_chunk > 0) {
         for (int64_t a = ix->pipe_chunk; a < nq; a += ix->pipe_chunk) cuts.push_back(a);
-    } else if (batched_path && moved >= (size_t(4) << 20)) {
+    } else if (batched_path && (moved >= (size_t(4) << 20) || multi)) {
         if (nq >= 3 * wave) {
             for (int64_t a = wave; a < nq; a += wave) cuts.push_back(a);
         } else if (nq >= 2048) {
@@ -1708,11 +1704,15 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
         D_dev = static_cast<float*>(ix->d_out.p);
         I_dev = static_cast<int64_t*>(ix->i_out.p);
     }
+    if (multi) {      // the shards' lists of the whole batch meet on the home device
+        CKR(ensure(ix->gat_d, static_cast<size_t>(G) * nq * row_d));
+        CKR(ensure(ix->gat_i, static_cast<size_t>(G) * nq * row_i));
+    }
     auto compute = [&](int64_t a, int64_t m) -> int {
         if (!multi) return search_device(ix, xq_dev[0] + a * ix->d, m, k, D_dev + a * k, I_dev + a * k);
         std::vector<const float*> xc(G);
         for (int g = 0; g < G; ++g) xc[g] = xq_dev[g] + a * ix->d;
-        return multi_compute_chunk(ix, xc, m, k, D_dev + a * k, I_dev + a * k);
+        return multi_search_chunk(ix, xc, nq, a, m, k);
     };
     if (!multi && n_chunks == 1 && !(x_host && nq * row_in >= kStageMin)) {
         // small call (the mining shapes): one copy in, one launch sequence, one copy out, one synchronisation
@@ -1782,11 +1782,28 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
         }
         return 0;
     };
-    for (int c = 0; c < n_chunks; ++c) {
+    auto emit_chunk = [&](int c) -> int {      // results of chunk c leave on s_out once everything queued on the compute stream is done
         const int64_t a = cuts[c], m = cuts[c + 1] - cuts[c];
         cudaEvent_t ev_done, ev_out;
         CKR(pipe_event(ix, 3 * c + 2, &ev_done));
         CKR(pipe_event(ix, 3 * c + 3, &ev_out));
+        CK(cudaEventRecord(ev_done, ix->stream));
+        if (stage_out && c >= 2) CKR(drain(c - 2));      // frees the pinned slot this chunk's results go to
+        CK(cudaStreamWaitEvent(ix->s_out, ev_done, 0));
+        if (stage_out) {
+            uint8_t* slot = ix->out_slot[c & 1];
+            CK(cudaMemcpyAsync(slot, D_dev + a * k, static_cast<size_t>(m) * row_d, cudaMemcpyDeviceToHost, ix->s_out));
+            CK(cudaMemcpyAsync(slot + static_cast<size_t>(max_chunk) * row_d, I_dev + a * k, static_cast<size_t>(m) * row_i,
+                               cudaMemcpyDeviceToHost, ix->s_out));
+        } else {
+            CK(cudaMemcpyAsync(D + a * k, D_dev + a * k, static_cast<size_t>(m) * row_d, cudaMemcpyDeviceToHost, ix->s_out));
+            CK(cudaMemcpyAsync(I + a * k, I_dev + a * k, static_cast<size_t>(m) * row_i, cudaMemcpyDeviceToHost, ix->s_out));
+        }
+        CK(cudaEventRecord(ev_out, ix->s_out));
+        return 0;
+    };
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t a = cuts[c], m = cuts[c + 1] - cuts[c];
         const size_t bytes = static_cast<size_t>(m) * row_in, off0 = static_cast<size_t>(a) * row_in;
         if (x_host) {
             const char* src = reinterpret_cast<const char*>(x) + off0;
@@ -1831,21 +1848,12 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
         }
         if (multi) CK(cudaSetDevice(ix->device));
         CKR(compute(a, m));
-        if (out_host) {
-            CK(cudaEventRecord(ev_done, ix->stream));
-            if (stage_out && c >= 2) CKR(drain(c - 2));      // frees the pinned slot this chunk's results go to
-            CK(cudaStreamWaitEvent(ix->s_out, ev_done, 0));
-            if (stage_out) {
-                uint8_t* slot = ix->out_slot[c & 1];
-                CK(cudaMemcpyAsync(slot, D_dev + a * k, static_cast<size_t>(m) * row_d, cudaMemcpyDeviceToHost, ix->s_out));
-                CK(cudaMemcpyAsync(slot + static_cast<size_t>(max_chunk) * row_d, I_dev + a * k, static_cast<size_t>(m) * row_i,
-                                   cudaMemcpyDeviceToHost, ix->s_out));
-            } else {
-                CK(cudaMemcpyAsync(D + a * k, D_dev + a * k, static_cast<size_t>(m) * row_d, cudaMemcpyDeviceToHost, ix->s_out));
-                CK(cudaMemcpyAsync(I + a * k, I_dev + a * k, static_cast<size_t>(m) * row_i, cudaMemcpyDeviceToHost, ix->s_out));
-            }
-            CK(cudaEventRecord(ev_out, ix->s_out));
-        }
+        if (out_host && !multi) CKR(emit_chunk(c));      // (multi-device: the results exist only after the final merge)
+    }
+    if (multi) {
+        CKR(multi_merge(ix, nq, k, D_dev, I_dev));
+        if (out_host)
+            for (int c = 0; c < n_chunks; ++c) CKR(emit_chunk(c));
     }
     if (out_host) {
         for (int c = std::max(0, n_chunks - 2); c < n_chunks; ++c) CKR(drain(c));
