@@ -638,24 +638,6 @@ static void prof_collect(agp_index* ix) {
     ix->ev_used = 0;
 }
 
-// choose the number of database splits: minimise waves * tiles-per-item (+ per-item overhead)
-static int choose_splits(int n_qtiles, int n_dbtiles, int num_sms) {
-    int best = 1;
-    double best_cost = 1e300;
-    const int max_s = std::min(n_dbtiles, 64);
-    for (int s = 1; s <= max_s; ++s) {
-        const int64_t items = static_cast<int64_t>(n_qtiles) * s;
-        const int64_t waves = (items + num_sms - 1) / num_sms;
-        const int tiles = (n_dbtiles + s - 1) / s;
-        const double cost = static_cast<double>(waves) * (tiles + 0.75);   // ~0.75 tile of fill/drain/emit per item
-        if (cost < best_cost * 0.999) {
-            best_cost = cost;
-            best = s;
-        }
-    }
-    return best;
-}
-
 // ------------------------------------------------------------------------------------------ search paths
 // every path writes D/I (device) for queries [q0, q0+nqc)
 
@@ -1079,32 +1061,6 @@ static int copy_h2d(agp_index* ix, void* dst, const void* src, size_t bytes) {
     }
     // the staging buffers are reused by the next transfer of this index: drain before returning
     for (int b = 0; b < 2; ++b) CK(cudaEventSynchronize(ix->stage_ev[b]));
-    return 0;
-}
-
-// device -> host after everything queued on the index's stream; returns with the host buffer complete
-static int copy_d2h_sync(agp_index* ix, void* dst, const void* src, size_t bytes) {
-    if (bytes < kStageMin || !is_pageable(dst)) {
-        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ix->stream));
-        CK(cudaStreamSynchronize(ix->stream));
-        return 0;
-    }
-    CKR(ensure_stage(ix));
-    std::lock_guard<std::mutex> lk(g_copy_mu);
-    const int n_chunks = static_cast<int>((bytes + kStageChunk - 1) / kStageChunk);
-    auto issue = [&](int c) -> cudaError_t {
-        const size_t off = static_cast<size_t>(c) * kStageChunk;
-        cudaError_t e = cudaMemcpyAsync(ix->stage[c & 1], static_cast<const char*>(src) + off, std::min(kStageChunk, bytes - off),
-                                        cudaMemcpyDeviceToHost, ix->stream);
-        return e != cudaSuccess ? e : cudaEventRecord(ix->stage_ev[c & 1], ix->stream);
-    };
-    CK(issue(0));
-    for (int c = 0; c < n_chunks; ++c) {
-        if (c + 1 < n_chunks) CK(issue(c + 1));                           // DMA of the next chunk overlaps this chunk's host copy
-        CK(cudaEventSynchronize(ix->stage_ev[c & 1]));
-        const size_t off = static_cast<size_t>(c) * kStageChunk;
-        CopyPool::get().memcpy_parallel(static_cast<char*>(dst) + off, ix->stage[c & 1], std::min(kStageChunk, bytes - off));
-    }
     return 0;
 }
 

@@ -609,24 +609,6 @@ __global__ void remap_ids_kernel(int64_t* __restrict__ I, int64_t count, const i
     I[i] = id + tab[2 * lo + 1] + extra;
 }
 
-__global__ void gather_rows_kernel(const float* __restrict__ x, const int* __restrict__ list, int n, int d, float* __restrict__ out) {
-    const int r = blockIdx.x;
-    if (r >= n) return;
-    const float* src = x + static_cast<int64_t>(list[r]) * d;
-    for (int c = threadIdx.x; c < d; c += blockDim.x) out[static_cast<int64_t>(r) * d + c] = src[c];
-}
-
-__global__ void scatter_results_kernel(const float* __restrict__ Dt, const int64_t* __restrict__ It, const int* __restrict__ list, int n,
-                                       int k, float* __restrict__ D, int64_t* __restrict__ I) {
-    const int r = blockIdx.x;
-    if (r >= n) return;
-    const int64_t q = list[r];
-    for (int c = threadIdx.x; c < k; c += blockDim.x) {
-        D[q * k + c] = Dt[static_cast<int64_t>(r) * k + c];
-        I[q * k + c] = It[static_cast<int64_t>(r) * k + c];
-    }
-}
-
 // N2 (batched mining): drop, per query, the ids on its exclusion list from an ascending result list of kp entries
 // and keep the first k survivors -- the reference's `setdiff1d(sampled_database_indexes, soft_positives)` followed by
 // `search(..., k)` (datasets/datasets_ws_kitti360.py:1088-1091,985-993), done for all queries at once.  One warp per query;
@@ -792,19 +774,6 @@ cudaError_t launch_ovf_exact(const int* ovf_count, const int* ovf_list, const fl
 cudaError_t launch_remap_ids(int64_t* I, int64_t count, const int64_t* tab, int n_chunks, int64_t extra, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     remap_ids_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, st>>>(I, count, tab, n_chunks, extra);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_gather_rows(const float* x, const int* list, int n, int d, float* out, cudaStream_t st) {
-    if (n <= 0) return cudaSuccess;
-    gather_rows_kernel<<<n, 128, 0, st>>>(x, list, n, d, out);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_scatter_results(const float* Dt, const int64_t* It, const int* list, int n, int k, float* D, int64_t* I,
-                                   cudaStream_t st) {
-    if (n <= 0) return cudaSuccess;
-    scatter_results_kernel<<<n, 64, 0, st>>>(Dt, It, list, n, k, D, I);
     return cudaGetLastError();
 }
 

@@ -145,9 +145,6 @@ cudaError_t launch_mask_select(const float* Dp, const int64_t* Ip, int kp, const
                                float* D, int64_t* I, cudaStream_t st);
 cudaError_t launch_best_of_lists(const float* xq, const float* rows, int d, const int64_t* off, int64_t nq, float* best_d,
                                  int64_t* best_pos, cudaStream_t st);
-// rows out[i] = x[list[i]] and results D/I[list[i]] = Dt/It[i] (exact fallback of overflowed queries)
-cudaError_t launch_gather_rows(const float* x, const int* list, int n, int d, float* out, cudaStream_t st);
-cudaError_t launch_scatter_results(const float* Dt, const int64_t* It, const int* list, int n, int k, float* D, int64_t* I, cudaStream_t st);
 cudaError_t launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st);
 // multi-device index: shard-local rows -> global ids through the shard's (local_start, delta) table
 cudaError_t launch_remap_ids(int64_t* I, int64_t count, const int64_t* tab, int n_chunks, int64_t extra, cudaStream_t st);
