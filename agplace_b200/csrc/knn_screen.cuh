@@ -348,15 +348,21 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                 const bool in_step = p.lockstep > 0 && item < p.n_full_items;
                 const int n_sync = in_step ? (p.n_dbtiles + p.lockstep - 1) / p.lockstep : 0;
                 unsigned int* ctr = in_step ? p.sync_ctr + static_cast<size_t>(item / n_clusters) * n_sync : nullptr;
+                // The meeting points are a performance hint, never a correctness requirement: a pair that has waited ~2 ms
+                // (another kernel holds SMs, so part of this grid is not resident yet -- two large searches sharing one GPU)
+                // stops waiting for the rest of the item but keeps announcing its arrivals, so nobody can wait on it forever.
+                bool waiting = true;
                 for (int t = it.t0; t < it.t1; ++t) {
                     if (in_step && t > 0 && t % p.lockstep == 0) {
                         unsigned int* c = ctr + t / p.lockstep;
                         if (rank == 0) atomicAdd(c, 1u);
-                        unsigned int seen;
-                        do {
+                        unsigned int seen = 0;
+                        for (int spins = 0; waiting; ++spins) {
                             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(c) : "memory");
-                            if (seen < static_cast<unsigned>(n_clusters)) __nanosleep(100);
-                        } while (seen < static_cast<unsigned>(n_clusters));
+                            if (seen >= static_cast<unsigned>(n_clusters)) break;
+                            if (spins > 20000) waiting = false;
+                            __nanosleep(100);
+                        }
                     }
                     const int brow0 = t * TC_BN + static_cast<int>(rank) * (TC_BN / 2);
                     for (int kc = 0; kc < num_kc; ++kc) {

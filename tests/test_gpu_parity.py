@@ -601,3 +601,40 @@ def test_host_pipeline_returns_the_device_path_bits(pinned):
     Dr, Ir = orc.knn_fp32(xq[sample], xb, k)
     ok, msg = orc.compare_knn(Dd[sample], Id[sample], Dr, Ir, xq=xq[sample], xb=xb, abs_floor_eps=8 * 2.0 ** -24)
     assert ok, msg
+
+
+def test_lockstep_sweep_is_only_a_hint():
+    """Large planes are swept in step (the TMA producers of a full wave meet every few tiles at a global counter).  The
+    meeting points must never be able to hang: two searches that share one GPU (two host threads; virtual shards of a
+    multi-device index) each leave part of the other's grid non-resident.  Forced on for a small plane here; results
+    must be the bits of the default configuration."""
+    import threading
+    import agplace_b200
+    rng = np.random.default_rng(61)
+    n, nq, d, k = 70_000, 19_200, 64, 20                   # 75 pair tiles: one full wave + a remainder
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    xq = rng.standard_normal((nq, d)).astype(np.float32)
+    ref = agplace_b200.IndexFlatL2(d); ref.add(xb)
+    D0, I0 = ref.search(xq, k)
+    out = {}
+
+    def worker(tag):
+        ix = agplace_b200.IndexFlatL2(d); ix.add(xb)
+        ix.set_knob("screen_lockstep", 4)
+        for _ in range(4):
+            out[tag] = ix.search(xq, k)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+        assert not t.is_alive(), "a search with lockstep enabled did not return"
+    for tag, (D, I) in out.items():
+        np.testing.assert_array_equal(I, I0, err_msg=f"thread {tag}")
+        np.testing.assert_array_equal(D, D0)
+    multi = agplace_b200.IndexFlatL2(d, devices=[0, 0]); multi.add(xb)
+    multi.set_knob("screen_lockstep", 4)
+    D, I = multi.search(xq, k)
+    np.testing.assert_array_equal(I, I0)
+    np.testing.assert_array_equal(D, D0)
