@@ -897,9 +897,6 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         CKR(ensure(ix->qn, static_cast<size_t>(nqc) * sizeof(float)));
         CKR(ensure(ix->sq, static_cast<size_t>(nqc) * sizeof(float)));
         CKR(ensure(ix->dq, static_cast<size_t>(nqc) * sizeof(float)));
-        ProfScope prof_prep(ix, AGP_PHASE_PREP);
-        LAUNCH(launch_prep_rows_screen(xq_dev + q0 * ix->d, nqc, ix->d, ix->d_pad, ix->q_hi.p, static_cast<float*>(ix->qn.p),
-                                       static_cast<float*>(ix->sq.p), static_cast<float*>(ix->dq.p), nullptr, 0, ix->num_sms * 32, ix->stream));
         CUtensorMap m_q;
         CKR(make_plane_map(&m_q, ix->q_hi.p, rows_pad, ix->d_pad, TC_BM, 2, ld));
         // whole waves of pair tiles sweep the database unsplit; the last partial wave is split to fill every pair
@@ -955,12 +952,23 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         CKR(ensure(ix->ovf, static_cast<size_t>(nqc) * sizeof(int)));
         CKR(ensure(ix->ovf_list, static_cast<size_t>(nqc + 1) * sizeof(int)));
         CKR(ensure(ix->hthr, n_lists_total * sizeof(uint32_t)));
-        // one launch: list counters, overflow flags / list head, shared bounds (+inf), zero padding rows of the query plane
-        LAUNCH(launch_screen_init(static_cast<int*>(ix->cand.p), static_cast<uint32_t*>(ix->hthr.p), static_cast<int64_t>(n_lists_total),
-                                  static_cast<int*>(ix->ovf.p), static_cast<uint32_t*>(ix->gthr.p), nqc, static_cast<int*>(ix->ovf_list.p),
-                                  static_cast<uint8_t*>(ix->q_hi.p) + static_cast<size_t>(nqc) * ld * 2,
-                                  static_cast<size_t>(rows_pad - nqc) * ld * 2, ix->stream));
-        prof_prep.stop();
+        {   // K1 on the queries; the same launch resets the search's state (list counters, bounds = +inf, overflow flags /
+            // list head, zero padding rows of the query plane)
+            ScreenInit init;
+            init.pcount = static_cast<int*>(ix->cand.p);
+            init.hthr = static_cast<uint32_t*>(ix->hthr.p);
+            init.n_lists = static_cast<int64_t>(n_lists_total);
+            init.ovf = static_cast<int*>(ix->ovf.p);
+            init.gthr = static_cast<uint32_t*>(ix->gthr.p);
+            init.nq = nqc;
+            init.ovf_count = static_cast<int*>(ix->ovf_list.p);
+            init.pad = static_cast<uint8_t*>(ix->q_hi.p) + static_cast<size_t>(nqc) * ld * 2;
+            init.pad_bytes = static_cast<size_t>(rows_pad - nqc) * ld * 2;
+            ProfScope prof_prep(ix, AGP_PHASE_PREP);
+            LAUNCH(launch_prep_rows_screen(xq_dev + q0 * ix->d, nqc, ix->d, ix->d_pad, ix->q_hi.p, static_cast<float*>(ix->qn.p),
+                                           static_cast<float*>(ix->sq.p), static_cast<float*>(ix->dq.p), nullptr, 0, ix->num_sms * 32, ix->stream, &init));
+            prof_prep.stop();
+        }
         p.hthr = static_cast<uint32_t*>(ix->hthr.p);
         p.qn = static_cast<const float*>(ix->qn.p);
         p.sq = static_cast<const float*>(ix->sq.p);

@@ -145,7 +145,22 @@ __global__ void __launch_bounds__(256) prep_rows_f16_kernel(const float* __restr
 __global__ void __launch_bounds__(256) prep_rows_screen_kernel(const float* __restrict__ x, int64_t n, int d, int d_pad,
                                                                __half* __restrict__ plane, float* __restrict__ norm,
                                                                float* __restrict__ scale_out, float* __restrict__ dres,
-                                                               uint32_t* __restrict__ stats, int is_db) {
+                                                               uint32_t* __restrict__ stats, int is_db, const ScreenInit init) {
+    if (init.ovf_count != nullptr) {      // query-side launch of a screened search: reset the search's state on the way
+        const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+        const int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+        for (int64_t i = i0; i < init.n_lists; i += stride) {
+            init.pcount[i] = 0;
+            init.hthr[i] = 0x7f800000u;
+        }
+        for (int64_t i = i0; i < init.nq; i += stride) {
+            init.ovf[i] = 0;
+            init.gthr[i] = 0x7f800000u;
+        }
+        uint4* pad = static_cast<uint4*>(init.pad);
+        for (int64_t i = i0; i < static_cast<int64_t>(init.pad_bytes / 16); i += stride) pad[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (i0 == 0) *init.ovf_count = 0;
+    }
     const int lane = threadIdx.x & 31;
     const int ld = d_pad + 64;
     const float inf = __int_as_float(0x7f800000);
@@ -453,25 +468,6 @@ __global__ void __launch_bounds__(128) recall_kernel(const int64_t* __restrict__
 }
 
 
-// One launch resets everything a screened search needs (was: two fill kernels + three memsets): list counters, overflow
-// flags and list head, the shared bounds (+inf) and the zero padding rows of the query plane.
-__global__ void screen_init_kernel(int* __restrict__ pcount, uint32_t* __restrict__ hthr, int64_t n_lists, int* __restrict__ ovf,
-                                   uint32_t* __restrict__ gthr, int64_t nq, int* __restrict__ ovf_count, uint4* __restrict__ pad,
-                                   int64_t pad_vec) {
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    const int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    for (int64_t i = i0; i < n_lists; i += stride) {
-        pcount[i] = 0;
-        hthr[i] = 0x7f800000u;
-    }
-    for (int64_t i = i0; i < nq; i += stride) {
-        ovf[i] = 0;
-        gthr[i] = 0x7f800000u;
-    }
-    for (int64_t i = i0; i < pad_vec; i += stride) pad[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (i0 == 0) *ovf_count = 0;
-}
-
 // Exact answer for the queries the screen flagged (certified band wider than the candidate slots: mass duplicates; rows
 // the fp16 plane cannot represent), run ON THE DEVICE from the overflow list the finish kernel wrote -- the host never
 // reads the count, so a screened search needs no synchronisation.  Launched after every finalize; with an empty list
@@ -746,15 +742,6 @@ cudaError_t launch_best_of_lists(const float* xq, const float* rows, int d, cons
     return cudaGetLastError();
 }
 
-cudaError_t launch_screen_init(int* pcount, uint32_t* hthr, int64_t n_lists, int* ovf, uint32_t* gthr, int64_t nq, int* ovf_count,
-                               void* pad, size_t pad_bytes, cudaStream_t st) {
-    const int64_t pad_vec = static_cast<int64_t>(pad_bytes / 16);      // plane rows are multiples of 128 bytes
-    const int64_t work = std::max<int64_t>({n_lists, nq, pad_vec, 1});
-    const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((work + 255) / 256, 2048));
-    screen_init_kernel<<<blocks, 256, 0, st>>>(pcount, hthr, n_lists, ovf, gthr, nq, ovf_count, static_cast<uint4*>(pad), pad_vec);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_ovf_exact(const int* ovf_count, const int* ovf_list, const float* xq, const float* xb, int64_t n, int d, int k,
                              int64_t id_base, int ip, float* D, int64_t* I, unsigned long long* stat_fallback, int num_sms,
                              cudaStream_t st) {
@@ -798,10 +785,15 @@ cudaError_t launch_prep_rows_f16(const float* x, int64_t n, int d, int d_pad, fl
 }
 
 cudaError_t launch_prep_rows_screen(const float* x, int64_t n, int d, int d_pad, void* plane, float* norm, float* scale_out, float* dres,
-                                    uint32_t* stats, int is_db, int max_blocks, cudaStream_t st) {
+                                    uint32_t* stats, int is_db, int max_blocks, cudaStream_t st, const ScreenInit* init) {
     if (n <= 0) return cudaSuccess;
-    const unsigned blocks = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, max_blocks)));
-    prep_rows_screen_kernel<<<blocks, 256, 0, st>>>(x, n, d, d_pad, static_cast<__half*>(plane), norm, scale_out, dres, stats, is_db);
+    unsigned blocks = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, max_blocks)));
+    if (init) {      // enough threads that the reset loops stay short next to the row work
+        const int64_t work = std::max<int64_t>({init->n_lists, init->nq, static_cast<int64_t>(init->pad_bytes / 16)});
+        blocks = static_cast<unsigned>(std::max<int64_t>(blocks, std::min<int64_t>((work + 1023) / 1024, max_blocks)));
+    }
+    prep_rows_screen_kernel<<<blocks, 256, 0, st>>>(x, n, d, d_pad, static_cast<__half*>(plane), norm, scale_out, dres, stats, is_db,
+                                                    init ? *init : ScreenInit());
     return cudaGetLastError();
 }
 

@@ -135,9 +135,22 @@ cudaError_t launch_prep_rows(bool split, const float* x, int64_t n, int d, int d
 // fp16 planes of the power-of-two scaled rows; scale[r] = factor * 2^ex (factor = 1 for queries, -2 for database rows)
 cudaError_t launch_prep_rows_f16(const float* x, int64_t n, int d, int d_pad, float* norm, void* hi, void* lo, float* scale, float factor,
                                  float* dres, uint32_t* stats, int max_blocks, cudaStream_t st);
+// Per-search state of the screen that the query-side prep launch resets on its way (one launch instead of prep + init):
+// list counters, shared bounds (+inf), overflow flags / list head, zero padding rows of the query plane.
+struct ScreenInit {
+    int* pcount = nullptr;
+    uint32_t* hthr = nullptr;
+    int64_t n_lists = 0;
+    int* ovf = nullptr;
+    uint32_t* gthr = nullptr;
+    int64_t nq = 0;
+    int* ovf_count = nullptr;
+    void* pad = nullptr;
+    size_t pad_bytes = 0;
+};
 // single-pass screen planes: [rows, d_pad + 64] fp16 = scaled row + aux chunk (k_misc.cu:prep_rows_screen_kernel)
 cudaError_t launch_prep_rows_screen(const float* x, int64_t n, int d, int d_pad, void* plane, float* norm, float* scale_out, float* dres,
-                                    uint32_t* stats, int is_db, int max_blocks, cudaStream_t st);
+                                    uint32_t* stats, int is_db, int max_blocks, cudaStream_t st, const ScreenInit* init = nullptr);
 cudaError_t launch_fix_db_scale(const float* x, int64_t count, uint32_t* stats, int max_blocks, cudaStream_t st);
 cudaError_t launch_init_aux(void* plane, int d_pad, int64_t row0, int64_t row1, cudaStream_t st);
 // N2 batched mining helpers (k_misc.cu)
@@ -148,9 +161,6 @@ cudaError_t launch_best_of_lists(const float* xq, const float* rows, int d, cons
 cudaError_t launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st);
 // multi-device index: shard-local rows -> global ids through the shard's (local_start, delta) table
 cudaError_t launch_remap_ids(int64_t* I, int64_t count, const int64_t* tab, int n_chunks, int64_t extra, cudaStream_t st);
-// one launch that resets the per-search state of the screen (list counters, bounds, overflow flags, query-plane padding)
-cudaError_t launch_screen_init(int* pcount, uint32_t* hthr, int64_t n_lists, int* ovf, uint32_t* gthr, int64_t nq, int* ovf_count,
-                               void* pad, size_t pad_bytes, cudaStream_t st);
 // device-side exact fallback over the overflow list written by the finish kernel (no host round trip)
 cudaError_t launch_ovf_exact(const int* ovf_count, const int* ovf_list, const float* xq, const float* xb, int64_t n, int d, int k,
                              int64_t id_base, int ip, float* D, int64_t* I, unsigned long long* stat_fallback, int num_sms,
