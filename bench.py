@@ -162,12 +162,25 @@ def cpu_search_rate(xb, xq_sample, k, repeats=1):
     return len(xq_sample) / best, best
 
 
-def cpu_sample_plan(c, seconds_per_pass, rate_hint=None):
-    """Bounded CPU sample of a workload: (database rows used, queries used).  The CPU cost of brute-force search is
-    linear in rows x queries, so a sample over R of N rows extrapolates as q/s(N) = q/s(R) * R / N."""
-    rows = min(c["n"], max(100_000, int(2e9 // (c["d"] * 4))))          # <= 2 GB of fp32 rows on the host
-    q = min(c["nq"], 4096)                                               # one faiss sgemm block
-    return rows, q
+def cpu_sample(c, xq, seconds_per_pass, orc):
+    """Bounded CPU sample of a workload.  The query block stays at faiss's own size (4096 queries per sgemm block: smaller
+    blocks run the BLAS below its efficient size and would understate the CPU); the DATABASE is what gets sampled -- the
+    CPU cost of brute-force search is linear in rows (faiss loops over 1024-row blocks), so a pass over R of N rows
+    extrapolates as q/s(N) = q/s(R) * R / N.  Returns (rows array, query sample, scale)."""
+    q = min(c["nq"], 4096)
+    rows_max = min(c["n"], max(100_000, int(2e9 // (c["d"] * 4))))          # <= 2 GB of fp32 rows on the host
+    sample = xq[:q]
+    probe_rows = min(rows_max, 65536)
+    xb = host_rows(c, 0, probe_rows if c["device_generated"] else rows_max)
+    orc.knn_fp32(sample[:256], xb[:probe_rows], c["k"])                       # throw-away call (thread pools, page faults)
+    t0 = time.perf_counter()
+    orc.knn_fp32(sample, xb[:probe_rows], c["k"])
+    t_probe = time.perf_counter() - t0
+    rows = int(min(rows_max, max(16384, probe_rows * seconds_per_pass / max(t_probe, 1e-6))))
+    rows = max(1024, rows // 1024 * 1024) if rows < rows_max else rows_max
+    if rows > len(xb):
+        xb = host_rows(c, 0, rows)
+    return np.ascontiguousarray(xb[:rows]), sample, rows / c["n"]
 
 
 def run_reference(args):
@@ -178,33 +191,18 @@ def run_reference(args):
     orc.build()
     c = workload(args.workload)
     cores = os.cpu_count() or 1
-    rows, _ = cpu_sample_plan(c, 2.0)
-    xb = host_rows(c, 0, rows)
     xq = host_queries(c, min(c["nq"], 4096))
-    # bounded sample: the CPU path is only efficient on large query blocks (faiss multiplies 4096 queries at a time), so
-    # the rate is probed on 1024 queries (after a throw-away call) and a step is sized so that the whole --steps K run
-    # stays within ~2.5 minutes
-    cpu_search_rate(xb, xq[:256], c["k"])
-    rate, _ = cpu_search_rate(xb, xq[: min(1024, len(xq))], c["k"])
     n_calls = max(args.steps + min(args.warmup, 2), 1)
-    per_step_s = min(4.0, 150.0 / n_calls)
-    sample_q = int(min(len(xq), max(256, rate * per_step_s)))
-    if sample_q < 4096 <= len(xq) and 4096 / rate * n_calls <= 150.0:
-        sample_q = 4096
-    sample = xq[:sample_q]
+    per_step_s = min(4.0, 150.0 / n_calls)          # the whole --steps K run stays within ~2.5 minutes
+    xb, sample, scale = cpu_sample(c, xq, per_step_s, orc)
+    sample_q, rows = len(sample), len(xb)
     for _ in range(max(1, min(args.warmup, 2))):
-        t0 = time.perf_counter()
         orc.knn_fp32(sample, xb, c["k"])
-        t_warm = time.perf_counter() - t0
-        if t_warm > 1.25 * per_step_s and sample_q > 256:      # the probe overstated the rate: shrink the sample to the budget
-            sample_q = max(256, int(sample_q * per_step_s / t_warm))
-            sample = xq[:sample_q]
     t0 = time.perf_counter()
     for _ in range(args.steps):
         orc.knn_fp32(sample, xb, c["k"])
     dt = time.perf_counter() - t0
-    scale = rows / c["n"]                      # linear extrapolation from the row sample to the full database
-    value = sample_q * args.steps / dt * scale
+    value = sample_q * args.steps / dt * scale      # linear extrapolation from the row sample to the full database
     sample_desc = (f"{sample_q} of {c['nq']} queries x {rows} of {c['n']} database rows x {c['d']}-d per step, k={c['k']}"
                    + (f"; queries/s extrapolated linearly in rows (x {scale:.4g})" if scale != 1.0 else ""))
     line = {
@@ -416,14 +414,10 @@ def run_ours(args):
         if not args.no_cpu_baseline:
             from oracle import flatl2_oracle as orc
             orc.build()
-            rows, q = cpu_sample_plan(c, args.cpu_seconds)
-            xb_s = r["xb"][:rows] if r["xb"] is not None else host_rows(c, 0, rows)
-            probe_rate, _ = cpu_search_rate(xb_s, r["xq"][:min(q, 1024)], k)
-            sample_q = int(min(nq, max(256, min(probe_rate * args.cpu_seconds, 4096 * 4))))
-            rate, dt = cpu_search_rate(xb_s, r["xq"][:sample_q], k)
-            scale = rows / n
+            xb_s, sample, scale = cpu_sample(c, r["xq"], args.cpu_seconds, orc)
+            rate, dt = cpu_search_rate(xb_s, sample, k)
             line["cpu_baseline"] = {"value": rate * scale, "unit": UNIT, "cores": os.cpu_count(), "threads": orc.num_threads(), "kind": "port",
-                                    "sample": f"{sample_q} of {nq} queries x {rows} of {n} database rows x {d}-d, k={k}, one pass ({dt:.1f} s)"
+                                    "sample": f"{len(sample)} of {nq} queries x {len(xb_s)} of {n} database rows x {d}-d, k={k}, one pass ({dt:.1f} s)"
                                               + (f", queries/s extrapolated linearly in rows (x {scale:.4g})" if scale != 1.0 else "")
                                               + "; faiss-IndexFlatL2-equivalent CPU restatement (numpy/OpenBLAS sgemm + C heaps)"}
             del xb_s
