@@ -213,6 +213,7 @@ public:
     // stream_dst: dst is pinned staging memory the CPU will not read again (non-temporal stores)
     void memcpy_parallel(void* dst, const void* src, size_t bytes, bool stream_dst = false) {
         if (workers_ == 0 || bytes < (size_t(1) << 20)) { copy_part(static_cast<char*>(dst), static_cast<const char*>(src), bytes, stream_dst && bytes >= 65536); return; }
+        std::lock_guard<std::mutex> job_lock(job_mu_);      // one job at a time drives the workers (callers of different indexes queue here)
         Job j;
         j.stream = stream_dst;
         j.d = static_cast<char*>(dst);
@@ -322,13 +323,12 @@ private:
             }
         }
     }
-    std::mutex mu_;
+    std::mutex mu_, job_mu_;
     std::condition_variable cv_;
     Job* job_ = nullptr;
     std::atomic<uint64_t> epoch_{0};
     unsigned workers_ = 0;
 };
-std::mutex g_copy_mu;      // one staged transfer at a time drives the pool (transfers of different indexes serialise here)
 
 bool is_pageable(const void* p) {
     cudaPointerAttributes a;
@@ -1057,7 +1057,6 @@ static int copy_h2d(agp_index* ix, void* dst, const void* src, size_t bytes) {
         return 0;
     }
     CKR(ensure_stage(ix));
-    std::lock_guard<std::mutex> lk(g_copy_mu);
     int c = 0;
     for (size_t off = 0; off < bytes; off += kStageChunk, ++c) {
         const int b = c & 1;
@@ -1732,7 +1731,6 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
     }
     CK(cudaSetDevice(ix->device));
 
-    std::lock_guard<std::mutex> lk(g_copy_mu);      // one pipelined transfer at a time drives the copy workers
     int ring_pos = 0, ring_used = 0;
     auto drain = [&](int c) -> int {      // results of chunk c: wait for its D2H, copy out of the pinned slot
         cudaEvent_t ev_out;

@@ -752,8 +752,14 @@ cudaError_t launch_ovf_exact(const int* ovf_count, const int* ovf_list, const fl
     while (gq > 1 && static_cast<size_t>(gq) * (OVF_CAP * sizeof(uint64_t) + static_cast<size_t>(d) * sizeof(float)) > budget) --gq;
     const size_t smem = static_cast<size_t>(gq) * (OVF_CAP * sizeof(uint64_t) + static_cast<size_t>(d) * sizeof(float));
     if (smem > 200 * 1024) return cudaErrorInvalidValue;      // d > ~48k
-    cudaError_t e = cudaFuncSetAttribute(ovf_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
+    static size_t attr_smem[16] = {0};      // per device: largest dynamic window requested so far (the attribute call costs microseconds)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16 || attr_smem[dev] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(ovf_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 16) attr_smem[dev] = smem;
+    }
     ovf_exact_kernel<<<num_sms, 256, smem, st>>>(ovf_count, ovf_list, xq, xb, n, d, k, id_base, ip, gq, D, I, stat_fallback);
     return cudaGetLastError();
 }

@@ -49,11 +49,11 @@ def _result_array(shape, dtype):
     blocks from torch's caching host allocator (the block goes back to that cache when the array is garbage
     collected): the engine's D2H copy then lands directly in the array the caller receives -- no pinned staging copy,
     no first-touch page faults on a fresh pageable allocation."""
-    nbytes = shape[0] * shape[1] * (4 if dtype is np.float32 else 8)
+    nbytes = shape[0] * shape[1] * np.dtype(dtype).itemsize
     if _PINNED_RESULT_MIN <= nbytes <= _PINNED_RESULT_MAX:
         try:
             import torch
-            t = torch.empty(shape, dtype=torch.float32 if dtype == np.float32 else torch.int64, pin_memory=True)
+            t = torch.empty(shape, dtype=torch.float32 if np.dtype(dtype) == np.float32 else torch.int64, pin_memory=True)
             return t.numpy()          # keeps the tensor (and its pinned block) alive through .base
         except Exception:
             pass

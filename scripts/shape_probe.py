@@ -33,6 +33,12 @@ def probe(name, counters, pipe, reps, sched=(), first_cuts=()):
         ix.search(xq_d, k)
         torch.cuda.synchronize()
         ix.set_knob("cycle_counters", 0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ix.search(xq_d, k)
+    host_enqueue_ms = (time.perf_counter() - t0) / reps * 1e3      # host time to enqueue one search (the GPU runs behind)
+    torch.cuda.synchronize()
     ix.set_profiling(True)
     ix.get_profile_phases(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -46,7 +52,7 @@ def probe(name, counters, pipe, reps, sched=(), first_cuts=()):
     ix.set_profiling(False)
     kms = ph["distance"][0] / max(ph["distance"][1], 1) * (ph["distance"][1] / reps)
     out = dict(cfg=name, step_ms=round(step, 4), kernel_ms=round(kms, 4), tflops=round(2.0 * nq * n * d / (kms * 1e-3) / 1e12, 1),
-               phases_ms={p: round(v[0] / reps, 4) for p, v in ph.items()}, kernel_share=round(kms / step, 3))
+               phases_ms={p: round(v[0] / reps, 4) for p, v in ph.items()}, kernel_share=round(kms / step, 3), host_enqueue_ms=round(host_enqueue_ms, 4))
     if sched:
         sw = {}
         for m in sched:
