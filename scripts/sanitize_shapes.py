@@ -71,6 +71,14 @@ agp.best_of_lists(xq, xb[np.concatenate(cands)], offs)
 agp.recall_hits(I, cands, [1, 5])
 agp.radius_neighbors(rng.uniform(0, 100, (300, 2)), rng.uniform(0, 100, (20, 2)), 10.0)
 print("ok mining helpers", flush=True)
+# 256 < k <= 512 on the 1024-slot instantiation of the screen kernel; the fused small-database kernel (host mirror path)
+xb, xq = data(1500, 40, 64)
+ix = agp.IndexFlatL2(64, precision="fp16_screen"); ix.add(xb)
+check("screen k=400", *ix.search(xq, 400), *orc.knn_fp32(xq, xb, 400), xq, xb)
+xb, xq = data(900, 3, 256)
+ix = agp.IndexFlatL2(256); ix.add(xb[:400]); ix.add(xb[400:])
+check("fused small-database kernel", *ix.search(xq, 10), *orc.knn_fp32(xq, xb, 10), xq, xb)
+check("fused small-database kernel, k > n", *ix.search(xq[:1], 512), *orc.knn_fp32(xq[:1], xb, 512), xq[:1], xb)
 # multi-device handle on virtual shards + the host pipeline in several chunks
 xb, xq = data(3000, 700, 64)
 single = agp.IndexFlatL2(64); single.add(xb)
