@@ -413,6 +413,7 @@ struct agp_index {
     int64_t dev_rows = 0;                            // rows [0, dev_rows) are resident in xb (< ntotal only while lazy)
     int pipe_chunk = 0;                              // knob: queries per pipeline chunk (0 = automatic)
     int pipe_first = 0;                              // knob: two chunks, the first with this many queries (0 = automatic)
+    int pipe_min_kb = 512;                           // knob: host queries of at least this size take the staged path even as one chunk
     int screen_chunk = 0;                            // knob: queries per screen launch (0 = automatic)
     int screen_lockstep = -1;                        // knob: tiles between the meeting points of a full wave (0 = off, -1 = automatic)
     Buf sync_ctr;
@@ -1285,7 +1286,7 @@ int agp_index_set_knob(agp_index* ix, const char* name, int value) {
         {"screen_flags", &ix->kn.screen_flags}, {"screen_e", &ix->kn.screen_e}, {"screen_stages", &ix->kn.screen_stages},
         {"screen_sched", &ix->kn.screen_sched}, {"tc_e", &ix->kn.tc_e}, {"tc_rerank", &ix->kn.tc_rerank},
         {"tc_compact_sort", &ix->kn.tc_compact_sort}, {"tc_share_bound", &ix->kn.tc_share_bound}, {"cycle_counters", &ix->kn.cycle_counters},
-        {"pipe_chunk", &ix->pipe_chunk}, {"pipe_first", &ix->pipe_first}, {"screen_chunk", &ix->screen_chunk}, {"screen_lockstep", &ix->screen_lockstep},
+        {"pipe_chunk", &ix->pipe_chunk}, {"pipe_first", &ix->pipe_first}, {"pipe_min_kb", &ix->pipe_min_kb}, {"screen_chunk", &ix->screen_chunk}, {"screen_lockstep", &ix->screen_lockstep},
 #ifdef AGP_DEBUG_KNOBS
         {"skip_epi", &ix->kn.skip_epi}, {"skip_mma", &ix->kn.skip_mma},
 #endif
@@ -1677,7 +1678,9 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
         for (int g = 0; g < G; ++g) xc[g] = xq_dev[g] + a * ix->d;
         return multi_search_chunk(ix, xc, nq, a, m, k);
     };
-    if (!multi && n_chunks == 1 && !(x_host && nq * row_in >= kStageMin)) {
+    // (a pageable cudaMemcpyAsync is staged by the driver at ~10 GB/s and blocks the caller; from ~0.5 MB on, our own
+    // pinned ring + multi-threaded streaming copy is faster even for a single chunk: cfg1's 2 MB of queries)
+    if (!multi && n_chunks == 1 && !(x_host && nq * row_in >= (static_cast<size_t>(ix->pipe_min_kb) << 10))) {
         // small call (the mining shapes): one copy in, one launch sequence, one copy out, one synchronisation
         if (x_host) CK(cudaMemcpyAsync(ix->q_raw.p, x, static_cast<size_t>(nq) * row_in, cudaMemcpyHostToDevice, ix->stream));
         CKR(compute(0, nq));

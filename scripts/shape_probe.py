@@ -81,6 +81,19 @@ def probe(name, counters, pipe, reps, sched=(), first_cuts=()):
         e2e[str(chunk)] = round((time.perf_counter() - t0) / reps * 1e3, 4)
     ix.set_knob("pipe_chunk", 0)
     out["numpy_e2e_ms_by_pipe_chunk"] = e2e
+    emin = {}
+    for kb in (512, 1 << 20):
+        ix.set_knob("pipe_min_kb", kb)
+        for _ in range(3):
+            ix.search(xq, k)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ix.search(xq, k)
+        torch.cuda.synchronize()
+        emin["staged" if kb == 512 else "driver_pageable"] = round((time.perf_counter() - t0) / reps * 1e3, 4)
+    ix.set_knob("pipe_min_kb", 512)
+    out["numpy_e2e_ms_small_call"] = emin
     e2f = {}
     for first in first_cuts:
         ix.set_knob("pipe_first", first)
