@@ -100,3 +100,37 @@ def test_multi_device_large_batch_pipeline():
     Dr, Ir = orc.knn_fp32(xq[sample], xb, 30)
     ok, msg = orc.compare_knn(Ds[sample], Is[sample], Dr, Ir, xq=xq[sample], xb=xb, abs_floor_eps=8 * 2.0 ** -24)
     assert ok, msg
+
+
+def test_multi_device_edge_cases():
+    """Empty index, fewer rows than shards, k beyond the row count, faiss's input coercions, and the entry points that are
+    one-device only."""
+    import agplace_b200 as agp
+    FLT_MAX = np.float32(3.4028234663852886e38)
+    rng = np.random.default_rng(11)
+    ix = agp.IndexFlatL2(24, devices=[0, 0, 0])
+    xq = rng.standard_normal((33, 24)).astype(np.float32)
+    D, I = ix.search(xq, 5)                                   # empty: faiss padding
+    assert (I == -1).all() and (D == FLT_MAX).all()
+    xb = rng.standard_normal((2, 24))                         # float64, 2 rows on 3 shards (one shard stays empty)
+    ix.add(xb)
+    assert ix.ntotal == 2
+    D, I = ix.search(xq.astype(np.float64), 4)                # k > ntotal
+    ref = agp.IndexFlatL2(24); ref.add(xb)
+    Dr, Ir = ref.search(xq, 4)
+    np.testing.assert_array_equal(I, Ir)
+    np.testing.assert_array_equal(D, Dr)
+    assert (I[:, 2:] == -1).all()
+    ix.add(np.asfortranarray(rng.standard_normal((700, 24)).astype(np.float32)))     # non-contiguous input
+    assert ix.ntotal == 702
+    with pytest.raises(AssertionError):
+        ix.search(xq[:, :20], 3)
+    with pytest.raises(RuntimeError, match="exceeds"):
+        ix.search(xq, 513)
+    with pytest.raises(RuntimeError, match="one-device"):
+        ix.search_masked(xq, 3, [np.array([0])] * len(xq))
+    with pytest.raises(RuntimeError, match="one-device"):
+        ix.search_subset(xq, 3, [np.array([0, 1])] * len(xq))
+    Dp = np.empty((33, 7), np.float32); Ip = np.empty((33, 7), np.int64)
+    D2, I2 = ix.search(xq, 7, D=Dp, I=Ip)                     # preallocated outputs, like faiss
+    assert D2 is Dp and I2 is Ip
