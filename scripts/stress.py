@@ -37,9 +37,15 @@ while time.time() < t_end:
     metric = "ip" if rng.random() < 0.15 else "l2"
     multi = rng.random() < 0.3
     cls = agp.IndexFlatIP if metric == "ip" else agp.IndexFlatL2
-    ix = cls(d, devices=[0] * int(rng.integers(2, 5))) if multi else cls(d)
+    n_gpu = torch.cuda.device_count()
+    if multi and n_gpu >= 2 and rng.random() < 0.7:       # real devices when the box has them (peer copies over NVLink)
+        devs = [int(v) for v in rng.permutation(n_gpu)[: int(rng.integers(2, min(n_gpu, 4) + 1))]]
+        devs = [0] + [v for v in devs if v != 0]           # CUDA-tensor inputs of this script live on cuda:0 = the home device
+    else:
+        devs = [0] * int(rng.integers(2, 5))
+    ix = cls(d, devices=devs) if multi else cls(d)
     rows = np.empty((0, d), np.float32)
-    desc = f"seq {n_seq}: d={d} {regime} {metric} multi={multi}"
+    desc = f"seq {n_seq}: d={d} {regime} {metric} multi={devs if multi else None}"
     for step in range(int(rng.integers(2, 7))):
         op = rng.random()
         if op < 0.45 or len(rows) == 0:
