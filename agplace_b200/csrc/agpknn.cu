@@ -1073,6 +1073,23 @@ static int copy_h2d(agp_index* ix, void* dst, const void* src, size_t bytes) {
     return 0;
 }
 
+// Every entry point leaves the caller's current CUDA device as it found it (a multi-device index switches devices while it
+// works; torch and other libraries in the process rely on "their" current device).
+namespace {
+struct DeviceRestore {
+    int prev = -1;
+    DeviceRestore() {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();
+            prev = -1;
+        }
+    }
+    ~DeviceRestore() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+}  // namespace
+
 // ------------------------------------------------------------------------------------------ C ABI
 extern "C" {
 
@@ -1096,6 +1113,7 @@ int agp_index_create(int d, int device, int precision_mode, agp_index** out) {
 int agp_index_metric(const agp_index* ix) { return ix && ix->ip ? AGP_METRIC_INNER_PRODUCT : AGP_METRIC_L2; }
 
 int agp_index_create_metric(int d, int device, int precision_mode, int metric, agp_index** out) {
+    DeviceRestore restore_device__;
     if (!out) return set_err(AGP_EINVAL, "out is null");
     *out = nullptr;
     if (d <= 0) return set_err(AGP_EINVAL, "d must be positive, got %d", d);
@@ -1164,6 +1182,7 @@ int agp_index_create_metric(int d, int device, int precision_mode, int metric, a
 }
 
 int agp_index_create_multi(int d, int n_devices, const int* device_ids, int precision_mode, int metric, agp_index** out) {
+    DeviceRestore restore_device__;
     if (!out) return set_err(AGP_EINVAL, "out is null");
     *out = nullptr;
     if (n_devices < 1 || n_devices > 64 || !device_ids) return set_err(AGP_EINVAL, "n_devices must be in 1..64 and device_ids non-null");
@@ -1209,6 +1228,7 @@ int agp_index_create_multi(int d, int n_devices, const int* device_ids, int prec
 int agp_index_n_shards(const agp_index* ix) { return ix ? std::max<int>(1, static_cast<int>(ix->shards.size())) : -1; }
 
 void agp_index_free(agp_index* ix) {
+    DeviceRestore restore_device__;
     if (!ix) return;
     for (size_t g = 0; g < ix->shards.size(); ++g) {
         agp_index* ch = ix->shards[g];
@@ -1266,6 +1286,7 @@ int64_t agp_index_ntotal(const agp_index* ix) { return ix ? ix->ntotal : -1; }
 int agp_index_dim(const agp_index* ix) { return ix ? ix->d : -1; }
 
 int agp_index_set_stream(agp_index* ix, void* s, int use_own_stream) {
+    DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
     // a NULL cudaStream_t is the legacy default stream (what torch uses unless told otherwise)
     cudaStream_t ns = use_own_stream ? ix->own_stream : static_cast<cudaStream_t>(s);
@@ -1302,6 +1323,7 @@ int agp_index_set_knob(agp_index* ix, const char* name, int value) {
 }
 
 int agp_index_screen_probe(agp_index* ix, int64_t nq, const float* x, float* dis, float* band) {
+    DeviceRestore restore_device__;
     if (!ix || !x || !dis || !band) return set_err(AGP_EINVAL, "null pointer");
     if (!ix->screen || ix->ip || !ix->shards.empty())
         return set_err(AGP_EINVAL, "screen_probe needs a one-device L2 index in precision auto or fp16_screen");
@@ -1352,6 +1374,7 @@ int agp_index_set_id_base(agp_index* ix, int64_t b) {
 }
 
 int agp_index_set_profiling(agp_index* ix, int on) {
+    DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
     for (agp_index* ch : ix->shards) CKR(agp_index_set_profiling(ch, on));
     if (!on && ix->profile) prof_collect(ix);
@@ -1360,6 +1383,7 @@ int agp_index_set_profiling(agp_index* ix, int on) {
 }
 
 int agp_index_get_profile(agp_index* ix, double* ms, int64_t* launches, int reset) {
+    DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
     if (!ix->shards.empty()) return agp_index_get_profile(ix->shards[0], ms, launches, reset);      // shard 0 stands for all
     ENTER(ix);
@@ -1372,6 +1396,7 @@ int agp_index_get_profile(agp_index* ix, double* ms, int64_t* launches, int rese
 }
 
 int agp_index_get_profile_phases(agp_index* ix, double* ms, int64_t* launches, int reset) {
+    DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
     if (!ix->shards.empty()) return agp_index_get_profile_phases(ix->shards[0], ms, launches, reset);
     ENTER(ix);
@@ -1385,6 +1410,7 @@ int agp_index_get_profile_phases(agp_index* ix, double* ms, int64_t* launches, i
 }
 
 int agp_index_reserve(agp_index* ix, int64_t n) {
+    DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
     if (!ix->shards.empty()) {
         const int64_t G = static_cast<int64_t>(ix->shards.size());
@@ -1396,6 +1422,7 @@ int agp_index_reserve(agp_index* ix, int64_t n) {
 }
 
 int agp_index_reset(agp_index* ix) {
+    DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
     if (!ix->shards.empty()) {
         for (size_t g = 0; g < ix->shards.size(); ++g) {
@@ -1423,6 +1450,7 @@ int agp_index_reset(agp_index* ix) {
 }
 
 int agp_index_get_stats(const agp_index* ix, int64_t* screened_queries, int64_t* fallback_queries) {
+    DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
     if (!ix->shards.empty()) {      // sums over the shards (every shard screens every query)
         int64_t a = 0, b = 0;
@@ -1448,6 +1476,7 @@ int agp_index_get_stats(const agp_index* ix, int64_t* screened_queries, int64_t*
 }
 
 int agp_index_add(agp_index* ix, int64_t n, const float* x, int mem_kind) {
+    DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
     if (n < 0) return set_err(AGP_EINVAL, "n must be >= 0");
     if (n == 0) return 0;
@@ -1833,6 +1862,7 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
 }
 
 int agp_index_search(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, int k, float* D, int64_t* I, int out_mem_kind) {
+    DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
     if (nq < 0) return set_err(AGP_EINVAL, "nq must be >= 0");
     if (k <= 0) return set_err(AGP_EINVAL, "k must be positive, got %d", k);
@@ -1895,6 +1925,7 @@ int agp_index_search(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, 
 
 int agp_index_search_masked(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, int k, const int64_t* excl_offsets,
                             const int64_t* excl_ids, float* D, int64_t* I, int out_mem_kind) {
+    DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
     if (nq < 0) return set_err(AGP_EINVAL, "nq must be >= 0");
     if (k <= 0) return set_err(AGP_EINVAL, "k must be positive, got %d", k);
@@ -1949,6 +1980,7 @@ int agp_index_search_masked(agp_index* ix, int64_t nq, const float* x, int x_mem
 
 int agp_index_search_subset(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, int k, const int64_t* cand_offsets,
                             const int64_t* cand_ids, float* D, int64_t* I, int out_mem_kind) {
+    DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
     if (nq < 0) return set_err(AGP_EINVAL, "nq must be >= 0");
     if (k <= 0) return set_err(AGP_EINVAL, "k must be positive, got %d", k);
@@ -2008,6 +2040,7 @@ int agp_index_search_subset(agp_index* ix, int64_t nq, const float* x, int x_mem
 
 int agp_best_of_lists(int device, int64_t nq, int d, const float* xq, const float* rows, const int64_t* offsets, float* best_d,
                       int64_t* best_pos) {
+    DeviceRestore restore_device__;
     if (nq < 0 || d <= 0) return set_err(AGP_EINVAL, "bad nq or d");
     if (nq == 0) return 0;
     if (!xq || !offsets || !best_d || !best_pos) return set_err(AGP_EINVAL, "null pointer");
@@ -2057,6 +2090,7 @@ int agp_merge_topk(int device, void* stream, int64_t nq, int k, int n_lists, con
 
 int agp_merge_topk_metric(int device, void* stream, int64_t nq, int k, int n_lists, const float* D_lists, int64_t d_list_stride,
                           const int64_t* I_lists, int64_t i_list_stride, int64_t id_bound, int metric, float* D_out, int64_t* I_out) {
+    DeviceRestore restore_device__;
     if (metric != AGP_METRIC_L2 && metric != AGP_METRIC_INNER_PRODUCT) return set_err(AGP_EINVAL, "unknown metric %d", metric);
     if (k <= 0 || k > AGP_MAX_K) return set_err(AGP_EINVAL, "k=%d out of range 1..%d", k, AGP_MAX_K);
     if (nq < 0 || n_lists < 0) return set_err(AGP_EINVAL, "negative size");
@@ -2071,6 +2105,7 @@ int agp_merge_topk_metric(int device, void* stream, int64_t nq, int k, int n_lis
 
 int agp_recall_at_n(int device, void* stream_v, const int64_t* I, int mem_kind, int64_t nq, int k, const int64_t* pos_offsets,
                     const int64_t* pos_ids, const int* ns, int n_ns, int64_t* hit_counts) {
+    DeviceRestore restore_device__;
     if (!I || !pos_offsets || !ns || !hit_counts) return set_err(AGP_EINVAL, "null pointer");
     if (n_ns <= 0 || n_ns > 32) return set_err(AGP_EINVAL, "n_ns must be in 1..32");
     if (k <= 0 || nq < 0) return set_err(AGP_EINVAL, "bad k or nq");
@@ -2131,6 +2166,7 @@ int agp_recall_at_n(int device, void* stream_v, const int64_t* I, int mem_kind, 
 // N4: radius neighbours (sklearn NearestNeighbors.radius_neighbors restated on the GPU), two-phase CSR.
 static int radius_common(int device, int64_t n_db, int dim, const double* db, int64_t nq, const double* q, double radius, int64_t* counts,
                          const int64_t* offsets, int64_t* ids) {
+    DeviceRestore restore_device__;
     if (n_db < 0 || nq < 0) return set_err(AGP_EINVAL, "n_db and nq must be >= 0");
     if (dim < 1 || dim > 8) return set_err(AGP_EINVAL, "dim must be in 1..8, got %d", dim);
     if (!(radius >= 0.0)) return set_err(AGP_EINVAL, "radius must be >= 0");

@@ -34,6 +34,7 @@ def test_multi_device_index_equals_single(metric):
     Ds, Is = single.search(xq, 40)
     Ds1, Is1 = single.search(xq[:3], 10)             # nq < 20: difference-form path on every shard
     Dsk, Isk = single.search(xq[:50], 512)
+    current = torch.cuda.current_device()
     for devices in _device_sets():
         ix = cls(96, devices=devices)
         assert ix.device == devices[0]
@@ -61,6 +62,9 @@ def test_multi_device_index_equals_single(metric):
         Dr, Ir = ref.search(xq[:64], 5)
         np.testing.assert_array_equal(I2, Ir)
         np.testing.assert_array_equal(D2, Dr)
+        del ix
+        # the library switches devices while it works but hands the caller's current device back at every entry point
+        assert torch.cuda.current_device() == current
 
 
 def test_multi_device_index_through_the_reference_call_site(monkeypatch):
