@@ -1198,8 +1198,9 @@ int agp_index_create_multi(int d, int n_devices, const int* device_ids, int prec
     for (int g = 0; g < n_devices; ++g) {
         agp_index* ch = nullptr;
         int rc = agp_index_create_metric(d, device_ids[g], precision_mode, metric, &ch);
-        cudaEvent_t ev = nullptr;
-        if (rc == 0 && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) rc = set_err(AGP_ECUDA, "event creation failed");
+        cudaEvent_t ev = nullptr;      // recorded on the shard's stream: it has to live on the shard's device
+        if (rc == 0 && (cudaSetDevice(device_ids[g]) != cudaSuccess || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess))
+            rc = set_err(AGP_ECUDA, "event creation failed");
         if (rc != 0) {
             if (ch) agp_index_free(ch);
             agp_index_free(parent);
