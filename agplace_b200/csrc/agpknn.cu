@@ -413,6 +413,9 @@ struct agp_index {
     int64_t dev_rows = 0;                            // rows [0, dev_rows) are resident in xb (< ntotal only while lazy)
     int pipe_chunk = 0;                              // knob: queries per pipeline chunk (0 = automatic)
     int pipe_first = 0;                              // knob: two chunks, the first with this many queries (0 = automatic)
+    int pipe_piece_kb = 0;                           // knob: staging piece size in KB (0 = a quarter of the chunk, 2..8 MB)
+    int pipe_sched = 0;                              // knob: 1 = the round-2 chunk schedule (two chunks / whole waves), 0 = automatic
+    int pipe_cut[3] = {0, 0, 0};                     // knobs pipe_cut1..3: explicit chunk boundaries (ascending query indexes; 0 = unused)
     int pipe_min_kb = 512;                           // knob: host queries of at least this size take the staged path even as one chunk
     int screen_chunk = 0;                            // knob: queries per screen launch (0 = automatic)
     int screen_lockstep = -1;                        // knob: tiles between the meeting points of a full wave (0 = off, -1 = automatic)
@@ -1309,7 +1312,8 @@ int agp_index_set_knob(agp_index* ix, const char* name, int value) {
         {"screen_flags", &ix->kn.screen_flags}, {"screen_e", &ix->kn.screen_e}, {"screen_stages", &ix->kn.screen_stages},
         {"screen_sched", &ix->kn.screen_sched}, {"tc_e", &ix->kn.tc_e}, {"tc_rerank", &ix->kn.tc_rerank},
         {"tc_compact_sort", &ix->kn.tc_compact_sort}, {"tc_share_bound", &ix->kn.tc_share_bound}, {"cycle_counters", &ix->kn.cycle_counters},
-        {"pipe_chunk", &ix->pipe_chunk}, {"pipe_first", &ix->pipe_first}, {"pipe_min_kb", &ix->pipe_min_kb}, {"screen_chunk", &ix->screen_chunk}, {"screen_lockstep", &ix->screen_lockstep},
+        {"pipe_chunk", &ix->pipe_chunk}, {"pipe_first", &ix->pipe_first}, {"pipe_sched", &ix->pipe_sched}, {"pipe_piece_kb", &ix->pipe_piece_kb}, {"pipe_cut1", &ix->pipe_cut[0]}, {"pipe_cut2", &ix->pipe_cut[1]}, {"pipe_cut3", &ix->pipe_cut[2]},
+        {"pipe_min_kb", &ix->pipe_min_kb}, {"screen_chunk", &ix->screen_chunk}, {"screen_lockstep", &ix->screen_lockstep},
 #ifdef AGP_DEBUG_KNOBS
         {"skip_epi", &ix->kn.skip_epi}, {"skip_mma", &ix->kn.skip_mma},
 #endif
@@ -1656,20 +1660,64 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
     const int64_t wave = static_cast<int64_t>(worker(0)->num_sms / 2) * 2 * TC_BM;      // queries one wave of pair tiles covers
     const size_t moved = (x_host ? nq * row_in : 0) + (out_host ? nq * (row_d + row_i) : 0);
     const bool batched_path = ix->ntotal > 0 && nq >= kMaxSmallNq;
-    if (ix->pipe_first > 0) {
+    if (ix->pipe_cut[0] > 0) {
+        for (int c : ix->pipe_cut)
+            if (c > cuts.back() && c < nq) cuts.push_back(c);
+    } else if (ix->pipe_first > 0) {
         if (ix->pipe_first < nq) cuts.push_back(ix->pipe_first);
     } else if (ix->pipe_chunk > 0) {
         for (int64_t a = ix->pipe_chunk; a < nq; a += ix->pipe_chunk) cuts.push_back(a);
     } else if (batched_path && (moved >= (size_t(4) << 20) || multi)) {
-        if (nq >= 3 * wave) {
+        // Chunk sizes are counted in pair tiles (256 queries) and taken from the sizes the screen kernel splits evenly over
+        // the chip's 74 CTA pairs: 9 tiles x 8 database ranges, 18 x 4, 24 x 3, 37 x 2, 74 x 1 -- any other size leaves
+        // pairs idle in its last wave of work items (cfg2, numpy in / out: [10|20|20|rest] tiles 3.41 ms, [18|24|37] 2.85 ms).
+        const int64_t T = 2 * TC_BM;
+        const int64_t tq = (nq + T - 1) / T;
+        const agp_index* w0 = worker(0);
+        const int64_t ndb = (w0->ntotal + TC_BN - 1) / TC_BN;
+        const int clusters = std::max(1, w0->num_sms / 2);
+        // Which stage limits the pipeline?  Search time of the whole batch from the screen's own work decomposition (items of
+        // ndb / sp tiles + ~10 tiles of per-item overhead, ~4 us per 256 x 256 x 528 tile incl. the epilogue's share) against the
+        // host staging copy (~35 GB/s into the pinned ring).  Both are rough; they only pick the shape of the schedule.
+        const double t_tile = 4.0 * (w0->d_pad + 16) / 528.0;
+        const int64_t sp = std::max<int64_t>(1, std::min<int64_t>({clusters / std::max<int64_t>(tq, 1), ndb, 64}));
+        const double t_search = t_tile * static_cast<double>((tq * sp + clusters - 1) / clusters) * (static_cast<double>(ndb) / sp + 10.6) + 30.0;
+        const double t_copy = x_host ? static_cast<double>(nq) * row_in / 35e3 : 0.0;
+        if (ix->pipe_sched == 1) {                // the first round-2 schedule, kept for A/B runs
+            if (nq >= 3 * wave) {
+                for (int64_t a = wave; a < nq; a += wave) cuts.push_back(a);
+            } else if (nq >= 2048) {
+                const int64_t c1 = round_up(nq / 8, 256);
+                if (c1 > 0 && c1 < nq) cuts.push_back(c1);
+            }
+        } else if (nq >= 3 * wave) {
+            // large batch: one wave per chunk (what search_screen launches anyway); the first wave's host copy (~1 ms) is
+            // small next to the batch
             for (int64_t a = wave; a < nq; a += wave) cuts.push_back(a);
+        } else if (t_search < t_copy && nq >= 2048) {
+            // copy-bound (small databases: the reference's own shapes): the GPU waits for the host copy whatever we do, so
+            // what is exposed is the LAST chunk's search and D2H -- keep that one small: [3/4 | 1/4]
+            // (10 k x 256 database, 8000 queries: [1/8 | 7/8] 0.70 ms, one chunk 0.72 ms, cut near the middle 0.50 ms)
+            cuts.push_back(round_up(nq - nq / 4, 256));
+        } else if (nq > wave + wave / 4) {
+            // search-bound, more than one wave: the GPU starts after 1/8 wave of host copy, the chunks double (the host copy
+            // runs ~2x faster than the search), then whole waves (40 k queries x 100 k x 512 rows: 6.05 -> 5.14 ms)
+            const int64_t ramp[3] = {9 * T, 27 * T, 64 * T};
+            for (int64_t a : ramp) cuts.push_back(a);
+            for (int64_t a = ramp[2] + wave; a < nq; a += wave) cuts.push_back(a);
+            if (nq - cuts.back() < 9 * T && cuts.size() > 1) cuts.pop_back();      // no sliver at the end
+        } else if (tq >= 68) {
+            // search-bound, about one wave (cfg2: 79 tiles): [18 | 24 | rest >= 26 tiles] (cfg2 2.97 -> 2.85 ms, 18 k queries
+            // 3.2 -> 2.8 ms; below ~17 k queries the third launch costs what the earlier start gains)
+            cuts.push_back(18 * T);
+            cuts.push_back(42 * T);
         } else if (nq >= 2048) {
-            // mid-sized batch: two chunks.  A small first chunk lets the GPU start after 1/8 of the host copy; everything
-            // else stays one launch, because the screen kernel loses efficiency on small query batches (cfg2, numpy in /
-            // out: 2.99 ms with [2560 | 17440], 3.34 ms with three chunks, 4.6 ms unchunked)
+            // search-bound, less than a wave: two chunks.  A small first chunk lets the GPU start after 1/8 of the host copy;
+            // everything else stays one launch, because the screen kernel loses efficiency on small query batches
             const int64_t c1 = round_up(nq / 8, 256);
             if (c1 > 0 && c1 < nq) cuts.push_back(c1);
         }
+        if (cuts.size() > 1 && cuts.back() >= nq) cuts.pop_back();
     }
     cuts.push_back(nq);
     const int n_chunks = static_cast<int>(cuts.size()) - 1;
@@ -1803,8 +1851,13 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
         const size_t bytes = static_cast<size_t>(m) * row_in, off0 = static_cast<size_t>(a) * row_in;
         if (x_host) {
             const char* src = reinterpret_cast<const char*>(x) + off0;
-            for (size_t off = 0; off < bytes; off += (stage_in ? kStageChunk : bytes)) {
-                const size_t len = stage_in ? std::min(kStageChunk, bytes - off) : bytes;
+            // staging pieces: a quarter of the chunk (2..8 MB), so that the DMA of one piece runs beside the host copy of the
+            // next inside a chunk too (a one-piece chunk pays host copy + DMA back to back)
+            const size_t piece = !stage_in ? bytes
+                               : ix->pipe_piece_kb > 0 ? std::min(kStageChunk, static_cast<size_t>(ix->pipe_piece_kb) << 10)
+                                                       : std::min(kStageChunk, std::max(size_t(2) << 20, (bytes / 4 + 0x3ffff) & ~size_t(0x3ffff)));
+            for (size_t off = 0; off < bytes; off += piece) {
+                const size_t len = std::min(piece, bytes - off);
                 const void* from = src + off;
                 int b = 0;
                 if (stage_in) {

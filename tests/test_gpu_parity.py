@@ -572,6 +572,32 @@ def test_cuda_tensor_search_is_asynchronous():
     assert ok, msg
 
 
+@pytest.mark.parametrize("n,d,nq,k", [(20_000, 64, 40_000, 10),      # copy-bound: [3/4 | 1/4]
+                                      (60_000, 256, 19_000, 30),     # search-bound, about one wave: [18 | 24 | rest] tiles
+                                      (60_000, 256, 30_000, 30),     # search-bound, 1.6 waves: ramp [9 | 18 | 37] tiles + waves
+                                      (3_000, 512, 61_000, 5)])      # more than three waves: one wave per chunk
+def test_every_automatic_chunk_schedule_returns_the_device_path_bits(n, d, nq, k):
+    """The host pipeline picks its chunk schedule from the batch size and from which stage limits it (agpknn.cu:
+    search_host_pipelined); each regime, and the staging-piece and explicit-cut knobs, return the bits of one
+    device-resident search."""
+    import torch
+    import agplace_b200
+    rng = np.random.default_rng(n + nq)
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    xq = rng.standard_normal((nq, d)).astype(np.float32)
+    ix = agplace_b200.IndexFlatL2(d); ix.add(xb)
+    Dd, Id = ix.search(torch.from_numpy(xq).cuda(), k)
+    Dd, Id = Dd.cpu().numpy(), Id.cpu().numpy()
+    for knobs in ({}, {"pipe_sched": 1}, {"pipe_piece_kb": 1024}, {"pipe_cut1": 2304, "pipe_cut2": 6912, "pipe_cut3": nq - 1}):
+        for name, v in knobs.items():
+            ix.set_knob(name, v)
+        D, I = ix.search(xq, k)
+        for name in knobs:
+            ix.set_knob(name, 0)
+        np.testing.assert_array_equal(I, Id, err_msg=str(knobs))
+        np.testing.assert_array_equal(D, Dd, err_msg=str(knobs))
+
+
 @pytest.mark.parametrize("pinned", [False, True])
 def test_host_pipeline_returns_the_device_path_bits(pinned):
     """numpy in / numpy out goes through the chunked H2D | compute | D2H pipeline (agp_index_search with host buffers):
