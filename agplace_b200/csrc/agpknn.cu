@@ -365,6 +365,9 @@ struct Knobs {
 struct ShardChunk { int64_t local_start, delta; };      // rows >= local_start of a shard (up to the next record): global id = local row + delta
 
 struct agp_index {
+    // Calls on one index are serialised (faiss allows concurrent search() on one index; here concurrent callers take turns:
+    // the scratch buffers and streams belong to the call in flight).  Recursive: entry points forward to each other.
+    std::recursive_mutex mu;
     // Single-process multi-device index (agp_index_create_multi): the parent owns no rows; shards[g] is an ordinary
     // index on device g holding a contiguous slice of every add() batch.  Empty for a one-device index.
     std::vector<agp_index*> shards;
@@ -1040,6 +1043,8 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
 }
 
 // every entry point that touches an index starts here: device current, scratch pool bound to the index's stream
+#define LOCK(ix) std::lock_guard<std::recursive_mutex> index_lock__(const_cast<agp_index*>(ix)->mu)
+
 #define ENTER(ix)                          \
     do {                                   \
         CK(cudaSetDevice((ix)->device));   \
@@ -1292,6 +1297,7 @@ int agp_index_dim(const agp_index* ix) { return ix ? ix->d : -1; }
 int agp_index_set_stream(agp_index* ix, void* s, int use_own_stream) {
     DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    LOCK(ix);
     // a NULL cudaStream_t is the legacy default stream (what torch uses unless told otherwise)
     cudaStream_t ns = use_own_stream ? ix->own_stream : static_cast<cudaStream_t>(s);
     if (ns != ix->stream) {
@@ -1308,6 +1314,7 @@ int agp_index_set_stream(agp_index* ix, void* s, int use_own_stream) {
 
 int agp_index_set_knob(agp_index* ix, const char* name, int value) {
     if (!ix || !name) return set_err(AGP_EINVAL, "index or name is null");
+    LOCK(ix);
     struct { const char* n; int* v; } table[] = {
         {"screen_flags", &ix->kn.screen_flags}, {"screen_e", &ix->kn.screen_e}, {"screen_stages", &ix->kn.screen_stages},
         {"screen_sched", &ix->kn.screen_sched}, {"tc_e", &ix->kn.tc_e}, {"tc_rerank", &ix->kn.tc_rerank},
@@ -1330,6 +1337,7 @@ int agp_index_set_knob(agp_index* ix, const char* name, int value) {
 int agp_index_screen_probe(agp_index* ix, int64_t nq, const float* x, float* dis, float* band) {
     DeviceRestore restore_device__;
     if (!ix || !x || !dis || !band) return set_err(AGP_EINVAL, "null pointer");
+    LOCK(ix);
     if (!ix->screen || ix->ip || !ix->shards.empty())
         return set_err(AGP_EINVAL, "screen_probe needs a one-device L2 index in precision auto or fp16_screen");
     if (nq <= 0 || nq > 65536 || ix->ntotal <= 0) return set_err(AGP_EINVAL, "need 1 <= nq <= 65536 and a non-empty index");
@@ -1374,6 +1382,7 @@ int agp_index_screen_probe(agp_index* ix, int64_t nq, const float* x, float* dis
 
 int agp_index_set_id_base(agp_index* ix, int64_t b) {
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    LOCK(ix);
     ix->id_base = b;
     return 0;
 }
@@ -1381,6 +1390,7 @@ int agp_index_set_id_base(agp_index* ix, int64_t b) {
 int agp_index_set_profiling(agp_index* ix, int on) {
     DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    LOCK(ix);
     for (agp_index* ch : ix->shards) CKR(agp_index_set_profiling(ch, on));
     if (!on && ix->profile) prof_collect(ix);
     ix->profile = on != 0;
@@ -1390,6 +1400,7 @@ int agp_index_set_profiling(agp_index* ix, int on) {
 int agp_index_get_profile(agp_index* ix, double* ms, int64_t* launches, int reset) {
     DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    LOCK(ix);
     if (!ix->shards.empty()) return agp_index_get_profile(ix->shards[0], ms, launches, reset);      // shard 0 stands for all
     ENTER(ix);
     prof_collect(ix);
@@ -1403,6 +1414,7 @@ int agp_index_get_profile(agp_index* ix, double* ms, int64_t* launches, int rese
 int agp_index_get_profile_phases(agp_index* ix, double* ms, int64_t* launches, int reset) {
     DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    LOCK(ix);
     if (!ix->shards.empty()) return agp_index_get_profile_phases(ix->shards[0], ms, launches, reset);
     ENTER(ix);
     prof_collect(ix);
@@ -1417,6 +1429,7 @@ int agp_index_get_profile_phases(agp_index* ix, double* ms, int64_t* launches, i
 int agp_index_reserve(agp_index* ix, int64_t n) {
     DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    LOCK(ix);
     if (!ix->shards.empty()) {
         const int64_t G = static_cast<int64_t>(ix->shards.size());
         for (agp_index* ch : ix->shards) CKR(agp_index_reserve(ch, (n + G - 1) / G));
@@ -1429,6 +1442,7 @@ int agp_index_reserve(agp_index* ix, int64_t n) {
 int agp_index_reset(agp_index* ix) {
     DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    LOCK(ix);
     if (!ix->shards.empty()) {
         for (size_t g = 0; g < ix->shards.size(); ++g) {
             CKR(agp_index_reset(ix->shards[g]));
@@ -1457,6 +1471,7 @@ int agp_index_reset(agp_index* ix) {
 int agp_index_get_stats(const agp_index* ix, int64_t* screened_queries, int64_t* fallback_queries) {
     DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    LOCK(ix);
     if (!ix->shards.empty()) {      // sums over the shards (every shard screens every query)
         int64_t a = 0, b = 0;
         for (const agp_index* ch : ix->shards) {
@@ -1483,6 +1498,7 @@ int agp_index_get_stats(const agp_index* ix, int64_t* screened_queries, int64_t*
 int agp_index_add(agp_index* ix, int64_t n, const float* x, int mem_kind) {
     DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    LOCK(ix);
     if (n < 0) return set_err(AGP_EINVAL, "n must be >= 0");
     if (n == 0) return 0;
     if (!x) return set_err(AGP_EINVAL, "x is null");
@@ -1918,6 +1934,7 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
 int agp_index_search(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, int k, float* D, int64_t* I, int out_mem_kind) {
     DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    LOCK(ix);
     if (nq < 0) return set_err(AGP_EINVAL, "nq must be >= 0");
     if (k <= 0) return set_err(AGP_EINVAL, "k must be positive, got %d", k);
     if (k > AGP_MAX_K) return set_err(AGP_EINVAL, "k=%d exceeds AGP_MAX_K=%d", k, AGP_MAX_K);
@@ -1981,6 +1998,7 @@ int agp_index_search_masked(agp_index* ix, int64_t nq, const float* x, int x_mem
                             const int64_t* excl_ids, float* D, int64_t* I, int out_mem_kind) {
     DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    LOCK(ix);
     if (nq < 0) return set_err(AGP_EINVAL, "nq must be >= 0");
     if (k <= 0) return set_err(AGP_EINVAL, "k must be positive, got %d", k);
     if (nq == 0) return 0;
@@ -2036,6 +2054,7 @@ int agp_index_search_subset(agp_index* ix, int64_t nq, const float* x, int x_mem
                             const int64_t* cand_ids, float* D, int64_t* I, int out_mem_kind) {
     DeviceRestore restore_device__;
     if (!ix) return set_err(AGP_EINVAL, "index is null");
+    LOCK(ix);
     if (nq < 0) return set_err(AGP_EINVAL, "nq must be >= 0");
     if (k <= 0) return set_err(AGP_EINVAL, "k must be positive, got %d", k);
     if (k > AGP_MAX_K) return set_err(AGP_EINVAL, "k=%d exceeds AGP_MAX_K=%d", k, AGP_MAX_K);

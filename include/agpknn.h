@@ -11,8 +11,10 @@
  * thread-local message of the most recent failure.  There is no CPU fallback: without a usable
  * sm_100 device every call fails with AGP_ENODEV.
  *
- * Threading: calls on different indexes are independent; one index must not be used from two
- * threads at once (same rule as faiss add()).  Host-output calls return after their results have
+ * Threading: calls on different indexes are independent and run concurrently; calls on ONE index
+ * from several threads are serialised by a per-index lock (faiss allows concurrent search() on one
+ * index: the same code works here, the searches take turns); agp_index_free must not race with a
+ * call on the same index.  Host-output calls return after their results have
  * landed; device-in / device-out calls are asynchronous on the index's stream (no host synchronisation at all: the
  * screen's overflow fallback runs on the device).
  */
@@ -138,7 +140,9 @@ AGP_API int agp_index_get_stats(const agp_index* idx, int64_t* screened_queries,
 /* Development switches of one index (A/B variants of the screen kernel, register budgets, the instrumented build with
  * cycle counters).  The library reads NO environment variable on the launch path; every switch reachable here leaves
  * the results unchanged (tests/test_gpu_parity.py runs every variant and compares bits).  Result-changing bandwidth
- * probes (skip_epi, skip_mma) exist only in -DAGP_DEBUG_KNOBS builds.  Unknown names: AGP_EINVAL. */
+ * probes (skip_epi, skip_mma) exist only in -DAGP_DEBUG_KNOBS builds.  Unknown names: AGP_EINVAL.
+ * Host pipeline of agp_index_search: pipe_sched (1 = the two-chunk / whole-wave schedule), pipe_cut1..3 (explicit
+ * chunk boundaries in queries), pipe_chunk, pipe_first, pipe_piece_kb (staging piece size), pipe_min_kb. */
 AGP_API int agp_index_set_knob(agp_index* idx, const char* name, int value);
 
 /* Certification probe (no reference equivalent; SURVEY 5 "sanitizers/diagnostics"): runs the tensor-core screen kernel

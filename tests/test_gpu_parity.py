@@ -664,3 +664,36 @@ def test_lockstep_sweep_is_only_a_hint():
     D, I = multi.search(xq, k)
     np.testing.assert_array_equal(I, I0)
     np.testing.assert_array_equal(D, D0)
+
+
+def test_concurrent_calls_on_one_index_take_turns():
+    """faiss lets several threads search one index at the same time; the engine's scratch buffers and streams belong to the
+    call in flight, so the C ABI serialises the calls on one index (a per-index lock).  Host threads hammering ONE index
+    with different batch sizes (screen path, small-batch path, host pipeline) all get the single-threaded bits."""
+    import threading
+    import agplace_b200
+    rng = np.random.default_rng(67)
+    n, d = 30_000, 128
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    ix = agplace_b200.IndexFlatL2(d); ix.add(xb)
+    jobs = [(rng.standard_normal((nq, d)).astype(np.float32), k) for nq, k in ((1, 10), (7, 3), (300, 20), (2500, 50), (12_000, 10))]
+    want = [ix.search(xq, k) for xq, k in jobs]
+    errors = []
+
+    def worker(tag):
+        try:
+            for rep in range(6):
+                j = (tag + rep) % len(jobs)
+                D, I = ix.search(*jobs[j])
+                np.testing.assert_array_equal(I, want[j][1], err_msg=f"thread {tag} job {j}")
+                np.testing.assert_array_equal(D, want[j][0])
+        except Exception as e:      # noqa: BLE001 -- reported by the main thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(5)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+        assert not t.is_alive()
+    assert not errors, errors[0]

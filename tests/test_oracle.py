@@ -146,3 +146,28 @@ def test_oracle_reproduces_the_published_output_of_the_faiss_tutorial():
     np.testing.assert_array_equal(I[-5:], np.array(pub["search_I_last5"]))
     D5, I5 = orc.knn_fp32(xb[:5], xb, 4, path="blas")      # same answers through the expansion form
     np.testing.assert_array_equal(I5, np.array(pub["sanity_I"]))
+
+
+@pytest.mark.parametrize("nq,n,d,k", [(7, 900, 48, 5), (40, 2500, 64, 20), (64, 4000, 256, 100), (33, 700, 512, 50)])
+def test_oracle_agrees_with_scikit_learn_brute_force(nq, n, d, k):
+    """A third-party cross-check (not faiss, but an independently written exact k-NN that IS installed here and that the
+    reference also depends on -- datasets_ws_kitti360.py:613): sklearn's brute-force NearestNeighbors with the squared
+    euclidean metric returns the same neighbours as both of the oracle's code paths (ids equal except ties within 1e-5
+    relative, distances within 1e-4 relative: BASELINE.json's tolerances)."""
+    from sklearn.neighbors import NearestNeighbors
+    rng = np.random.default_rng(nq + n + d + k)
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    xq = rng.standard_normal((nq, d)).astype(np.float32)
+    nn = NearestNeighbors(n_neighbors=k, algorithm="brute", metric="sqeuclidean").fit(xb.astype(np.float64))
+    Ds, Is = nn.kneighbors(xq.astype(np.float64))
+    for path in ("seq", "blas"):
+        D, I = orc.knn_fp32(xq, xb, k, path=path)
+        ok, msg = orc.compare_knn(D, I, Ds.astype(np.float32), Is.astype(np.int64), xq=xq, xb=xb, abs_floor_eps=8 * 2.0 ** -24)
+        assert ok, f"{path}: {msg}"
+    # inner product: the same library's dot products, descending
+    Dip, Iip = orc.knn_ip_fp32(xq, xb, k)
+    P = xq.astype(np.float64) @ xb.astype(np.float64).T
+    order = np.argsort(-P, axis=1, kind="stable")[:, :k]
+    top = np.take_along_axis(P, order, axis=1)
+    assert np.allclose(Dip, top, rtol=1e-4, atol=1e-4)
+    assert (Iip == order).mean() > 0.999
