@@ -421,6 +421,7 @@ struct agp_index {
     int pipe_cut[3] = {0, 0, 0};                     // knobs pipe_cut1..3: explicit chunk boundaries (ascending query indexes; 0 = unused)
     int pipe_min_kb = 512;                           // knob: host queries of at least this size take the staged path even as one chunk
     int screen_chunk = 0;                            // knob: queries per screen launch (0 = automatic)
+    int screen_item_overhead = 0;                    // knob: per-item overhead of the remainder cost model in tenths of a tile (0 = default)
     int screen_lockstep = -1;                        // knob: tiles between the meeting points of a full wave (0 = off, -1 = automatic)
     Buf sync_ctr;
     int64_t stat_screened = 0;
@@ -911,16 +912,19 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         p.n_dbtiles = n_dbtiles;
         p.n_full_items = (p.n_ptiles / clusters) * clusters;
         const int rem_tiles = p.n_ptiles - p.n_full_items;
-        // remainder: database ranges per pair tile chosen to minimise waves x (range length + per-item overhead of
-        // ~3 tiles: query tile load, pipeline fill/drain, first compaction rounds)
+        // remainder: database ranges per pair tile chosen to minimise waves x (range length + per-item overhead)
         p.rem_splits = 1;
+        // per-item overhead in tiles (query tile load, pipeline fill / drain, the first compaction rounds of fresh lists):
+        // measured ~13 tiles at d = 512, < 12 at d = 256 (scripts/split_model_probe.py: with the earlier constant of 3 the
+        // model preferred many short items -- 16 pair tiles 0.69 -> 0.59 ms, 32 tiles 1.14 -> 0.98 ms, 63 tiles 1.91 -> 1.82 ms)
+        const double item_overhead = ix->screen_item_overhead > 0 ? ix->screen_item_overhead * 0.1 : std::min(14.0, 6.0 + ix->d_pad / 64.0);
         if (rem_tiles > 0) {
             double best_cost = 1e300;
             const int max_s = std::min(n_dbtiles, 64);      // 2 lists per range, finalize handles up to 256 lists
             for (int sp = 1; sp <= max_s; ++sp) {
                 const int64_t items = static_cast<int64_t>(rem_tiles) * sp;
                 const int64_t waves = (items + clusters - 1) / clusters;
-                const double cost = static_cast<double>(waves) * ((n_dbtiles + sp - 1) / sp + 3.0);
+                const double cost = static_cast<double>(waves) * ((n_dbtiles + sp - 1) / sp + item_overhead);
                 if (cost < best_cost * 0.999) { best_cost = cost; p.rem_splits = sp; }
             }
         }
@@ -1320,7 +1324,7 @@ int agp_index_set_knob(agp_index* ix, const char* name, int value) {
         {"screen_sched", &ix->kn.screen_sched}, {"tc_e", &ix->kn.tc_e}, {"tc_rerank", &ix->kn.tc_rerank},
         {"tc_compact_sort", &ix->kn.tc_compact_sort}, {"tc_share_bound", &ix->kn.tc_share_bound}, {"cycle_counters", &ix->kn.cycle_counters},
         {"pipe_chunk", &ix->pipe_chunk}, {"pipe_first", &ix->pipe_first}, {"pipe_sched", &ix->pipe_sched}, {"pipe_piece_kb", &ix->pipe_piece_kb}, {"pipe_cut1", &ix->pipe_cut[0]}, {"pipe_cut2", &ix->pipe_cut[1]}, {"pipe_cut3", &ix->pipe_cut[2]},
-        {"pipe_min_kb", &ix->pipe_min_kb}, {"screen_chunk", &ix->screen_chunk}, {"screen_lockstep", &ix->screen_lockstep},
+        {"pipe_min_kb", &ix->pipe_min_kb}, {"screen_chunk", &ix->screen_chunk}, {"screen_lockstep", &ix->screen_lockstep}, {"screen_item_overhead", &ix->screen_item_overhead},
 #ifdef AGP_DEBUG_KNOBS
         {"skip_epi", &ix->kn.skip_epi}, {"skip_mma", &ix->kn.skip_mma},
 #endif
