@@ -380,7 +380,7 @@ struct agp_index {
     Knobs kn;
     float* probe_dump = nullptr;      // agp_index_screen_probe: device buffer [nq][probe_ld] for dis~
     int64_t probe_ld = 0;
-    int d = 0, d_pad = 0, device = 0, mode = 0, num_sms = 0;
+    int d = 0, d_pad = 0, device = 0, mode = 0, num_sms = 0, l2_bytes = 0;
     int ip = 0;                   // 1: inner-product index (faiss.IndexFlatIP); 0: squared L2
     int64_t ntotal = 0, cap = 0, id_base = 0;
     float *xb = nullptr, *yn = nullptr, *wx = nullptr;
@@ -421,6 +421,7 @@ struct agp_index {
     int pipe_cut[3] = {0, 0, 0};                     // knobs pipe_cut1..3: explicit chunk boundaries (ascending query indexes; 0 = unused)
     int pipe_min_kb = 512;                           // knob: host queries of at least this size take the staged path even as one chunk
     int screen_chunk = 0;                            // knob: queries per screen launch (0 = automatic)
+    int screen_balanced = -1;                        // knob: balanced remainder decomposition (-1 = when the cost model prefers it, 0 = never, 1 = always)
     int screen_item_overhead = 0;                    // knob: per-item overhead of the remainder cost model in tenths of a tile (0 = default)
     int screen_lockstep = -1;                        // knob: tiles between the meeting points of a full wave (0 = off, -1 = automatic)
     Buf sync_ctr;
@@ -929,14 +930,46 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
             }
         }
         p.rem_tiles = rem_tiles;
-        p.list_splits = p.rem_splits;
         p.n_items = p.n_full_items + rem_tiles * p.rem_splits;
+        // Balanced alternative: equal ranges leave pairs idle whenever rem_tiles x splits is not a multiple of the pair count
+        // (63 pair tiles: one wave of 63 long items, 11 pairs idle).  Cut the remainder's whole (pair tile, database tile)
+        // space into one contiguous segment per pair instead -- segments cross pair-tile boundaries, so a pair runs W >= 1
+        // pieces of unequal length and a tile is covered by up to S ranges (its lists) -- when the model says it is cheaper
+        // AND the plane stays in L2: the pairs then sit at 74 different places of the plane instead of sweeping it together,
+        // so a plane larger than about half the L2 comes out of HBM once per pair tile (measured: 200 k x 64 rows, 51 MB plane,
+        // 32 / 63 pair tiles of queries 0.71 -> 0.58 / 1.22 -> 0.97 ms; 100 k x 512 rows, 115 MB, 63 tiles 1.70 -> 1.84 ms;
+        // 1 M x 128 rows, 384 MB, 63 tiles 4.40 -> 4.72 ms -- profiles/r2_split_cost_model.log).
+        p.balanced = 0;
+        const bool plane_in_l2 = static_cast<size_t>(n_dbtiles) * TC_BN * ld * 2 * 2 <= static_cast<size_t>(ix->l2_bytes);
+        if (rem_tiles > 0 && (ix->screen_balanced > 0 || (ix->screen_balanced < 0 && plane_in_l2))) {
+            const int64_t L = static_cast<int64_t>(rem_tiles) * n_dbtiles;
+            int W = 0, S = 0;
+            for (int c = 0; c < clusters; ++c) {
+                const int64_t b0 = sc_seg_begin(L, clusters, c), b1 = sc_seg_begin(L, clusters, c + 1);
+                if (b0 < b1) W = std::max(W, static_cast<int>((b1 - 1) / n_dbtiles - b0 / n_dbtiles) + 1);
+            }
+            for (int t = 0; t < rem_tiles; ++t) {
+                const int64_t tb = static_cast<int64_t>(t) * n_dbtiles;
+                S = std::max(S, sc_first_seg(L, clusters, tb + n_dbtiles - 1) - sc_first_seg(L, clusters, tb) + 1);
+            }
+            const double cost_bal = static_cast<double>((L + clusters - 1) / clusters) + W * item_overhead;
+            const int64_t items_u = static_cast<int64_t>(rem_tiles) * p.rem_splits;
+            const double cost_uni = static_cast<double>((items_u + clusters - 1) / clusters) * ((n_dbtiles + p.rem_splits - 1) / p.rem_splits + item_overhead);
+            if (L >= clusters && S <= 64 && (ix->screen_balanced > 0 || cost_bal < 0.97 * cost_uni)) {
+                p.balanced = 1;
+                p.rem_splits = S;
+                p.n_items = p.n_full_items + W * clusters;
+            }
+        }
+        p.list_splits = p.rem_splits;
         p.q_resident = resident;
         p.n_stages = n_stages;
         // compaction rounds after tiles 1, m, m^2, ... (quarters: 8 = x2, 12 = x3).  Long sweeps: doubling (a tighter bound
         // admits less); sweeps of <= 64 tiles (small databases, heavily split remainders): x3 -- a round costs as much as
         // ~3-5 tiles there (cfg1 0.054 -> 0.048 ms, cfg3 0.132 -> 0.127 ms; cfg2 is 10 % slower with x3)
-        const int tiles_per_item = p.n_full_items > 0 ? n_dbtiles : (n_dbtiles + p.rem_splits - 1) / p.rem_splits;
+        const int tiles_per_item = p.n_full_items > 0 ? n_dbtiles
+                                   : p.balanced ? static_cast<int>((static_cast<int64_t>(rem_tiles) * n_dbtiles + clusters - 1) / clusters)
+                                                : (n_dbtiles + p.rem_splits - 1) / p.rem_splits;
         p.sched_mul = ix->kn.screen_sched >= 5 ? ix->kn.screen_sched : (tiles_per_item <= 64 ? 12 : 8);
         p.flags = ix->kn.screen_flags;
         p.ip = ix->ip;
@@ -1140,15 +1173,16 @@ int agp_index_create_metric(int d, int device, int precision_mode, int metric, a
     }
     if (device < 0 || device >= ndev) return set_err(AGP_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
     // device attributes are cached: the mining loop constructs thousands of indexes (cudaGetDeviceProperties is slow)
-    static int s_major[16] = {0}, s_minor[16] = {0}, s_sms[16] = {0};
-    int major = 0, minor = 0, sms = 0;
+    static int s_major[16] = {0}, s_minor[16] = {0}, s_sms[16] = {0}, s_l2[16] = {0};
+    int major = 0, minor = 0, sms = 0, l2 = 0;
     if (device < 16 && s_sms[device] > 0) {
-        major = s_major[device]; minor = s_minor[device]; sms = s_sms[device];
+        major = s_major[device]; minor = s_minor[device]; sms = s_sms[device]; l2 = s_l2[device];
     } else {
         CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
         CK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-        if (device < 16) { s_major[device] = major; s_minor[device] = minor; s_sms[device] = sms; }
+        CK(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, device));
+        if (device < 16) { s_major[device] = major; s_minor[device] = minor; s_sms[device] = sms; s_l2[device] = l2; }
     }
     if (major != 10) return set_err(AGP_ENODEV, "device %d is sm_%d%d; agpknn is built for sm_100a only", device, major, minor);
     CK(cudaSetDevice(device));
@@ -1160,6 +1194,7 @@ int agp_index_create_metric(int d, int device, int precision_mode, int metric, a
     ix->mode = precision_mode;
     ix->ip = metric == AGP_METRIC_INNER_PRODUCT ? 1 : 0;
     ix->num_sms = sms;
+    ix->l2_bytes = l2;
     ix->planes = (precision_mode == AGP_PRECISION_3XTF32 || precision_mode == AGP_PRECISION_3XFP16);
     ix->screen = (precision_mode == AGP_PRECISION_AUTO || precision_mode == AGP_PRECISION_FP16_SCREEN);
     ix->kind = (precision_mode == AGP_PRECISION_3XTF32) ? KIND_TF32 : KIND_F16;
@@ -1324,7 +1359,7 @@ int agp_index_set_knob(agp_index* ix, const char* name, int value) {
         {"screen_sched", &ix->kn.screen_sched}, {"tc_e", &ix->kn.tc_e}, {"tc_rerank", &ix->kn.tc_rerank},
         {"tc_compact_sort", &ix->kn.tc_compact_sort}, {"tc_share_bound", &ix->kn.tc_share_bound}, {"cycle_counters", &ix->kn.cycle_counters},
         {"pipe_chunk", &ix->pipe_chunk}, {"pipe_first", &ix->pipe_first}, {"pipe_sched", &ix->pipe_sched}, {"pipe_piece_kb", &ix->pipe_piece_kb}, {"pipe_cut1", &ix->pipe_cut[0]}, {"pipe_cut2", &ix->pipe_cut[1]}, {"pipe_cut3", &ix->pipe_cut[2]},
-        {"pipe_min_kb", &ix->pipe_min_kb}, {"screen_chunk", &ix->screen_chunk}, {"screen_lockstep", &ix->screen_lockstep}, {"screen_item_overhead", &ix->screen_item_overhead},
+        {"pipe_min_kb", &ix->pipe_min_kb}, {"screen_chunk", &ix->screen_chunk}, {"screen_lockstep", &ix->screen_lockstep}, {"screen_item_overhead", &ix->screen_item_overhead}, {"screen_balanced", &ix->screen_balanced},
 #ifdef AGP_DEBUG_KNOBS
         {"skip_epi", &ix->kn.skip_epi}, {"skip_mma", &ix->kn.skip_mma},
 #endif

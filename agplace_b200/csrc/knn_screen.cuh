@@ -44,14 +44,30 @@ constexpr int SC_CHUNK_BYTES = TC_BM * TC_KCHUNK_BYTES;      // 128 rows x 128 B
 constexpr int SC_MAX_STAGES = 8;
 
 struct ScItem {
-    int pt, split, t0, t1;
+    int pt, split, t0, t1;      // t0 >= t1: an empty item (balanced remainder: this pair's segment has fewer pieces than others)
 };
-__device__ __forceinline__ ScItem sc_decode_item(const ScreenParams& p, int item) {
+__device__ __forceinline__ ScItem sc_decode_item(const ScreenParams& p, int item, int n_clusters) {
     ScItem it;
     int nsp = 1;
     if (item < p.n_full_items) {
         it.pt = item;
         it.split = 0;
+    } else if (p.balanced) {
+        const int r = item - p.n_full_items;
+        const int j = r / n_clusters, c = r - j * n_clusters;      // piece j of segment c (n_full_items is a multiple of n_clusters)
+        const int64_t L = static_cast<int64_t>(p.rem_tiles) * p.n_dbtiles;
+        const int64_t b0 = sc_seg_begin(L, n_clusters, c), b1 = sc_seg_begin(L, n_clusters, c + 1);
+        const int64_t T = b0 / p.n_dbtiles + j;
+        const int64_t tb = T * p.n_dbtiles;
+        it.pt = p.n_full_items + static_cast<int>(T);
+        it.split = 0;
+        it.t0 = it.t1 = 0;
+        if (b0 < b1 && tb < b1) {
+            it.t0 = static_cast<int>((b0 > tb ? b0 : tb) - tb);
+            it.t1 = static_cast<int>((b1 < tb + p.n_dbtiles ? b1 : tb + p.n_dbtiles) - tb);
+            it.split = c - sc_first_seg(L, n_clusters, tb);
+        }
+        return it;
     } else {
         // range-major: the ranges of one pair tile are spread over successive waves, so every later range starts from
         // the bound gthr[] the earlier ones have published instead of rediscovering it (concurrent items also stream
@@ -333,7 +349,8 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             uint32_t phase = 0, qphase = 0;
             const uint32_t qfull_leader = mapa_u32(smem_u32(qfull), 0);
             for (int item = cluster_id; item < n_items; item += n_clusters) {
-                const ScItem it = sc_decode_item(p, item);
+                const ScItem it = sc_decode_item(p, item, n_clusters);
+                if (it.t0 >= it.t1) continue;      // empty piece: all three roles skip it, no barrier is touched
                 const int qrow0 = (it.pt * 2 + static_cast<int>(rank)) * TC_BM;
                 if (p.q_resident) {
                     mbar_wait(qempty, qphase ^ 1);
@@ -388,7 +405,8 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             uint32_t acc_phase = 0;
             long long w_full = 0, w_tempty = 0, t_begin = dbg_on ? clock64() : 0;
             for (int item = cluster_id; item < n_items; item += n_clusters) {
-                const ScItem it = sc_decode_item(p, item);
+                const ScItem it = sc_decode_item(p, item, n_clusters);
+                if (it.t0 >= it.t1) continue;
                 if (p.q_resident) {
                     mbar_wait(qfull, qphase);
                     qphase ^= 1;
@@ -452,7 +470,8 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         tempty_leader[0] = mapa_u32(smem_u32(&tempty[0]), 0);
         tempty_leader[1] = mapa_u32(smem_u32(&tempty[1]), 0);
         for (int item = cluster_id; item < n_items; item += n_clusters) {
-            const ScItem it = sc_decode_item(p, item);
+            const ScItem it = sc_decode_item(p, item, n_clusters);
+            if (it.t0 >= it.t1) continue;
             const int qt = it.pt * 2 + static_cast<int>(rank);
             const int q = qt * TC_BM + g * 32 + lane;
             const float band2 = q < p.nq ? 2.f * screen_band(__ldg(p.qn + q), __ldg(p.dq + q), ymax2, dymax, sy, p.d_pad) : inf;

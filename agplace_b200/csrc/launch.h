@@ -41,6 +41,15 @@ struct TcParams {
     uint32_t* gthr;         // [nq] shared pruning bound (fp32 bits, +inf initially); nullptr disables sharing
 };
 
+// Balanced remainder of the screen (ScreenParams::balanced): the rem_tiles x n_dbtiles tile space, pair-tile major, is cut
+// into n_seg equal contiguous segments, segment c = [c L / n_seg, (c + 1) L / n_seg).  Piece j of a segment = its
+// intersection with the j-th pair tile it touches.  Shared by the kernel's item decoder and the host's sizing.
+__host__ __device__ inline int64_t sc_seg_begin(int64_t L, int n_seg, int c) { return static_cast<int64_t>(c) * L / n_seg; }
+// the segment that contains tile-space position pos (0 <= pos < L): smallest c with seg_begin(c + 1) > pos
+__host__ __device__ inline int sc_first_seg(int64_t L, int n_seg, int64_t pos) {
+    return static_cast<int>(((pos + 1) * n_seg + L - 1) / L) - 1;
+}
+
 // Single-pass certified screen (knn_screen.cuh): one fp16 plane per operand, CTA pairs (cta_group::2).
 struct ScreenParams {
     int nq;
@@ -50,6 +59,8 @@ struct ScreenParams {
     int n_full_items;       // pair tiles swept unsplit (multiple of the number of clusters)
     int rem_splits;         // database ranges each remaining pair tile is split into
     int rem_tiles;          // pair tiles in the split remainder
+    int balanced;           // 1: the remainder's (pair tile, database tile) space is cut into one contiguous segment per CTA pair
+                            //    (segments cross pair-tile boundaries: items of unequal length, rem_splits = most ranges any tile gets)
     int list_splits;        // candidate lists are indexed [q][list_splits][2]
     int n_items;
     int n_dbtiles;

@@ -1,6 +1,6 @@
 """Development aid: the remainder cost model of search_screen (waves x (range + per-item overhead)) -- device-resident
 search time over batch sizes for several values of the overhead constant (knob screen_item_overhead, tenths of a tile).
-    python scripts/split_model_probe.py [reps]"""
+    python scripts/split_model_probe.py [reps] [balanced|overhead]"""
 import json
 import sys
 
@@ -12,6 +12,7 @@ import torch
 import agplace_b200 as agp
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+mode = sys.argv[2] if len(sys.argv) > 2 else "balanced"
 rng = np.random.default_rng(2)
 
 
@@ -44,17 +45,21 @@ for name, n, d, k, sizes in (("100kx512 k=50", 100000, 512, 50, [1000, 2048, 256
         xq = torch.from_numpy(unit(nq, d)).cuda()
         D0, I0 = ix.search(xq, k)
         res = {"nq": nq, "tiles": -(-nq // 256)}
-        variants = (30, 0)          # the earlier constant (3 tiles) vs the automatic one; interleaved: the clock drifts under load
+        # interleaved A/B (the clock drifts under load): mode "overhead" = the earlier per-item constant (3 tiles) vs the
+        # automatic one; mode "balanced" = equal ranges only (screen_balanced = 0) vs automatic (balanced when cheaper)
+        knob, variants, labels = (("screen_item_overhead", (30, 0), {30: "c0=3", 0: "auto"}) if mode == "overhead" else
+                                  ("screen_balanced", (0, -1), {0: "equal ranges", -1: "auto"}))
         best = {v: 1e9 for v in variants}
         for rnd in range(max(2, reps // 4)):
             for ov in variants if rnd % 2 == 0 else variants[::-1]:
-                ix.set_knob("screen_item_overhead", ov)
+                ix.set_knob(knob, ov)
                 if rnd == 0:
                     D, I = ix.search(xq, k)
                     assert torch.equal(I, I0) and torch.equal(D, D0), (name, nq, ov)
                     timed(ix, xq, k, 2)
                 best[ov] = min(best[ov], timed(ix, xq, k))
-        res.update({("c0=3" if ov else "auto"): round(best[ov], 4) for ov in variants})
+        res.update({labels[ov]: round(best[ov], 4) for ov in variants})
         ix.set_knob("screen_item_overhead", 0)
+        ix.set_knob("screen_balanced", -1)
         print(json.dumps({name: res}), flush=True)
     del ix

@@ -697,3 +697,37 @@ def test_concurrent_calls_on_one_index_take_turns():
         t.join(timeout=120)
         assert not t.is_alive()
     assert not errors, errors[0]
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(12_000, 64, 300, 10),        # 2 pair tiles x 47 database tiles over 74 pairs: segments of 1-2 tiles
+                                      (5_000, 64, 5_000, 10),       # 20 x 20
+                                      (30_000, 128, 16_128, 50),    # 63 x 118: the case equal ranges serve worst
+                                      (30_000, 128, 10_240, 1),     # 40 x 118
+                                      (70_000, 64, 24_000, 100),    # one full wave + 20 tiles of remainder
+                                      (9_000, 576, 4_200, 20),      # d_pad > 512: queries streamed with the database
+                                      (300, 32, 2_100, 300)])       # 2 database tiles, k > 256 (1024-slot lists)
+def test_balanced_remainder_returns_the_bits_of_equal_ranges(n, d, nq, k):
+    """The remainder of a batch (pair tiles beyond whole waves) is either split into equal database ranges per pair tile or
+    cut into one contiguous segment per CTA pair that crosses pair-tile boundaries (ScreenParams::balanced).  The exact
+    finish makes the result independent of the decomposition: forced on, forced off and automatic return the same bits,
+    and those equal the oracle's neighbours."""
+    import torch
+    import agplace_b200
+    rng = np.random.default_rng(n + nq + k)
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    xq = rng.standard_normal((nq, d)).astype(np.float32)
+    ix = agplace_b200.IndexFlatL2(d, precision="fp16_screen"); ix.add(xb)
+    xq_dev = torch.from_numpy(xq).cuda()
+    out = {}
+    for mode in (0, 1, -1):
+        ix.set_knob("screen_balanced", mode)
+        D, I = ix.search(xq_dev, k)
+        out[mode] = (D.cpu().numpy(), I.cpu().numpy())
+    for mode in (1, -1):
+        np.testing.assert_array_equal(out[mode][1], out[0][1], err_msg=f"screen_balanced={mode}")
+        np.testing.assert_array_equal(out[mode][0], out[0][0], err_msg=f"screen_balanced={mode}")
+    sample = np.arange(0, nq, max(1, nq // 200))
+    Dr, Ir = orc.knn_fp32(xq[sample], xb, k)
+    ok, msg = orc.compare_knn(out[1][0][sample], out[1][1][sample], Dr, Ir, xq=xq[sample], xb=xb, abs_floor_eps=32 * 2.0 ** -24)
+    assert ok, msg
+    assert ix.get_stats()[1] == 0          # nothing went through the exact fallback
