@@ -35,6 +35,12 @@ for (n, nq, d, k) in [(520, 33, 513, 5), (700, 260, 1024, 50), (400, 40, 4096, 2
     xb, xq = data(n, nq, d)
     ix = agp.IndexFlatL2(d, precision="fp16_screen"); ix.add(xb)
     check(f"screen streamed d={d}", *ix.search(xq, k), *orc.knn_fp32(xq, xb, k), xq, xb)
+# balanced remainder (segments of the tile space per CTA pair, pieces that cross pair-tile boundaries, empty pieces)
+for (n, nq, d, k) in [(12000, 300, 64, 10), (5000, 1300, 128, 20), (2600, 700, 576, 5)]:
+    xb, xq = data(n, nq, d)
+    ix = agp.IndexFlatL2(d, precision="fp16_screen"); ix.add(xb)
+    ix.set_knob("screen_balanced", 1)
+    check(f"screen balanced d={d}", *ix.search(xq, k), *orc.knn_fp32(xq, xb, k), xq, xb)
 # overflow fallback (device-side exact pass): mass duplicates
 xb, xq = data(900, 50, 64)
 xb = xb[rng.integers(0, 3, 900)]
