@@ -61,7 +61,7 @@ def run(budget=120.0, seed=0):
                 rows = np.concatenate([rows, x])
                 desc += f" | add {n}"
             elif op < 0.93:
-                nq = int(rng.choice([1, 2, 19, 20, 33, 257, 700, 3000]))
+                nq = int(rng.choice([1, 2, 19, 20, 33, 257, 700, 3000] + ([5000, 9000] if d <= 256 else [])))
                 k = int(rng.choice([1, 5, 10, 50, 77, 100, 256, 300, 512]))
                 xq = make(nq, d, regime)
                 how = rng.random()
