@@ -85,14 +85,16 @@ class _PeerExchange:
         self.n += 1
         return s, d_bytes
 
-    def push(self, s, d_bytes, a, k, D_loc, I_loc):
-        """Rows [a, a + m) of this rank's lists -> row ``rank`` of slot ``s`` on every rank (current stream, copy engines)."""
+    def push(self, s, d_bytes, a, k, D_loc, I_loc, dst=None):
+        """Rows [a, a + m) of this rank's lists -> row ``rank`` of slot ``s`` on every rank, or only on rank ``dst``
+        (current stream, copy engines)."""
         import torch
         m_k = D_loc.numel()
         Db = D_loc.reshape(-1).view(torch.uint8)
         Ib = I_loc.reshape(-1).view(torch.uint8)
-        for off in range(self.world):                      # start with myself, then the ring: spreads the link load
-            row = self.peers[(self.rank + off) % self.world][s, self.rank]
+        targets = [(self.rank + off) % self.world for off in range(self.world)] if dst is None else [dst]
+        for peer in targets:                               # start with myself, then the ring: spreads the link load
+            row = self.peers[peer][s, self.rank]
             row[a * k * 4: a * k * 4 + m_k * 4].copy_(Db, non_blocking=True)
             row[d_bytes + a * k * 8: d_bytes + a * k * 8 + m_k * 8].copy_(Ib, non_blocking=True)
 
@@ -222,10 +224,13 @@ class ShardedIndexFlatL2:
         which = torch.searchsorted(starts, I_local.clamp(min=0), right=True) - 1
         return torch.where(I_local < 0, I_local, I_local + gbase[which.clamp(min=0)])
 
-    def search(self, x, k, *, params=None, D=None, I=None, gather=True):
+    def search(self, x, k, *, params=None, D=None, I=None, gather=True, dst=None):
         """``gather=False`` (query-split only): return just this rank's slice of the results -- rows
         ``shard_bounds(nq, world)[rank]`` of ``(D, I)`` -- and skip the all-gather; the results then stay
-        partitioned by query like the work was (no collective on the data path)."""
+        partitioned by query like the work was (no collective on the data path).
+        ``dst=r`` (row-sharded only; like ``torch.distributed.gather``): only rank ``r`` receives ``(D, I)``, every other
+        rank returns ``(None, None)`` -- the per-shard lists travel to rank ``r`` alone, only that rank merges and copies
+        the result to its host (the reference evaluates in ONE process: test.py:27-32 is called from the training process)."""
         import torch
         import torch.distributed as dist
         nq, d = x.shape
@@ -239,14 +244,17 @@ class ShardedIndexFlatL2:
             xs = x[lo:hi]
         else:
             xs = x
+        if dst is not None:
+            assert self.shard == "db" and D is None and I is None and 0 <= int(dst) < self.world
+            dst = int(dst)
         base_applied = self._engine_applies_base()
         if hasattr(self.local, "set_id_base"):
             self.local.set_id_base(self._chunks[0][1] if base_applied else 0)
         native = self.shard == "db" and isinstance(self.local, IndexFlatL2) and self._merge is _cuda_merge and torch.cuda.is_available()
         if native and as_numpy and D is None and I is None and nq * d * 4 >= self.PIPELINE_MIN_BYTES:
-            return self._search_host_pipelined(np.ascontiguousarray(x, dtype=np.float32), k, base_applied)
+            return self._search_host_pipelined(np.ascontiguousarray(x, dtype=np.float32), k, base_applied, dst)
         if native and _is_torch(x) and x.is_cuda and D is None and I is None and nq > self.PIPELINE_CHUNK + self.PIPELINE_CHUNK // 4:
-            return self._search_device_chunked(x, k, base_applied)
+            return self._search_device_chunked(x, k, base_applied, dst)
         if isinstance(self.local, IndexFlatL2) and not (_is_torch(xs) and xs.is_cuda) and xs.shape[0]:
             # host queries: one H2D copy, then everything (search, exchange, merge) stays on the GPU
             xh = xs if _is_torch(xs) else torch.from_numpy(np.ascontiguousarray(xs, dtype=np.float32))
@@ -297,6 +305,8 @@ class ShardedIndexFlatL2:
             # int64 view must start 8-byte aligned: d_bytes is a multiple of 8
             I_lists = recv.view(torch.int64)[d_bytes // 8:]
             id_bound = self._ntotal
+            if dst is not None and self.rank != dst:
+                return None, None
             with self._phase("merge"):
                 if self._metric == METRIC_L2:
                     Dg, Ig = self._merge(D_lists, stride // 4, I_lists, stride // 8, nq, k, self.world, id_bound)
@@ -375,7 +385,7 @@ class ShardedIndexFlatL2:
         return _cuda_merge(flat.view(torch.float32), stride // 4, flat.view(torch.int64)[d_bytes // 8:], stride // 8, nq, k, self.world,
                            self._ntotal, self._metric, out=out)
 
-    def _search_device_chunked(self, x, k, base_applied):
+    def _search_device_chunked(self, x, k, base_applied, dst=None):
         """CUDA queries in, CUDA results out, one wave of query tiles at a time: while the (persistent, SM-filling) screen
         kernel of chunk c + 1 runs on the main stream, the lists of chunk c travel to every rank through peer memory on a
         second stream (copy engines only); one barrier + one merge launch after the last chunk."""
@@ -392,9 +402,11 @@ class ShardedIndexFlatL2:
         if ex is None:                                    # no peer memory here: one NCCL all-gather + merge at the end
             with self._phase("local_search"):
                 D_loc, I_loc = self.local.search(x, k)
-            return self._exchange_and_merge(D_loc, self._to_global(I_loc, base_applied), nq, k)
-        D = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        I = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            out = self._exchange_and_merge(D_loc, self._to_global(I_loc, base_applied), nq, k)
+            return out if dst is None or self.rank == dst else (None, None)
+        mine = dst is None or self.rank == dst
+        D = torch.empty((nq, k), dtype=torch.float32, device=dev) if mine else None
+        I = torch.empty((nq, k), dtype=torch.int64, device=dev) if mine else None
         slot_id, d_bytes = ex.begin(nq, k)
         comm.wait_stream(main)
         for a in range(0, nq, chunk):
@@ -405,16 +417,17 @@ class ShardedIndexFlatL2:
             ev = torch.cuda.Event(); ev.record(main)
             with torch.cuda.stream(comm):
                 comm.wait_event(ev)
-                ex.push(slot_id, d_bytes, a, k, D_loc, I_loc)
+                ex.push(slot_id, d_bytes, a, k, D_loc, I_loc, dst)
             D_loc.record_stream(comm); I_loc.record_stream(comm)
         main.wait_stream(comm)
         with self._phase("exchange_barrier"):
             slot = ex.finish(slot_id)
-        with self._phase("merge"):
-            self._merge_slot(slot, d_bytes, nq, k, (D, I))
+        if mine:
+            with self._phase("merge"):
+                self._merge_slot(slot, d_bytes, nq, k, (D, I))
         return D, I
 
-    def _search_host_pipelined(self, x, k, base_applied):
+    def _search_host_pipelined(self, x, k, base_applied, dst=None):
         """numpy in / numpy out on every rank, as a pipeline over query chunks: host copy into a pinned buffer + H2D
         (copy stream) | local search + all-gather + merge (compute stream; nothing in it synchronises the host) | D2H
         into the pinned result arrays (copy-out stream).  Every rank issues the same sequence of collectives."""
@@ -429,10 +442,11 @@ class ShardedIndexFlatL2:
         chunk = self.PIPELINE_CHUNK
         first = max(256, chunk // 4)                    # a short first chunk: the GPU starts after a quarter-wave of host copy
         cuts = [0] + list(range(first, nq, chunk)) + [nq] if nq > first + chunk // 2 else [0, nq]
-        D = _result_array((nq, k), np.float32)
-        I = _result_array((nq, k), np.int64)
-        Dt, It = torch.from_numpy(D), torch.from_numpy(I)
-        pinned_out = Dt.is_pinned() and It.is_pinned()
+        mine = dst is None or self.rank == dst
+        D = _result_array((nq, k), np.float32) if mine else None
+        I = _result_array((nq, k), np.int64) if mine else None
+        Dt, It = (torch.from_numpy(D), torch.from_numpy(I)) if mine else (None, None)
+        pinned_out = mine and Dt.is_pinned() and It.is_pinned()
         xt = torch.from_numpy(x)
         xq_dev = torch.empty((nq, self.d), dtype=torch.float32, device=dev)
         stage_ev = [None, None]
@@ -461,10 +475,12 @@ class ShardedIndexFlatL2:
                 ev = torch.cuda.Event(); ev.record(main)
                 with torch.cuda.stream(self._s_out):
                     self._s_out.wait_event(ev)
-                    ex.push(slot_id, d_bytes, a, k, D_loc, I_loc)
+                    ex.push(slot_id, d_bytes, a, k, D_loc, I_loc, dst)
                 D_loc.record_stream(self._s_out); I_loc.record_stream(self._s_out)
                 continue
             Dg, Ig = self._exchange_and_merge(D_loc, I_loc, b - a, k)      # NCCL fallback: all-gather + merge per chunk, in line
+            if not mine:
+                continue
             ev = torch.cuda.Event(); ev.record(main)
             with torch.cuda.stream(self._s_out):
                 self._s_out.wait_event(ev)
@@ -475,14 +491,15 @@ class ShardedIndexFlatL2:
         if ex is not None:                              # one barrier + one merge launch, then the results leave in four pieces
             main.wait_stream(self._s_out)
             slot = ex.finish(slot_id)
-            Dg = torch.empty((nq, k), dtype=torch.float32, device=dev)
-            Ig = torch.empty((nq, k), dtype=torch.int64, device=dev)
-            self._merge_slot(slot, d_bytes, nq, k, (Dg, Ig))
-            self._s_out.wait_stream(main)
-            with torch.cuda.stream(self._s_out):
-                Dt.copy_(Dg, non_blocking=pinned_out)
-                It.copy_(Ig, non_blocking=pinned_out)
-            Dg.record_stream(self._s_out); Ig.record_stream(self._s_out)
+            if mine:
+                Dg = torch.empty((nq, k), dtype=torch.float32, device=dev)
+                Ig = torch.empty((nq, k), dtype=torch.int64, device=dev)
+                self._merge_slot(slot, d_bytes, nq, k, (Dg, Ig))
+                self._s_out.wait_stream(main)
+                with torch.cuda.stream(self._s_out):
+                    Dt.copy_(Dg, non_blocking=pinned_out)
+                    It.copy_(Ig, non_blocking=pinned_out)
+                Dg.record_stream(self._s_out); Ig.record_stream(self._s_out)
         self._s_out.synchronize()
         xq_dev.record_stream(self._s_in)
         return D, I

@@ -42,6 +42,19 @@ def _worker(rank, world, port, shard, out_dir, metric="l2"):
             D4, I4 = ix.search(torch.from_numpy(xq).cuda(), 40)   # CUDA in, chunked: exchange through peer memory on a second stream
             assert np.array_equal(D4.cpu().numpy(), D) and np.array_equal(I4.cpu().numpy(), I)
             extra["peer_memory"] = np.array([0 if getattr(ix, "_peer", None) in (None, False) else 1])
+            for r in range(world):                                 # dst = r: lists travel to rank r alone, only r merges and copies out
+                D5, I5 = ix.search(xq, 40, dst=r)                  # host pipeline
+                D6, I6 = ix.search(torch.from_numpy(xq).cuda(), 40, dst=r)      # device-resident, chunked
+                if rank == r:
+                    assert np.array_equal(D5, D) and np.array_equal(I5, I)
+                    assert np.array_equal(D6.cpu().numpy(), D) and np.array_equal(I6.cpu().numpy(), I)
+                else:
+                    assert D5 is None and I5 is None and D6 is None and I6 is None
+            ix.PIPELINE_MIN_BYTES, ix.PIPELINE_CHUNK = 16 << 20, 18944
+            D7, I7 = ix.search(xq, 40, dst=0)                      # small batch: the generic path (NCCL all-gather, merge on dst only)
+            assert (np.array_equal(D7, D) and np.array_equal(I7, I)) if rank == 0 else (D7 is None and I7 is None)
+            D8, I8 = ix.search(xq, 40)                             # and everybody again afterwards (slot protocol intact)
+            assert np.array_equal(D8, D) and np.array_equal(I8, I)
         if shard == "query":                                       # results left partitioned by query: this rank's slice only
             Dl, Il = ix.search(xq, 40, gather=False)
             extra = dict(Dl=Dl, Il=Il)

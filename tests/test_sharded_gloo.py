@@ -79,6 +79,13 @@ def _worker(rank, world, port, shard, out_dir):
             assert ix.local.ntotal == sum(b - a for a, b in (shard_bounds(300, world)[rank], shard_bounds(201, world)[rank]))
         D, I = ix.search(xq, 12)
         D2, I2 = ix.search(torch.from_numpy(xq), 60)                     # k spanning shards, torch in -> torch out
+        if shard == "db":                                                # dst = r: only rank r receives the result (like dist.gather)
+            for r in range(world):
+                Dg, Ig = ix.search(xq, 12, dst=r)
+                if rank == r:
+                    assert np.array_equal(Dg, D) and np.array_equal(Ig, I)
+                else:
+                    assert Dg is None and Ig is None
         np.savez(Path(out_dir) / f"r{rank}.npz", D=D, I=I, D2=D2.numpy(), I2=I2.numpy())
     finally:
         dist.destroy_process_group()
