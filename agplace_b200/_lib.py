@@ -46,6 +46,9 @@ SIGNATURES = {
     "agp_recall_at_n": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "agp_radius_count": (c_int, [c_int, c_int64, c_int, c_void_p, c_int64, c_void_p, c_double, c_void_p]),
     "agp_radius_fill": (c_int, [c_int, c_int64, c_int, c_void_p, c_int64, c_void_p, c_double, c_void_p, c_void_p]),
+    "agp_plan_screen": (c_int, [c_int64, c_int64, c_int, c_int, c_int64, c_int, POINTER(c_int)]),
+    "agp_plan_screen_piece": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int)]),
+    "agp_plan_host_chunks": (c_int, [c_int64, c_int, c_int, c_int64, c_int, c_int, c_int, POINTER(c_int64), c_int]),
     "agp_last_error": (c_char_p, []),
     "agp_device_count": (c_int, []),
     "agp_kernel_launches": (c_int64, []),

@@ -909,58 +909,15 @@ static int search_screen(agp_index* ix, const float* xq_dev, int64_t nq, int k, 
         CKR(ensure(ix->dq, static_cast<size_t>(nqc) * sizeof(float)));
         CUtensorMap m_q;
         CKR(make_plane_map(&m_q, ix->q_hi.p, rows_pad, ix->d_pad, TC_BM, 2, ld));
-        // whole waves of pair tiles sweep the database unsplit; the last partial wave is split to fill every pair
+        // work decomposition (launch.h:plan_screen): whole waves unsplit, the remainder in equal ranges or balanced segments
+        const ScreenPlan pl = plan_screen(nqc, n, ix->d_pad, clusters, ix->l2_bytes, ix->screen_balanced, ix->screen_item_overhead);
         p.n_dbtiles = n_dbtiles;
-        p.n_full_items = (p.n_ptiles / clusters) * clusters;
-        const int rem_tiles = p.n_ptiles - p.n_full_items;
-        // remainder: database ranges per pair tile chosen to minimise waves x (range length + per-item overhead)
-        p.rem_splits = 1;
-        // per-item overhead in tiles (query tile load, pipeline fill / drain, the first compaction rounds of fresh lists):
-        // measured ~13 tiles at d = 512, < 12 at d = 256 (scripts/split_model_probe.py: with the earlier constant of 3 the
-        // model preferred many short items -- 16 pair tiles 0.69 -> 0.59 ms, 32 tiles 1.14 -> 0.98 ms, 63 tiles 1.91 -> 1.82 ms)
-        const double item_overhead = ix->screen_item_overhead > 0 ? ix->screen_item_overhead * 0.1 : std::min(14.0, 6.0 + ix->d_pad / 64.0);
-        if (rem_tiles > 0) {
-            double best_cost = 1e300;
-            const int max_s = std::min(n_dbtiles, 64);      // 2 lists per range, finalize handles up to 256 lists
-            for (int sp = 1; sp <= max_s; ++sp) {
-                const int64_t items = static_cast<int64_t>(rem_tiles) * sp;
-                const int64_t waves = (items + clusters - 1) / clusters;
-                const double cost = static_cast<double>(waves) * ((n_dbtiles + sp - 1) / sp + item_overhead);
-                if (cost < best_cost * 0.999) { best_cost = cost; p.rem_splits = sp; }
-            }
-        }
+        p.n_full_items = pl.n_full_items;
+        const int rem_tiles = pl.rem_tiles;
         p.rem_tiles = rem_tiles;
-        p.n_items = p.n_full_items + rem_tiles * p.rem_splits;
-        // Balanced alternative: equal ranges leave pairs idle whenever rem_tiles x splits is not a multiple of the pair count
-        // (63 pair tiles: one wave of 63 long items, 11 pairs idle).  Cut the remainder's whole (pair tile, database tile)
-        // space into one contiguous segment per pair instead -- segments cross pair-tile boundaries, so a pair runs W >= 1
-        // pieces of unequal length and a tile is covered by up to S ranges (its lists) -- when the model says it is cheaper
-        // AND the plane stays in L2: the pairs then sit at 74 different places of the plane instead of sweeping it together,
-        // so a plane larger than about half the L2 comes out of HBM once per pair tile (measured: 200 k x 64 rows, 51 MB plane,
-        // 32 / 63 pair tiles of queries 0.71 -> 0.58 / 1.22 -> 0.97 ms; 100 k x 512 rows, 115 MB, 63 tiles 1.70 -> 1.84 ms;
-        // 1 M x 128 rows, 384 MB, 63 tiles 4.40 -> 4.72 ms -- profiles/r2_split_cost_model.log).
-        p.balanced = 0;
-        const bool plane_in_l2 = static_cast<size_t>(n_dbtiles) * TC_BN * ld * 2 * 2 <= static_cast<size_t>(ix->l2_bytes);
-        if (rem_tiles > 0 && (ix->screen_balanced > 0 || (ix->screen_balanced < 0 && plane_in_l2))) {
-            const int64_t L = static_cast<int64_t>(rem_tiles) * n_dbtiles;
-            int W = 0, S = 0;
-            for (int c = 0; c < clusters; ++c) {
-                const int64_t b0 = sc_seg_begin(L, clusters, c), b1 = sc_seg_begin(L, clusters, c + 1);
-                if (b0 < b1) W = std::max(W, static_cast<int>((b1 - 1) / n_dbtiles - b0 / n_dbtiles) + 1);
-            }
-            for (int t = 0; t < rem_tiles; ++t) {
-                const int64_t tb = static_cast<int64_t>(t) * n_dbtiles;
-                S = std::max(S, sc_first_seg(L, clusters, tb + n_dbtiles - 1) - sc_first_seg(L, clusters, tb) + 1);
-            }
-            const double cost_bal = static_cast<double>((L + clusters - 1) / clusters) + W * item_overhead;
-            const int64_t items_u = static_cast<int64_t>(rem_tiles) * p.rem_splits;
-            const double cost_uni = static_cast<double>((items_u + clusters - 1) / clusters) * ((n_dbtiles + p.rem_splits - 1) / p.rem_splits + item_overhead);
-            if (L >= clusters && S <= 64 && (ix->screen_balanced > 0 || cost_bal < 0.97 * cost_uni)) {
-                p.balanced = 1;
-                p.rem_splits = S;
-                p.n_items = p.n_full_items + W * clusters;
-            }
-        }
+        p.rem_splits = pl.rem_splits;
+        p.balanced = pl.balanced;
+        p.n_items = pl.n_items;
         p.list_splits = p.rem_splits;
         p.q_resident = resident;
         p.n_stages = n_stages;
@@ -1692,53 +1649,41 @@ static int multi_merge(agp_index* ix, int64_t nq, int k, float* D_home, int64_t*
                         static_cast<const int64_t*>(ix->gat_i.p), static_cast<int64_t>(whole), by_id, nq, G, k, D_home, I_home, ix->ip, ix->stream);
 }
 
-// Host-buffer search as a three-stage pipeline (what the reference's call hands over: numpy arrays in, numpy arrays
-// out -- test.py:32).  The query batch is cut into chunks; for chunk c
-//     host memcpy into a pinned ring + H2D   (copy-in stream of every device that holds a shard)
-//  -> prep / screen / finish / fallback      (the compute stream(s), after the chunk's H2D event; multi-device: + gather + merge)
-//  -> D2H of (D, I) into the caller's pinned arrays or a pinned slot (stream s_out, after the chunk's compute event)
-// run concurrently for chunks c + 1, c and c - 1.  No stage needs a host synchronisation of the compute stream (the
-// screen's overflow fallback is device-side), so the host thread only ever blocks on a staging slot or a finished chunk.
-// Chunks are whole waves of pair tiles (74 x 256 queries on B200) when the batch is large; a mid-sized batch is cut
-// unevenly (small first chunk: the GPU starts early; large later chunks: the kernel stays efficient).
-// Also serves device-resident queries of a multi-device index (peer copies instead of H2D).
-static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, int k, float* D, int64_t* I, int out_mem_kind) {
-    const bool x_host = x_mem_kind != AGP_MEM_DEVICE, out_host = out_mem_kind != AGP_MEM_DEVICE;
-    const bool multi = !ix->shards.empty();
-    const int G = multi ? static_cast<int>(ix->shards.size()) : 1;
-    auto worker = [&](int g) { return multi ? ix->shards[g] : ix; };
-    const size_t row_in = static_cast<size_t>(ix->d) * sizeof(float);
+// Chunk schedule of the host-buffer search pipeline (pure host logic: search_host_pipelined uses it, agp_plan_host_chunks
+// exposes it to the CPU tests).  Returns the chunk boundaries, first 0, last nq.
+struct PipeKnobs { int cut[3]; int first, chunk, sched; };
+static std::vector<int64_t> plan_host_chunks(int64_t nq, int d, int d_pad, int k, int64_t ntotal_index, int64_t ntotal_worker, int num_sms,
+                                             bool x_host, bool out_host, bool multi, const PipeKnobs& kn) {
+    const size_t row_in = static_cast<size_t>(d) * sizeof(float);
     const size_t row_d = static_cast<size_t>(k) * sizeof(float), row_i = static_cast<size_t>(k) * sizeof(int64_t);
-    // ---- chunk schedule
     std::vector<int64_t> cuts;       // chunk c = [cuts[c], cuts[c + 1])
     cuts.push_back(0);
-    const int64_t wave = static_cast<int64_t>(worker(0)->num_sms / 2) * 2 * TC_BM;      // queries one wave of pair tiles covers
+    const int64_t wave = static_cast<int64_t>(num_sms / 2) * 2 * TC_BM;      // queries one wave of pair tiles covers
     const size_t moved = (x_host ? nq * row_in : 0) + (out_host ? nq * (row_d + row_i) : 0);
-    const bool batched_path = ix->ntotal > 0 && nq >= kMaxSmallNq;
-    if (ix->pipe_cut[0] > 0) {
-        for (int c : ix->pipe_cut)
+    const bool batched_path = ntotal_index > 0 && nq >= kMaxSmallNq;
+    if (kn.cut[0] > 0) {
+        for (int c : kn.cut)
             if (c > cuts.back() && c < nq) cuts.push_back(c);
-    } else if (ix->pipe_first > 0) {
-        if (ix->pipe_first < nq) cuts.push_back(ix->pipe_first);
-    } else if (ix->pipe_chunk > 0) {
-        for (int64_t a = ix->pipe_chunk; a < nq; a += ix->pipe_chunk) cuts.push_back(a);
+    } else if (kn.first > 0) {
+        if (kn.first < nq) cuts.push_back(kn.first);
+    } else if (kn.chunk > 0) {
+        for (int64_t a = kn.chunk; a < nq; a += kn.chunk) cuts.push_back(a);
     } else if (batched_path && (moved >= (size_t(4) << 20) || multi)) {
         // Chunk sizes are counted in pair tiles (256 queries) and taken from the sizes the screen kernel splits evenly over
         // the chip's 74 CTA pairs: 9 tiles x 8 database ranges, 18 x 4, 24 x 3, 37 x 2, 74 x 1 -- any other size leaves
         // pairs idle in its last wave of work items (cfg2, numpy in / out: [10|20|20|rest] tiles 3.41 ms, [18|24|37] 2.85 ms).
         const int64_t T = 2 * TC_BM;
         const int64_t tq = (nq + T - 1) / T;
-        const agp_index* w0 = worker(0);
-        const int64_t ndb = (w0->ntotal + TC_BN - 1) / TC_BN;
-        const int clusters = std::max(1, w0->num_sms / 2);
+        const int64_t ndb = (ntotal_worker + TC_BN - 1) / TC_BN;
+        const int clusters = std::max(1, num_sms / 2);
         // Which stage limits the pipeline?  Search time of the whole batch from the screen's own work decomposition (items of
         // ndb / sp tiles + ~10 tiles of per-item overhead, ~4 us per 256 x 256 x 528 tile incl. the epilogue's share) against the
         // host staging copy (~35 GB/s into the pinned ring).  Both are rough; they only pick the shape of the schedule.
-        const double t_tile = 4.0 * (w0->d_pad + 16) / 528.0;
+        const double t_tile = 4.0 * (d_pad + 16) / 528.0;
         const int64_t sp = std::max<int64_t>(1, std::min<int64_t>({clusters / std::max<int64_t>(tq, 1), ndb, 64}));
         const double t_search = t_tile * static_cast<double>((tq * sp + clusters - 1) / clusters) * (static_cast<double>(ndb) / sp + 10.6) + 30.0;
         const double t_copy = x_host ? static_cast<double>(nq) * row_in / 35e3 : 0.0;
-        if (ix->pipe_sched == 1) {                // the first round-2 schedule, kept for A/B runs
+        if (kn.sched == 1) {                // the first round-2 schedule, kept for A/B runs
             if (nq >= 3 * wave) {
                 for (int64_t a = wave; a < nq; a += wave) cuts.push_back(a);
             } else if (nq >= 2048) {
@@ -1775,6 +1720,30 @@ static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int 
         if (cuts.size() > 1 && cuts.back() >= nq) cuts.pop_back();
     }
     cuts.push_back(nq);
+    return cuts;
+}
+
+// Host-buffer search as a three-stage pipeline (what the reference's call hands over: numpy arrays in, numpy arrays
+// out -- test.py:32).  The query batch is cut into chunks; for chunk c
+//     host memcpy into a pinned ring + H2D   (copy-in stream of every device that holds a shard)
+//  -> prep / screen / finish / fallback      (the compute stream(s), after the chunk's H2D event; multi-device: + gather + merge)
+//  -> D2H of (D, I) into the caller's pinned arrays or a pinned slot (stream s_out, after the chunk's compute event)
+// run concurrently for chunks c + 1, c and c - 1.  No stage needs a host synchronisation of the compute stream (the
+// screen's overflow fallback is device-side), so the host thread only ever blocks on a staging slot or a finished chunk.
+// Chunks are whole waves of pair tiles (74 x 256 queries on B200) when the batch is large; a mid-sized batch is cut
+// unevenly (small first chunk: the GPU starts early; large later chunks: the kernel stays efficient).
+// Also serves device-resident queries of a multi-device index (peer copies instead of H2D).
+static int search_host_pipelined(agp_index* ix, int64_t nq, const float* x, int x_mem_kind, int k, float* D, int64_t* I, int out_mem_kind) {
+    const bool x_host = x_mem_kind != AGP_MEM_DEVICE, out_host = out_mem_kind != AGP_MEM_DEVICE;
+    const bool multi = !ix->shards.empty();
+    const int G = multi ? static_cast<int>(ix->shards.size()) : 1;
+    auto worker = [&](int g) { return multi ? ix->shards[g] : ix; };
+    const size_t row_in = static_cast<size_t>(ix->d) * sizeof(float);
+    const size_t row_d = static_cast<size_t>(k) * sizeof(float), row_i = static_cast<size_t>(k) * sizeof(int64_t);
+    // ---- chunk schedule (plan_host_chunks above)
+    const agp_index* w0 = worker(0);
+    const PipeKnobs pk = {{ix->pipe_cut[0], ix->pipe_cut[1], ix->pipe_cut[2]}, ix->pipe_first, ix->pipe_chunk, ix->pipe_sched};
+    const std::vector<int64_t> cuts = plan_host_chunks(nq, ix->d, w0->d_pad, k, ix->ntotal, w0->ntotal, w0->num_sms, x_host, out_host, multi, pk);
     const int n_chunks = static_cast<int>(cuts.size()) - 1;
 
     // ---- where the queries live on every device that computes
@@ -2148,6 +2117,34 @@ int agp_index_search_subset(agp_index* ix, int64_t nq, const float* x, int x_mem
     }
     CK(cudaStreamSynchronize(ix->stream));      // the candidate lists are host memory the caller may reuse
     return 0;
+}
+
+// ---- planning diagnostics: the host logic that decides HOW a search runs, callable without a GPU (tests/test_planning.py)
+int agp_plan_screen(int64_t nq, int64_t ntotal, int d, int num_sms, int64_t l2_bytes, int balanced_knob, int* plan) {
+    if (!plan || nq <= 0 || ntotal <= 0 || d <= 0 || num_sms < 2) return set_err(AGP_EINVAL, "agp_plan_screen: bad argument");
+    const int d_pad = static_cast<int>(round_up(d, TC_KPAD));
+    const ScreenPlan pl = plan_screen(nq, ntotal, d_pad, num_sms / 2, l2_bytes, balanced_knob, 0);
+    const int out[8] = {pl.n_ptiles, pl.n_dbtiles, pl.n_full_items, pl.rem_tiles, pl.rem_splits, pl.balanced, pl.n_items, pl.pieces};
+    std::memcpy(plan, out, sizeof(out));
+    return 0;
+}
+
+int agp_plan_screen_piece(int rem_tiles, int n_dbtiles, int n_segments, int piece, int segment, int* out) {
+    if (!out || rem_tiles <= 0 || n_dbtiles <= 0 || n_segments <= 0 || piece < 0 || segment < 0 || segment >= n_segments)
+        return set_err(AGP_EINVAL, "agp_plan_screen_piece: bad argument");
+    int T = 0, split = 0, t0 = 0, t1 = 0;
+    const bool live = sc_balanced_piece(rem_tiles, n_dbtiles, n_segments, piece, segment, &T, &split, &t0, &t1);
+    out[0] = T; out[1] = split; out[2] = t0; out[3] = t1;
+    return live ? 1 : 0;
+}
+
+int agp_plan_host_chunks(int64_t nq, int d, int k, int64_t ntotal, int num_sms, int x_host, int out_host, int64_t* cuts, int max_cuts) {
+    if (!cuts || nq <= 0 || d <= 0 || k <= 0 || ntotal < 0 || num_sms < 2 || max_cuts < 2) return set_err(AGP_EINVAL, "agp_plan_host_chunks: bad argument");
+    const PipeKnobs none = {{0, 0, 0}, 0, 0, 0};
+    const std::vector<int64_t> c = plan_host_chunks(nq, d, static_cast<int>(round_up(d, TC_KPAD)), k, ntotal, ntotal, num_sms, x_host != 0, out_host != 0, false, none);
+    if (static_cast<int>(c.size()) > max_cuts) return set_err(AGP_EINVAL, "agp_plan_host_chunks: %d boundaries do not fit max_cuts=%d", static_cast<int>(c.size()), max_cuts);
+    std::copy(c.begin(), c.end(), cuts);
+    return static_cast<int>(c.size());
 }
 
 int agp_best_of_lists(int device, int64_t nq, int d, const float* xq, const float* rows, const int64_t* offsets, float* best_d,

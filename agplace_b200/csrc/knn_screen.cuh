@@ -55,18 +55,9 @@ __device__ __forceinline__ ScItem sc_decode_item(const ScreenParams& p, int item
     } else if (p.balanced) {
         const int r = item - p.n_full_items;
         const int j = r / n_clusters, c = r - j * n_clusters;      // piece j of segment c (n_full_items is a multiple of n_clusters)
-        const int64_t L = static_cast<int64_t>(p.rem_tiles) * p.n_dbtiles;
-        const int64_t b0 = sc_seg_begin(L, n_clusters, c), b1 = sc_seg_begin(L, n_clusters, c + 1);
-        const int64_t T = b0 / p.n_dbtiles + j;
-        const int64_t tb = T * p.n_dbtiles;
-        it.pt = p.n_full_items + static_cast<int>(T);
-        it.split = 0;
-        it.t0 = it.t1 = 0;
-        if (b0 < b1 && tb < b1) {
-            it.t0 = static_cast<int>((b0 > tb ? b0 : tb) - tb);
-            it.t1 = static_cast<int>((b1 < tb + p.n_dbtiles ? b1 : tb + p.n_dbtiles) - tb);
-            it.split = c - sc_first_seg(L, n_clusters, tb);
-        }
+        int T;
+        sc_balanced_piece(p.rem_tiles, p.n_dbtiles, n_clusters, j, c, &T, &it.split, &it.t0, &it.t1);
+        it.pt = p.n_full_items + T;
         return it;
     } else {
         // range-major: the ranges of one pair tile are spread over successive waves, so every later range starts from

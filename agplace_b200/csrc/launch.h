@@ -50,6 +50,95 @@ __host__ __device__ inline int sc_first_seg(int64_t L, int n_seg, int64_t pos) {
     return static_cast<int>(((pos + 1) * n_seg + L - 1) / L) - 1;
 }
 
+// Piece j of segment c of the balanced remainder: pair tile T (relative to the remainder), its range index `split` among
+// the ranges that cover T, database tiles [t0, t1) of T.  Returns false for an empty piece (the segment touches fewer tiles).
+__host__ __device__ inline bool sc_balanced_piece(int rem_tiles, int n_dbtiles, int n_seg, int j, int c, int* T_out, int* split, int* t0, int* t1) {
+    const int64_t L = static_cast<int64_t>(rem_tiles) * n_dbtiles;
+    const int64_t b0 = sc_seg_begin(L, n_seg, c), b1 = sc_seg_begin(L, n_seg, c + 1);
+    const int64_t T = b0 / n_dbtiles + j;
+    const int64_t tb = T * n_dbtiles;
+    *T_out = static_cast<int>(T);
+    *split = 0;
+    *t0 = *t1 = 0;
+    if (!(b0 < b1 && tb < b1)) return false;
+    *t0 = static_cast<int>((b0 > tb ? b0 : tb) - tb);
+    *t1 = static_cast<int>((b1 < tb + n_dbtiles ? b1 : tb + n_dbtiles) - tb);
+    *split = c - sc_first_seg(L, n_seg, tb);
+    return true;
+}
+
+// Work decomposition of one screen launch (pure host logic; agpknn.cu:search_screen uses it, agp_plan_screen exposes it
+// to the CPU tests).  Whole waves of pair tiles sweep the database unsplit; the remainder is either split into equal
+// database ranges per pair tile -- rem_splits chosen to minimise waves x (range + per-item overhead) -- or, when the
+// model prefers it and the plane stays in (half of) the L2, balanced: one contiguous segment of the remainder's tile
+// space per pair (`pieces` = most pieces a segment has, rem_splits = most ranges that cover one pair tile).
+struct ScreenPlan {
+    int n_ptiles, n_dbtiles, n_full_items, rem_tiles, rem_splits, balanced, n_items, pieces;
+    double item_overhead;
+};
+inline ScreenPlan plan_screen(int64_t nq, int64_t n_rows, int d_pad, int clusters, int64_t l2_bytes, int knob_balanced, int knob_overhead) {
+    ScreenPlan pl;
+    pl.n_ptiles = static_cast<int>((nq + 2 * TC_BM - 1) / (2 * TC_BM));
+    pl.n_dbtiles = static_cast<int>((n_rows + TC_BN - 1) / TC_BN);
+    pl.n_full_items = (pl.n_ptiles / clusters) * clusters;
+    pl.rem_tiles = pl.n_ptiles - pl.n_full_items;
+    pl.rem_splits = 1;
+    pl.balanced = 0;
+    pl.pieces = 1;
+    const int n_dbtiles = pl.n_dbtiles, rem_tiles = pl.rem_tiles;
+    // per-item overhead in tiles (query tile load, pipeline fill / drain, the first compaction rounds of fresh lists):
+    // measured ~13 tiles at d = 512, < 12 at d = 256 (scripts/split_model_probe.py: with the earlier constant of 3 the
+    // model preferred many short items -- 16 pair tiles 0.69 -> 0.59 ms, 32 tiles 1.14 -> 0.98 ms, 63 tiles 1.91 -> 1.82 ms)
+    const double c0 = double(d_pad) / 64.0 + 6.0;
+    pl.item_overhead = knob_overhead > 0 ? knob_overhead * 0.1 : (c0 < 14.0 ? c0 : 14.0);
+    if (rem_tiles > 0) {
+        double best_cost = 1e300;
+        const int max_s = n_dbtiles < 64 ? n_dbtiles : 64;      // 2 lists per range, finalize handles up to 256 lists
+        for (int sp = 1; sp <= max_s; ++sp) {
+            const int64_t items = static_cast<int64_t>(rem_tiles) * sp;
+            const int64_t waves = (items + clusters - 1) / clusters;
+            const double cost = static_cast<double>(waves) * ((n_dbtiles + sp - 1) / sp + pl.item_overhead);
+            if (cost < best_cost * 0.999) { best_cost = cost; pl.rem_splits = sp; }
+        }
+    }
+    pl.n_items = pl.n_full_items + rem_tiles * pl.rem_splits;
+    // Balanced alternative: equal ranges leave pairs idle whenever rem_tiles x splits is not a multiple of the pair count
+    // (63 pair tiles: one wave of 63 long items, 11 pairs idle).  Cut the remainder's whole (pair tile, database tile)
+    // space into one contiguous segment per pair instead -- segments cross pair-tile boundaries, so a pair runs W >= 1
+    // pieces of unequal length and a tile is covered by up to S ranges (its lists) -- when the model says it is cheaper
+    // AND the plane stays in L2: the pairs then sit at 74 different places of the plane instead of sweeping it together,
+    // so a plane larger than about half the L2 comes out of HBM once per pair tile (measured: 200 k x 64 rows, 51 MB plane,
+    // 32 / 63 pair tiles of queries 0.71 -> 0.58 / 1.22 -> 0.97 ms; 100 k x 512 rows, 115 MB, 63 tiles 1.70 -> 1.84 ms;
+    // 1 M x 128 rows, 384 MB, 63 tiles 4.40 -> 4.72 ms -- profiles/r2_split_cost_model.log).
+    const bool plane_in_l2 = static_cast<int64_t>(n_dbtiles) * TC_BN * (d_pad + 64) * 2 * 2 <= l2_bytes;
+    if (rem_tiles > 0 && (knob_balanced > 0 || (knob_balanced < 0 && plane_in_l2))) {
+        const int64_t L = static_cast<int64_t>(rem_tiles) * n_dbtiles;
+        int W = 0, S = 0;
+        for (int c = 0; c < clusters; ++c) {
+            const int64_t b0 = sc_seg_begin(L, clusters, c), b1 = sc_seg_begin(L, clusters, c + 1);
+            if (b0 < b1) {
+                const int w = static_cast<int>((b1 - 1) / n_dbtiles - b0 / n_dbtiles) + 1;
+                W = w > W ? w : W;
+            }
+        }
+        for (int t = 0; t < rem_tiles; ++t) {
+            const int64_t tb = static_cast<int64_t>(t) * n_dbtiles;
+            const int sdiff = sc_first_seg(L, clusters, tb + n_dbtiles - 1) - sc_first_seg(L, clusters, tb) + 1;
+            S = sdiff > S ? sdiff : S;
+        }
+        const double cost_bal = static_cast<double>((L + clusters - 1) / clusters) + W * pl.item_overhead;
+        const int64_t items_u = static_cast<int64_t>(rem_tiles) * pl.rem_splits;
+        const double cost_uni = static_cast<double>((items_u + clusters - 1) / clusters) * ((n_dbtiles + pl.rem_splits - 1) / pl.rem_splits + pl.item_overhead);
+        if (L >= clusters && S <= 64 && (knob_balanced > 0 || cost_bal < 0.97 * cost_uni)) {
+            pl.balanced = 1;
+            pl.rem_splits = S;
+            pl.pieces = W;
+            pl.n_items = pl.n_full_items + W * clusters;
+        }
+    }
+    return pl;
+}
+
 // Single-pass certified screen (knn_screen.cuh): one fp16 plane per operand, CTA pairs (cta_group::2).
 struct ScreenParams {
     int nq;

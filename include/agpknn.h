@@ -219,6 +219,22 @@ AGP_API int agp_radius_count(int device, int64_t n_db, int dim, const double* db
 AGP_API int agp_radius_fill(int device, int64_t n_db, int dim, const double* db, int64_t nq, const double* q, double radius,
                             const int64_t* offsets, int64_t* ids);
 
+/* Planning diagnostics (no reference equivalent; host logic only -- these run WITHOUT a GPU, so the CPU test suite can
+ * check the decisions the product path takes; tests/test_planning.py):
+ *   agp_plan_screen       -> plan[8] = {pair tiles of 256 queries, database tiles of 256 rows, pair tiles swept unsplit (whole
+ *                            waves of num_sms / 2 CTA pairs), pair tiles in the remainder, ranges per remainder tile (= lists / 2
+ *                            per query), balanced (1: one contiguous segment of the remainder's tile space per CTA pair),
+ *                            work items, most pieces per segment} for one screen launch of nq queries against ntotal rows
+ *                            (balanced_knob: -1 automatic, 0 never, 1 always);
+ *   agp_plan_screen_piece -> out[4] = {remainder pair tile, range index within that tile, first database tile, end tile} of
+ *                            piece `piece` of segment `segment` of a balanced remainder; returns 1, or 0 for an empty piece;
+ *   agp_plan_host_chunks  -> the chunk boundaries (first 0, last nq) of agp_index_search's host pipeline for host queries /
+ *                            host results; returns their count. */
+AGP_API int agp_plan_screen(int64_t nq, int64_t ntotal, int d, int num_sms, int64_t l2_bytes, int balanced_knob, int* plan);
+AGP_API int agp_plan_screen_piece(int rem_tiles, int n_dbtiles, int n_segments, int piece, int segment, int* out);
+AGP_API int agp_plan_host_chunks(int64_t nq, int d, int k, int64_t ntotal, int num_sms, int x_host, int out_host, int64_t* cuts,
+                                 int max_cuts);
+
 /* Diagnostics. */
 AGP_API const char* agp_last_error(void);
 AGP_API int agp_device_count(void);
