@@ -5,7 +5,11 @@ ranks of a ``torch.distributed`` group, every rank searches the (replicated) que
 its shard with the single-GPU engine, the per-shard ``(D fp32, I int64 global)[nq, k]`` lists are
 exchanged with ONE all-gather of a packed byte buffer (NCCL over NVLink on GPUs, gloo in the CPU
 tests), and every rank runs the K4 merge kernel (``agp_merge_topk``) so all ranks return the same
-canonical (distance, id) ordered result as a single index would.
+canonical (distance, id) ordered result as a single index would.  ``search(..., dst=r)`` delivers
+the merged result to rank ``r`` only (the lists travel to that rank alone; the other ranks return
+``(None, None)``), which is what an evaluation that consumes the neighbours in one process needs.
+On GPUs the exchange of large batches goes through symmetric peer memory (copy-engine pushes per
+query chunk beside the next chunk's search, one signal barrier, one merge): ``_PeerExchange``.
 
 ``shard="query"`` is the zero-compute-redundancy alternative for databases that fit one GPU:
 every rank holds the whole database and searches only its slice of the queries; the all-gather
