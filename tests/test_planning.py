@@ -108,3 +108,25 @@ def test_host_chunk_schedules():
             c = chunks(nq, d, 10, n)
             assert c[0] == 0 and c[-1] == nq and all(a < b for a, b in zip(c, c[1:])), (nq, d, n, c)
             assert all(b % T == 0 for b in c[1:-1]), (nq, d, n, c)                        # cuts on pair-tile boundaries
+
+
+def test_random_shapes_keep_the_plan_invariants():
+    """Randomised shapes: the plan is internally consistent (what the kernel's item decoder and the finish kernel assume)."""
+    rng = np.random.default_rng(2026)
+    for _ in range(400):
+        nq = int(rng.integers(20, 70_000))
+        n = int(rng.choice([rng.integers(1, 3_000), rng.integers(3_000, 300_000), rng.integers(300_000, 12_000_000)]))
+        d = int(rng.choice([1, 7, 64, 200, 256, 512, 513, 1024, 4096]))
+        knob = int(rng.choice([-1, 0, 1]))
+        pl = plan_screen(nq, n, d, balanced=knob)
+        assert pl["n_ptiles"] == -(-nq // 256) and pl["n_dbtiles"] == -(-n // 256)
+        assert pl["n_full_items"] % C == 0 and pl["n_full_items"] + pl["rem_tiles"] == pl["n_ptiles"] and 0 <= pl["rem_tiles"] < C
+        assert 1 <= pl["rem_splits"] <= 64                                   # 2 lists per range, the finish handles 256 lists
+        if pl["balanced"]:
+            assert knob != 0 and pl["rem_tiles"] > 0 and pl["rem_tiles"] * pl["n_dbtiles"] >= C
+            assert pl["n_items"] == pl["n_full_items"] + pl["pieces"] * C    # piece-major: item = full items + piece * pairs + pair
+            live = sum(piece(pl["rem_tiles"], pl["n_dbtiles"], C, j, c)[0] for c in range(0, C, 9) for j in range(pl["pieces"]))
+            assert live >= len(range(0, C, 9))                               # every sampled segment has at least one live piece
+        else:
+            assert pl["n_items"] == pl["n_full_items"] + pl["rem_tiles"] * pl["rem_splits"]
+            assert pl["rem_splits"] <= max(1, pl["n_dbtiles"])
